@@ -1,0 +1,104 @@
+"""ctypes binding of libclane_b200.so (include/clane_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a device entry point is
+called without a CUDA device, this module raises.  The oracle under ``oracle/`` is never
+imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libclane_b200.so"
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_vp = C.c_void_p
+
+
+class Patience(C.Structure):
+    """Mirror of ``struct clane_patience`` (32 bytes)."""
+    _fields_ = [("minimum", C.c_float), ("patience", C.c_int32), ("tol", C.c_int32), ("sweeps", C.c_int32),
+                ("max_sweeps", C.c_int32), ("stop", C.c_int32), ("last_amount", C.c_float), ("reserved", C.c_int32)]
+
+
+class ClaneError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/clane_b200.h declaration by declaration
+SIGNATURES = {
+    "clane_version": (C.c_int, []),
+    "clane_error_string": (C.c_char_p, [C.c_int]),
+    "clane_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "clane_padded_ld": (C.c_int32, [C.c_int32]),
+    "clane_csr_from_edges": (C.c_int64, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "clane_row_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_i32p, c_vp, c_i32p]),
+    "clane_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "clane_edge_rows": (C.c_int, [c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
+    "clane_scores_cosine": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      C.c_size_t, c_vp]),
+    "clane_row_softmax": (C.c_int, [c_vp, c_vp, C.c_int32, c_vp, c_vp, c_vp]),
+    "clane_cosine_finalize": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
+    "clane_build_p_cosine": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                       c_vp, C.c_size_t, c_vp]),
+    "clane_sweep": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, c_vp, C.c_float,
+                              c_vp, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp, C.c_int32, c_vp, C.c_size_t, c_vp]),
+    "clane_l1_diff": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, C.c_size_t, c_vp]),
+    "clane_patience_reset": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp]),
+    "clane_session_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, c_vp, c_vp, C.c_int32]),
+    "clane_session_destroy": (C.c_int, [c_vp]),
+    "clane_session_set_z": (C.c_int, [c_vp, c_vp]),
+    "clane_session_get_z": (C.c_int, [c_vp, c_vp]),
+    "clane_session_build_p": (C.c_int, [c_vp, c_vp]),
+    "clane_session_propagate": (C.c_int, [c_vp, C.c_float, C.c_int32, C.c_int32, c_vp, C.c_int32, c_i32p]),
+    "clane_session_iterate": (C.c_int, [c_vp, C.c_float, C.c_int32, C.c_int32, c_f32p, c_vp, C.c_int32, c_i32p]),
+    "clane_session_sweeps": (C.c_int, [c_vp, C.c_float, C.c_int32, c_f32p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libclane_b200.so (built in-tree by clane_b200/build.py).  Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ClaneError(
+                f"{LIB_PATH} is missing: build it with `python -m clane_b200.build` "
+                "(nvcc, sm_100a).  clane_b200 has no CPU fallback.")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> int:
+    """Raise ClaneError for a non-zero return code of a C-ABI call."""
+    if code != 0:
+        msg = lib().clane_error_string(int(code)).decode()
+        raise ClaneError(f"{what or 'clane call'} failed: {msg} (code {code})")
+    return code
+
+
+def require_cuda():
+    """The hot path runs on a B200 or not at all."""
+    import torch
+    if not torch.cuda.is_available():
+        raise ClaneError("clane_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def ptr(t) -> int:
+    """data_ptr of a torch tensor (or 0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_handle() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,252 @@
+// ATen cascade sum on the device, bit-exact with torch.sum on one CPU thread
+// (reference call sites /root/reference/clane/similarity.py:37 and
+// /root/reference/clane/embedder.py:60,94).
+//
+// The CPU algorithm keeps 32 accumulators keyed by (flat index mod 32) -- exactly one warp --
+// and four cascade levels: level 0 adds `step` consecutive 32-element rows sequentially, is
+// added into level 1 and cleared; level 1 is dumped into level 2 every step^2 rows, level 2
+// into level 3 every step^3 rows.  Every complete level-k node therefore starts from zero and
+// is independent of its siblings: nodes are computed in parallel, and only the (short)
+// sequences of node sums are added in order.
+//
+//   k_cascade_l01   : one CTA per level-1 node (step^2 rows); warps own level-0 chunks
+//   k_cascade_finish: one CTA; levels 2 and 3, the ragged tails, the final lane combine,
+//                     and (optionally) the patience state machine of Embedder.propagate.
+#pragma once
+#include "common.cuh"
+
+namespace clane {
+
+// An element source maps a flat index of the UNPADDED array to NQ fp32 values.
+// prepare(t0) decomposes a chunk base once per warp; load(off) serves t0 + off.
+
+struct ElemAbsDiff {  // |a[t] - b[t]| over an [n, d] matrix stored with leading dimension ld
+    static constexpr int NQ = 1;
+    const float* a;
+    const float* b;
+    int d, ld;
+    struct Base { int64_t r0; uint32_t j0; };
+    __device__ __forceinline__ Base prepare(int64_t t0) const {
+        Base bs;
+        if (d == ld) { bs.r0 = t0; bs.j0 = 0; }
+        else { bs.r0 = t0 / d; bs.j0 = (uint32_t)(t0 - bs.r0 * d); }
+        return bs;
+    }
+    __device__ __forceinline__ void load(const Base& bs, uint32_t off, float* v) const {
+        size_t idx;
+        if (d == ld) idx = (size_t)bs.r0 + off;
+        else {
+            uint32_t jj = bs.j0 + off, q = jj / (uint32_t)d;
+            idx = (size_t)(bs.r0 + q) * ld + (jj - q * (uint32_t)d);
+        }
+        v[0] = fabsf(fsub(__ldg(a + idx), __ldg(b + idx)));
+    }
+};
+
+struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + j
+    static constexpr int NQ = 2;
+    const float* Z;
+    const int32_t* erow;
+    const int32_t* col;
+    int d, ld;
+    struct Base { int64_t e0; uint32_t j0; };
+    __device__ __forceinline__ Base prepare(int64_t t0) const {
+        Base bs;
+        bs.e0 = t0 / d;
+        bs.j0 = (uint32_t)(t0 - bs.e0 * d);
+        return bs;
+    }
+    __device__ __forceinline__ void load(const Base& bs, uint32_t off, float* v) const {
+        uint32_t jj = bs.j0 + off, q = jj / (uint32_t)d, j = jj - q * (uint32_t)d;
+        int64_t e = bs.e0 + q;
+        float x = __ldg(Z + (size_t)__ldg(erow + e) * ld + j);
+        float y = __ldg(Z + (size_t)__ldg(col + e) * ld + j);
+        v[0] = fmul(x, x);
+        v[1] = fmul(y, y);
+    }
+};
+
+constexpr int kCascadeWarps = 16;
+
+// workspace layout (floats): P1[(n1_nodes + 1)][NQ][32] | R0[NQ][32] | P2[(n2_full + 1)][NQ][32]
+template <class Elem>
+__global__ void __launch_bounds__(kCascadeWarps * 32)
+k_cascade_l01(Elem elem, CascadeShape sh, float* __restrict__ ws, const clane_patience* __restrict__ st) {
+    constexpr int NQ = Elem::NQ;
+    extern __shared__ float part[];  // [step][NQ][32]
+    if (st != nullptr && st->stop) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t node = blockIdx.x;
+    const int step = (int)sh.step;
+    const int64_t row0 = node * sh.node1_rows;
+    const bool full = node < sh.n1_full;
+    const int nchunks = full ? step : (int)sh.c_rem;
+    float* P1 = ws;
+    float* R0 = ws + (size_t)(sh.n1_nodes + 1) * 32 * NQ;
+
+    for (int ch = warp; ch < nchunks; ch += kCascadeWarps) {
+        const int64_t t0 = (row0 + (int64_t)ch * step) * 32;
+        typename Elem::Base bs = elem.prepare(t0);
+        float acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = 0.0f;
+        for (int r = 0; r < step; r += 8) {
+            float v[8][NQ];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) elem.load(bs, (uint32_t)((r + u) * 32 + lane), v[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] = fadd(acc[q], v[u][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) part[(ch * NQ + q) * 32 + lane] = acc[q];
+    }
+    if (!full && sh.r_rem > 0 && warp == (int)(sh.c_rem % kCascadeWarps)) {
+        // leftover rows of the last, incomplete chunk: they stay in acc[0] to the end
+        const int64_t t0 = (row0 + sh.c_rem * step) * 32;
+        typename Elem::Base bs = elem.prepare(t0);
+        float acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = 0.0f;
+        for (int r = 0; r < (int)sh.r_rem; ++r) {
+            float v[NQ];
+            elem.load(bs, (uint32_t)(r * 32 + lane), v);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] = fadd(acc[q], v[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) R0[q * 32 + lane] = acc[q];
+    }
+    __syncthreads();
+    if (warp < NQ) {
+        const int q = warp;
+        float acc = 0.0f;
+        for (int ch = 0; ch < nchunks; ++ch) acc = fadd(acc, part[(ch * NQ + q) * 32 + lane]);
+        P1[((size_t)node * NQ + q) * 32 + lane] = acc;
+    }
+}
+
+// Advance the patience state machine of Embedder.propagate (embedder.py:98-108).
+__device__ __forceinline__ void patience_step(clane_patience* st, float amount, float* log, int log_cap) {
+    const int sweep = st->sweeps;
+    if (log != nullptr && sweep < log_cap) log[sweep] = amount;
+    st->last_amount = amount;
+    st->sweeps = sweep + 1;
+    if (st->minimum > amount) { st->patience = st->tol; st->minimum = amount; }
+    else st->patience -= 1;
+    if (st->patience == 0) st->stop = 1;
+    if (st->max_sweeps > 0 && st->sweeps >= st->max_sweeps) st->stop = 1;
+}
+
+template <class Elem>
+__global__ void __launch_bounds__(1024)
+k_cascade_finish(Elem elem, CascadeShape sh, float* __restrict__ ws, float* __restrict__ out,
+                 clane_patience* __restrict__ st, float* __restrict__ log, int log_cap) {
+    constexpr int NQ = Elem::NQ;
+    __shared__ float lanes[NQ][32];
+    if (st != nullptr && st->stop) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int step = (int)sh.step;
+    const float* P1 = ws;
+    const float* R0 = ws + (size_t)(sh.n1_nodes + 1) * 32 * NQ;
+    float* P2 = ws + (size_t)(sh.n1_nodes + 2) * 32 * NQ;
+
+    // level 2: complete nodes in parallel (one warp per (node, quantity)); slot n2_full holds
+    // the sum of the complete level-1 nodes after the last complete level-2 node.
+    const int64_t n2_slots = sh.n2_full + 1;
+    for (int64_t item = warp; item < n2_slots * NQ; item += nwarps) {
+        const int64_t k = item / NQ;
+        const int q = (int)(item - k * NQ);
+        const int64_t first = k * step;
+        const int cnt = (k < sh.n2_full) ? step : (int)(sh.n1_full - first);
+        float acc = 0.0f;
+        int i = 0;
+        for (; i + 8 <= cnt; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = P1[((size_t)(first + i + u) * NQ + q) * 32 + lane];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+        }
+        for (; i < cnt; ++i) acc = fadd(acc, P1[((size_t)(first + i) * NQ + q) * 32 + lane]);
+        P2[((size_t)k * NQ + q) * 32 + lane] = acc;
+    }
+    __syncthreads();
+    if (warp < NQ) {
+        const int q = warp;
+        float acc3 = 0.0f;
+        for (int64_t k = 0; k < sh.n2_full; ++k) acc3 = fadd(acc3, P2[((size_t)k * NQ + q) * 32 + lane]);
+        float a = 0.0f;
+        if (sh.ni > 0) {
+            const float r0 = (sh.rem_rows > 0 && sh.r_rem > 0) ? R0[q * 32 + lane] : 0.0f;
+            const float r1 = (sh.rem_rows > 0) ? P1[((size_t)sh.n1_full * NQ + q) * 32 + lane] : 0.0f;
+            const float r2 = P2[((size_t)sh.n2_full * NQ + q) * 32 + lane];
+            a = fadd(r0, r1);
+            a = fadd(a, r2);
+            a = fadd(a, acc3);
+        }
+        lanes[q][lane] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float result[NQ];
+        if (sh.n < 8) {
+            // ATen's scalar path: four interleaved accumulators
+            float x[8][NQ];
+            typename Elem::Base bs = elem.prepare(0);
+            for (int i = 0; i < (int)sh.n; ++i) elem.load(bs, (uint32_t)i, x[i]);
+            for (int q = 0; q < NQ; ++q) {
+                float p4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                const int qd = (int)sh.n / 4;
+                for (int i = 0; i < qd; ++i)
+                    for (int k = 0; k < 4; ++k) p4[k] = fadd(p4[k], x[4 * i + k][q]);
+                for (int i = 4 * qd; i < (int)sh.n; ++i) p4[0] = fadd(p4[0], x[i][q]);
+                for (int k = 1; k < 4; ++k) p4[0] = fadd(p4[0], p4[k]);
+                result[q] = p4[0];
+            }
+        } else {
+            // leftover 8-vectors -> ILP row 0; combine the four ILP rows; scalar tail; 8 lanes
+            typename Elem::Base bs = elem.prepare(sh.ni * 32);
+            const int nleft = (int)(sh.nv - sh.ni * 4);
+            for (int v = 0; v < nleft; ++v)
+                for (int l = 0; l < 8; ++l) {
+                    float x[NQ];
+                    elem.load(bs, (uint32_t)(v * 8 + l), x);
+                    for (int q = 0; q < NQ; ++q) lanes[q][l] = fadd(lanes[q][l], x[q]);
+                }
+            const int ntail = (int)(sh.n - sh.nv * 8);
+            float tail[8][NQ];
+            for (int k = 0; k < ntail; ++k) elem.load(bs, (uint32_t)(nleft * 8 + k), tail[k]);
+            for (int q = 0; q < NQ; ++q) {
+                for (int k = 1; k < 4; ++k)
+                    for (int l = 0; l < 8; ++l) lanes[q][l] = fadd(lanes[q][l], lanes[q][k * 8 + l]);
+                float o = 0.0f;
+                for (int k = 0; k < ntail; ++k) o = fadd(o, tail[k][q]);
+                for (int l = 0; l < 8; ++l) o = fadd(o, lanes[q][l]);
+                result[q] = o;
+            }
+        }
+        if (out != nullptr)
+            for (int q = 0; q < NQ; ++q) out[q] = result[q];
+        if (st != nullptr) patience_step(st, result[0], log, log_cap);
+    }
+}
+
+// enqueue a full cascade sum of n elements; result(s) -> out[0..NQ)
+template <class Elem>
+inline int cascade_launch(const Elem& elem, int64_t n, float* ws, size_t ws_bytes, float* out, clane_patience* st,
+                          float* log, int log_cap, cudaStream_t s) {
+    CascadeShape sh = cascade_shape(n);
+    if (ws_bytes < cascade_ws_floats(n, Elem::NQ) * sizeof(float)) return CLANE_EWORKSPACE;
+    if (sh.n1_nodes > 0) {
+        const size_t smem = (size_t)sh.step * Elem::NQ * 32 * sizeof(float);
+        k_cascade_l01<Elem><<<(unsigned)sh.n1_nodes, kCascadeWarps * 32, smem, s>>>(elem, sh, ws, st);
+        CLANE_LAUNCH_CHECK();
+    }
+    k_cascade_finish<Elem><<<1, 1024, 0, s>>>(elem, sh, ws, out, st, log, log_cap);
+    CLANE_LAUNCH_CHECK();
+    return CLANE_OK;
+}
+
+}  // namespace clane

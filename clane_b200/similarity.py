@@ -1,0 +1,77 @@
+"""Similarity plugins -- drop-in for ``clane.similarity`` (/root/reference/clane/similarity.py).
+
+The registry is this module's namespace: the CLI resolves ``similarity.method`` with
+``getattr(similarity, name)`` and constructs it with ``**kwargs`` (__main__.py:39-48).
+Plugins are called as ``sim(v1, v2)`` with two ``[E, d]`` (or 1-D) tensors and return ``[E]``.
+
+Built-in plugins carry ``_clane_kernel``; ``Graph.build_P`` dispatches on it to the fused
+per-edge score + neighbour-softmax kernels.  A user plugin without the tag is still honoured
+(its scores are computed by the plugin on device tensors, the softmax stays in CUDA).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class Similarity:
+    def is_trainable(self):
+        return isinstance(self, nn.Module)
+
+
+class CosineSimilarity(Similarity):
+    """``<v1_e, v2_e> / (||V1||_F * ||V2||_F)`` -- the reference divides every per-pair dot by
+    the two GLOBAL Frobenius norms of the batched inputs (similarity.py:37); it is the true
+    cosine only for a single pair.  That behaviour is reproduced, not fixed."""
+
+    _clane_kernel = "cosine"
+
+    def __init__(self, **kwargs) -> None:
+        super(CosineSimilarity, self).__init__()
+
+    def __call__(self, v1: torch.Tensor, v2: torch.Tensor) -> torch.Tensor:
+        if v1.dim() == 1:
+            v1 = v1.unsqueeze(0)
+        if v2.dim() == 1:
+            v2 = v2.unsqueeze(0)
+        if v1.shape != v2.shape or v1.dim() != 2:
+            raise RuntimeError(f"CosineSimilarity expects two [E, d] batches, got {tuple(v1.shape)} and {tuple(v2.shape)}")
+        dev = _lib.require_cuda()
+        L = _lib.lib()
+        out_device = v1.device
+        e, d = int(v1.shape[0]), int(v1.shape[1])
+        ld = int(L.clane_padded_ld(d))
+        # pair i is the edge  i -> e + i  of a bipartite helper graph over the stacked rows
+        Z = torch.zeros([2 * e, ld], dtype=torch.float32, device=dev)
+        Z[:e, :d] = v1.to(device=dev, dtype=torch.float32)
+        Z[e:, :d] = v2.to(device=dev, dtype=torch.float32)
+        erow = torch.arange(0, e, dtype=torch.int32, device=dev)
+        col = torch.arange(e, 2 * e, dtype=torch.int32, device=dev)
+        out = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+        norms2 = torch.empty(2, dtype=torch.float32, device=dev)
+        ws_bytes = int(L.clane_workspace_bytes(2 * e, e, d))
+        ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=dev)
+        s = _lib.stream_handle()
+        _lib.check(L.clane_scores_cosine(Z.data_ptr(), ld, d, 2 * e, e, erow.data_ptr(), col.data_ptr(), out.data_ptr(),
+                                         norms2.data_ptr(), ws.data_ptr(), ws_bytes, s), "clane_scores_cosine")
+        _lib.check(L.clane_cosine_finalize(out.data_ptr(), norms2.data_ptr(), e, out.data_ptr(), s),
+                   "clane_cosine_finalize")
+        return out[:e].to(out_device)
+
+
+class AsymmertricSimilarity(nn.Module, Similarity):
+    """Trainable bilinear score (similarity.py:40-57).  Only reachable through the reference's
+    IterativeEmbedder, which is broken upstream: kept as a plain torch module
+    so the registry stays complete; it runs on whatever device its inputs are on."""
+
+    def __init__(self, n_dim: int, **kwargs) -> None:
+        super(AsymmertricSimilarity, self).__init__()
+        self.Phi_src = nn.Linear(n_dim, n_dim, bias=False)
+        self.Phi_dst = nn.Linear(n_dim, n_dim, bias=False)
+        nn.init.xavier_normal_(self.Phi_src.weight)
+        nn.init.xavier_normal_(self.Phi_dst.weight)
+
+    def forward(self, z_src: torch.Tensor, z_dst: torch.Tensor) -> torch.Tensor:
+        return self.Phi_src(z_src).unsqueeze(-2).matmul(self.Phi_dst(z_dst).unsqueeze(-1)).squeeze()

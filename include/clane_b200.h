@@ -1,0 +1,169 @@
+/*
+ * clane_b200.h -- C-ABI of the B200-native CLANE hot path (libclane_b200.so).
+ *
+ * The reference (helloybz/CLANE) has no FFI boundary of its own: its hot path is Python
+ * calling PyTorch-CPU.  Each entry point below therefore names the
+ * reference *Python* interface it replaces; the Python host package (clane_b200/, mirroring
+ * clane/graph.py, clane/similarity.py, clane/embedder.py) binds them with ctypes
+ * (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - "d_" arguments are DEVICE pointers, "h_" arguments are HOST pointers;
+ *   - every function returns 0 on success, a positive cudaError_t value, or a negative
+ *     CLANE_E* code; nothing throws across the boundary (clane_error_string decodes both);
+ *   - kernels are enqueued on the given stream (a cudaStream_t passed as void*) and do not
+ *     synchronise unless the comment says so;
+ *   - feature matrices are row-major fp32 [n, ld] with ld = clane_padded_ld(d) (rows 16-byte
+ *     aligned); the pad columns must be zero and stay zero;
+ *   - rowptr / col are int32 CSR of the coalesced (sorted-unique) adjacency, rows = sources.
+ *
+ * All floating-point work reproduces the reference's fp32 rounding sequence bit for bit
+ * (SURVEY.md section 7.1): the kernels are compiled with -fmad=false and use explicit
+ * __fmaf_rn / __fmul_rn / __fadd_rn where the reference's CPU kernels fuse or do not fuse.
+ */
+#ifndef CLANE_B200_H
+#define CLANE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define CLANE_OK 0
+#define CLANE_EINVAL (-1)      /* bad argument (null pointer, negative size, d < 1 ...) */
+#define CLANE_ERANGE (-2)      /* edge endpoint outside [0, n) / size exceeds int32 indexing */
+#define CLANE_EWORKSPACE (-3)  /* workspace too small (see clane_workspace_bytes) */
+#define CLANE_ENODEVICE (-4)   /* no CUDA device / not an sm_100 class device */
+
+typedef void* clane_stream_t;  /* cudaStream_t */
+
+/* Device-resident patience ("tolerence") state machine of Embedder.propagate
+ * (/root/reference/clane/embedder.py:78-79, :98-108).  32 bytes. */
+typedef struct clane_patience {
+    float   minimum;      /* running strict minimum of the per-sweep L1 amount (starts +inf) */
+    int32_t patience;     /* current counter; reset to tol on a strict new minimum, else -1   */
+    int32_t tol;          /* initial value ("tolerence")                                       */
+    int32_t sweeps;       /* sweeps completed in this propagate() call                         */
+    int32_t max_sweeps;   /* 0 = unbounded                                                     */
+    int32_t stop;         /* 1 once patience hit 0 (or max_sweeps reached): later sweeps no-op */
+    float   last_amount;  /* L1 amount of the last completed sweep                             */
+    int32_t reserved;
+} clane_patience;
+
+/* ---- library / device ---------------------------------------------------------------- */
+int         clane_version(void);
+const char* clane_error_string(int code);
+/* sm count and compute capability of the current device */
+int         clane_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* leading dimension used for [n, d] fp32 matrices: d rounded up to a multiple of 4 */
+int32_t     clane_padded_ld(int32_t d);
+
+/* ---- graph build (host side) --------------------------------------------------------- */
+/* Replaces Graph.A (/root/reference/clane/graph.py:104-110): coalesce the raw edge list --
+ * sort by (src, dst), merge duplicates, keep self-loops.  h_rowptr has n+1 entries, h_col
+ * capacity e_raw.  Returns the number of coalesced edges E >= 0, or CLANE_E* (< 0). */
+int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t e_raw, int64_t n,
+                             int32_t* h_rowptr, int32_t* h_col);
+
+/* Degree-binned row schedule (north_star: "degree-sorted row blocks").  Rows without
+ * out-neighbours are dropped (embedder.py:88-89: they are never updated); rows with degree
+ * > hub_threshold go to h_hub_rows (degree-descending); the others to h_light_order
+ * (degree > 32 first, degree-descending, then the rest in ascending id order).
+ * Both outputs have capacity n. */
+int clane_row_schedule(const int32_t* h_rowptr, int32_t n, int32_t hub_threshold,
+                       int32_t* h_light_order, int32_t* n_light, int32_t* h_hub_rows, int32_t* n_hub);
+
+/* ---- device kernels ------------------------------------------------------------------ */
+/* bytes of scratch the calls below need for a graph of n rows, e coalesced edges, width d */
+size_t clane_workspace_bytes(int64_t n, int64_t e, int32_t d);
+
+/* d_erow[e] = source row of coalesced edge e (the first row of A.indices(), graph.py:119) */
+int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_erow, clane_stream_t s);
+
+/* CosineSimilarity.__call__ on (Z[src], Z[dst]) (/root/reference/clane/similarity.py:26-37),
+ * split where the reference has its global reduction:
+ *   d_dots[e]   = <z_src(e), z_dst(e)>   sequential over the feature index (mul+add for
+ *                 d < 400, fma for d >= 400 -- the ATen / MKL switch);
+ *   d_norms2[0] = sum(Z[src]^2), d_norms2[1] = sum(Z[dst]^2) over the flattened [E*d]
+ *                 gathered arrays in ATen cascade-sum order. */
+int clane_scores_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e,
+                        const int32_t* d_erow, const int32_t* d_col, float* d_dots, float* d_norms2,
+                        void* d_ws, size_t ws_bytes, clane_stream_t s);
+
+/* The per-source softmax of Graph.build_P (/root/reference/clane/graph.py:122-123) for all
+ * rows at once.  If d_norms2 != NULL each score is first divided by
+ * fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))) (similarity.py:37); pass NULL for scores
+ * produced by a user plugin.  d_w may alias d_scores. */
+int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t n, const int32_t* d_rowptr,
+                      float* d_w, clane_stream_t s);
+
+/* The final division of CosineSimilarity.__call__ (similarity.py:37) for standalone plugin
+ * calls: d_out[i] = d_dots[i] / fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))).  May alias. */
+int clane_cosine_finalize(const float* d_dots, const float* d_norms2, int64_t e, float* d_out, clane_stream_t s);
+
+/* Graph.build_P with CosineSimilarity (graph.py:118-128): clane_scores_cosine + clane_row_softmax. */
+int clane_build_p_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e,
+                         const int32_t* d_rowptr, const int32_t* d_erow, const int32_t* d_col,
+                         float* d_w, float* d_norms2, void* d_ws, size_t ws_bytes, clane_stream_t s);
+
+/* One Jacobi sweep of Embedder.propagate (/root/reference/clane/embedder.py:84-94) over the
+ * scheduled rows:  Znext[v] = X[v] + gamma * (w_v @ Zcur[nbrs(v)]) in oneMKL's summation
+ * order, gamma*(.) and x+(.) rounded separately; rows outside the schedule are not touched
+ * (Znext must already hold their value).  If d_amount != NULL the L1 change
+ * sum|Znext - Zcur| over the flattened [n*d] array (ATen cascade order, embedder.py:94) is
+ * written to d_amount[0]; if d_state != NULL the patience state machine (embedder.py:98-108)
+ * is advanced on the device, d_amounts_log[sweep] (capacity log_cap) receives the amount, and
+ * the whole call is a no-op once d_state->stop is set. */
+int clane_sweep(const float* d_X, const float* d_Zcur, float* d_Znext, int32_t ld, int32_t d, int32_t n,
+                const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma,
+                const int32_t* d_light_order, int32_t n_light, const int32_t* d_hub_rows, int32_t n_hub,
+                float* d_amount, clane_patience* d_state, float* d_amounts_log, int32_t log_cap,
+                void* d_ws, size_t ws_bytes, clane_stream_t s);
+
+/* (Za - Zb).abs().sum() over the flattened [n*d] array in ATen cascade order
+ * (/root/reference/clane/embedder.py:60).  Result in d_out[0]. */
+int clane_l1_diff(const float* d_Za, const float* d_Zb, int32_t ld, int32_t d, int32_t n, float* d_out,
+                  void* d_ws, size_t ws_bytes, clane_stream_t s);
+
+/* Reset the device patience state for a new propagate() call (embedder.py:78-79). */
+int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweeps, clane_stream_t s);
+
+/* ---- host-buffer session API (pure C consumers; bench e2e) ---------------------------- */
+typedef struct clane_session clane_session;
+
+/* Upload a coalesced CSR graph and features from HOST memory.  h_X is [n, d] (unpadded).
+ * Z starts as a copy of X (graph.py:18-19). */
+int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
+                         const int32_t* h_col, const float* h_X, int32_t hub_threshold);
+int clane_session_destroy(clane_session* s);
+/* replace Z (Graph.set_Z, graph.py:136-138) / read Z (Graph.Z, graph.py:130-134); [n, d] host */
+int clane_session_set_z(clane_session* s, const float* h_Z);
+int clane_session_get_z(clane_session* s, float* h_Z);
+/* Graph.build_P values for the current Z -> h_w[e] (optional, may be NULL) */
+int clane_session_build_p(clane_session* s, float* h_w);
+/* One propagate() call (embedder.py:71-108): build_P once, sweep until the patience counter
+ * reaches 0 (or max_sweeps > 0 sweeps).  h_amounts (capacity cap, may be NULL) receives the
+ * per-sweep L1 amounts; *sweeps the count.  Synchronous. */
+int clane_session_propagate(clane_session* s, float gamma, int32_t tol, int32_t max_sweeps,
+                            float* h_amounts, int32_t cap, int32_t* sweeps);
+/* Embedder.iterate() (embedder.py:56-69).  min_amount is the running minimum kept on the
+ * Embedder object (embedder.py:43), in/out.  h_sweeps_per_call capacity cap. */
+int clane_session_iterate(clane_session* s, float gamma, int32_t tol, int32_t max_outer, float* min_amount,
+                          int32_t* h_sweeps_per_call, int32_t cap, int32_t* outer);
+/* exactly `sweeps` sweeps with the current P (bench inner loop; no patience); returns the
+ * last L1 amount in *h_amount (may be NULL).  Synchronous. */
+int clane_session_sweeps(clane_session* s, float gamma, int32_t sweeps, float* h_amount);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLANE_B200_H */

@@ -1,0 +1,270 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the CPU
+oracle and the golden vectors of the real reference.
+
+Bars (BASELINE.json north_star): CSR / neighbour indexing bit-exact; identical iteration
+counts; final embeddings within max-abs 1e-5 / rel 1e-4 in fp32.  Because the kernels
+reproduce the reference's rounding sequence, every comparison below is also asserted
+BIT-EXACT (np.array_equal), which implies the stated tolerance.
+"""
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from clane_b200 import _lib, similarity, synth
+from clane_b200.embedder import Embedder
+from clane_b200.graph import Graph
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+REF_CASES = sorted(p.stem for p in GOLD.glob("ref_*.npz"))
+ATOL, RTOL = 1e-5, 1e-4      # north_star tolerance for final embeddings
+
+
+def within_tolerance(a, b):
+    return bool(np.all(np.abs(a - b) <= ATOL + RTOL * np.abs(b)))
+
+
+def gpu_l1(a: np.ndarray, b: np.ndarray) -> np.float32:
+    """clane_l1_diff on two [n, d] host arrays."""
+    L = _lib.lib()
+    n, d = a.shape
+    ld = L.clane_padded_ld(d)
+    A = torch.zeros([n, ld], device="cuda"); A[:, :d] = torch.from_numpy(a).cuda()
+    B = torch.zeros([n, ld], device="cuda"); B[:, :d] = torch.from_numpy(b).cuda()
+    out = torch.zeros(1, device="cuda")
+    wsb = L.clane_workspace_bytes(n, 0, d)
+    ws = torch.zeros(wsb // 4 + 1, device="cuda")
+    _lib.check(L.clane_l1_diff(A.data_ptr(), B.data_ptr(), ld, d, n, out.data_ptr(), ws.data_ptr(), wsb,
+                               _lib.stream_handle()))
+    return np.float32(out.cpu().numpy()[0])
+
+
+# ---- cascade sum (embedder.py:60,94) -------------------------------------------------------------
+@pytest.mark.parametrize("n,d", [(1, 1), (1, 3), (1, 7), (2, 4), (3, 5), (17, 2), (34, 2), (100, 8), (64, 128),
+                                 (257, 100), (40, 1433), (3000, 500), (8192, 128), (8193, 128), (70001, 31),
+                                 (169343, 128)])
+def test_l1_cascade_bit_exact(n, d):
+    rng = np.random.default_rng(n * 31 + d)
+    a = rng.standard_normal((n, d)).astype(np.float32)
+    b = rng.standard_normal((n, d)).astype(np.float32)
+    assert gpu_l1(a, b) == O.l1_diff(a, b)
+    assert gpu_l1(a, a) == np.float32(0)
+
+
+def test_l1_cascade_matches_torch_sum_live():
+    torch.set_num_threads(1)
+    if torch.backends.cpu.get_cpu_capability() != "AVX512":
+        pytest.skip("torch.sum order was characterised on the AVX-512 host")
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((5000, 128)).astype(np.float32)
+    b = rng.standard_normal((5000, 128)).astype(np.float32)
+    assert gpu_l1(a, b) == (torch.from_numpy(a) - torch.from_numpy(b)).abs().sum().item()
+
+
+# ---- build_P: scores + norms + softmax (graph.py:118-128, similarity.py:26-37) ----------------------
+@pytest.mark.parametrize("case", REF_CASES)
+def test_build_p_bit_exact_with_reference(case):
+    G = np.load(GOLD / f"{case}.npz")
+    g = Graph.from_arrays(int(G["n"]), G["raw_src"], G["raw_dst"], G["X"])
+    P = g.build_P(similarity.CosineSimilarity())
+    assert np.array_equal(P.indices().numpy(), G["P0_indices"])
+    assert np.array_equal(P.values().numpy(), G["P0_values"])
+    rs = P.to_dense().sum(1)
+    assert abs(rs.max().item() - 1) < 1e-3 and abs(rs.min().item()) < 1e-3 or int(G["n"]) == len(set(G["A_indices"][0]))
+
+
+def test_row_softmax_generic_plugin_and_long_rows():
+    rng = np.random.default_rng(11)
+    ks = [1, 2, 7, 15, 16, 17, 31, 32, 33, 48, 100, 255, 1000, 8234, 0, 5]
+    rowptr = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    for scale in (0.01, 1.0, 30.0):
+        s = (rng.standard_normal(rowptr[-1]) * scale).astype(np.float32)
+        want = O.softmax_rows(s, rowptr.astype(np.int64))
+        L = _lib.lib()
+        sd, rp = torch.from_numpy(s).cuda(), torch.from_numpy(rowptr).cuda()
+        w = torch.zeros_like(sd)
+        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, len(ks), rp.data_ptr(), w.data_ptr(), _lib.stream_handle()))
+        assert np.array_equal(w.cpu().numpy(), want)
+        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, len(ks), rp.data_ptr(), sd.data_ptr(), _lib.stream_handle()))
+        assert np.array_equal(sd.cpu().numpy(), want)      # in place
+
+
+def test_user_plugin_is_honoured():
+    G = np.load(GOLD / "ref_hub60_d20.npz")
+    g = Graph.from_arrays(int(G["n"]), G["raw_src"], G["raw_dst"], G["X"])
+
+    class Dot:
+        def __call__(self, a, b):
+            assert a.is_cuda and a.shape == b.shape
+            return (a * b).sum(1)
+
+    P = g.build_P(Dot())
+    rows, cols = G["A_indices"]
+    s = (torch.from_numpy(G["X"]).cuda()[rows] * torch.from_numpy(G["X"]).cuda()[cols]).sum(1).cpu().numpy()
+    want = O.softmax_rows(s, G["nbr_ptr"])
+    assert np.array_equal(P.values().numpy(), want)
+
+
+# ---- similarity plugin KATs (reference tests/test_similarity.py) -----------------------------------
+def test_cosine_plugin_known_answers():
+    cos = similarity.CosineSimilarity()
+    v = torch.Tensor([1, 2, 3])
+    assert abs(cos(v, v.clone()).item() - 1) < 1e-4
+    assert abs(cos(torch.Tensor([0, 1]), torch.Tensor([1, 0])).item()) < 1e-4
+    assert abs(cos(v, v.neg()).item() + 1) < 1e-4
+    a, b = torch.rand(10), torch.rand(10)
+    assert torch.equal(cos(a, b), cos(b, a))
+    assert cos(torch.rand(4, 16), torch.rand(4, 16)).size() == torch.Size([4])
+
+
+@pytest.mark.parametrize("e,d", [(1, 3), (64, 2), (64, 128), (50, 399), (50, 400), (30, 1433)])
+def test_cosine_plugin_batched_quirk_bit_exact(e, d):
+    rng = np.random.default_rng(e * 7 + d)
+    a = rng.standard_normal((e, d)).astype(np.float32)
+    b = rng.standard_normal((e, d)).astype(np.float32)
+    rowptr = np.concatenate([np.arange(e + 1), np.full(e, e)]).astype(np.int64)
+    dots, s1, s2 = O.scores_raw(np.concatenate([a, b]), rowptr, np.arange(e, 2 * e, dtype=np.int32))
+    want = (dots / np.float32(np.sqrt(s1, dtype=np.float32) * np.sqrt(s2, dtype=np.float32))).astype(np.float32)
+    got = similarity.CosineSimilarity()(torch.from_numpy(a), torch.from_numpy(b))
+    assert not got.is_cuda and np.array_equal(got.numpy(), want)
+
+
+# ---- sweep (embedder.py:84-94) ---------------------------------------------------------------------
+@pytest.mark.parametrize("case", REF_CASES)
+def test_first_sweep_bit_exact_with_reference(case):
+    G = np.load(GOLD / f"{case}.npz")
+    g = Graph.from_arrays(int(G["n"]), G["raw_src"], G["raw_dst"], G["X"])
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=float(G["gamma"]),
+                 tolerence=int(G["tol"]))
+    e.verbose = False
+    e.propagate(max_sweeps=1)
+    assert np.array_equal(g.Z.numpy(), G["Z_after_first_sweep"])
+    assert e.amounts_per_call[0][0] == G["amounts"][0]
+
+
+# ---- full iterate: counts + embeddings ---------------------------------------------------------------
+@pytest.mark.parametrize("case", REF_CASES)
+def test_iterate_matches_reference(case, capsys):
+    G = np.load(GOLD / f"{case}.npz")
+    g = Graph.from_arrays(int(G["n"]), G["raw_src"], G["raw_dst"], G["X"])
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=float(G["gamma"]),
+                 tolerence=int(G["tol"]), save_history=(case == "ref_toy_d2"))
+    e.iterate()
+    assert e.sweeps_per_call == G["sweeps_per_call"].tolist()            # identical iteration counts
+    assert np.array_equal(np.concatenate(e.amounts_per_call), G["amounts"])
+    Z = g.Z.numpy()
+    assert within_tolerance(Z, G["Z_final"])                             # the stated bar
+    assert np.array_equal(Z, G["Z_final"])                               # and in fact bit-exact
+    lines = capsys.readouterr().out.strip().split("\n")
+    assert len(lines) == len(G["amounts"])
+    assert [int(l.split()[-1]) for l in lines] == G["counters"].tolist() # the printed patience counters
+    if e.save_history:
+        assert [len(h) for h in e.history["Z"]] == G["sweeps_per_call"].tolist()
+        assert np.array_equal(e.history["Z"][0][0].numpy(), G["Z_after_first_sweep"])
+        assert np.array_equal(e.history["Z"][0][-1].numpy(), G["Z_after_first_call"])
+
+
+def test_session_api_host_buffers():
+    """The pure-C host-buffer API (what bench.py's e2e leg and a C consumer call)."""
+    G = np.load(GOLD / "ref_n120_d128.npz")
+    n, d = int(G["n"]), int(G["d"])
+    L = _lib.lib()
+    g = Graph.from_arrays(n, G["raw_src"], G["raw_dst"], G["X"])
+    X = np.ascontiguousarray(G["X"])
+    h = ctypes.c_void_p()
+    _lib.check(L.clane_session_create(ctypes.byref(h), n, g._nnz, d, g._rowptr.ctypes.data, g._col.ctypes.data,
+                                      X.ctypes.data, 0))
+    try:
+        w = np.zeros(g._nnz, np.float32)
+        _lib.check(L.clane_session_build_p(h, w.ctypes.data))
+        assert np.array_equal(w, G["P0_values"])
+        spc = np.zeros(64, np.int32)
+        outer = ctypes.c_int32()
+        mn = ctypes.c_float(float("inf"))
+        _lib.check(L.clane_session_iterate(h, ctypes.c_float(float(G["gamma"])), int(G["tol"]), 0, ctypes.byref(mn),
+                                           spc.ctypes.data, 64, ctypes.byref(outer)))
+        assert spc[:outer.value].tolist() == G["sweeps_per_call"].tolist()
+        Z = np.zeros((n, d), np.float32)
+        _lib.check(L.clane_session_get_z(h, Z.ctypes.data))
+        assert np.array_equal(Z, G["Z_final"])
+        assert mn.value == G["outer_amounts"].min()
+        # set_Z + bounded propagate
+        _lib.check(L.clane_session_set_z(h, X.ctypes.data))
+        am = np.zeros(8, np.float32)
+        k = ctypes.c_int32()
+        _lib.check(L.clane_session_propagate(h, ctypes.c_float(float(G["gamma"])), int(G["tol"]), 5, am.ctypes.data, 8,
+                                             ctypes.byref(k)))
+        assert k.value == 5 and np.array_equal(am[:5], G["amounts"][:5])
+    finally:
+        L.clane_session_destroy(h)
+
+
+# ---- the reference's own tests, restated against the new package -------------------------------------
+def test_reference_test_graph_build_p(data_root):
+    g = Graph(data_root=data_root, embedding_dim=16)
+    P = g.build_P(similarity.CosineSimilarity()).to_dense()
+    assert P.shape == (34, 34)
+    assert abs(P.sum(1).max().item() - 1) < 1e-3 and abs(P.sum(1).min().item()) < 1e-3
+
+
+def test_reference_test_embedder(data_root):
+    g = Graph(data_root=data_root, embedding_dim=16)
+    e = Embedder(graph=g, similarity_measure=similarity.CosineSimilarity(), gamma=0.74, device=torch.device("cpu"))
+    e.verbose = False
+    e.iterate()
+    assert (g.Z - g.X).abs().sum() != 0
+
+
+def test_reference_test_cli(tmp_path, data_root, monkeypatch):
+    from clane_b200.__main__ import embedding, get_parser
+    G = np.load(GOLD / "ref_toy_d2.npz")
+    torch.manual_seed(int(G["seed"]))
+    out = tmp_path / "test_output"
+    args = get_parser().parse_args(["--data_root", str(data_root), "--output_root", str(out), "--config_file",
+                                    str(ROOT / "tests" / "config.yaml"), "--save_history"])
+    embedding(args)
+    Z0 = np.load(out / "0" / "Z_0.npy")
+    Z = np.load(out / "Z.npy")
+    assert Z0.shape == (34, 2) and Z.shape == (34, 2) and Z.dtype == np.float32
+    assert np.array_equal(Z0, G["Z_after_first_sweep"]) and np.array_equal(Z, G["Z_final"])   # config 1, end to end
+    assert sorted(p.name for p in out.iterdir() if p.is_dir()) == sorted(str(i) for i in range(len(G["sweeps_per_call"])))
+
+
+# ---- BASELINE shapes: oracle comparison at sizes it finishes in seconds, properties at full size ------
+@pytest.mark.parametrize("shape,scale", [("cora", 1.0), ("pubmed", 1.0), ("arxiv", 1.0)])
+def test_baseline_shapes_against_oracle(shape, scale):
+    n, src, dst, X = synth.make_graph(shape, seed=0, scale=scale)
+    g = Graph.from_arrays(n, src, dst, X)
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    assert np.array_equal(g._rowptr, rowptr) and np.array_equal(g._col, col)
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=10)
+    e.verbose = False
+    e.propagate(max_sweeps=3)
+    Zo, amounts, w = O.propagate(X, X, rowptr.astype(np.int64), col, 0.76, 10, max_sweeps=3)
+    S = g._device_state()
+    assert np.array_equal(S.w[:S.e].cpu().numpy(), w)                    # P bit-exact
+    assert np.array_equal(e.amounts_per_call[0], amounts)                # L1 amounts bit-exact
+    Z = g.Z.numpy()
+    assert within_tolerance(Z, Zo) and np.array_equal(Z, Zo)
+    sinks = np.diff(rowptr) == 0
+    assert np.array_equal(Z[sinks], X[sinks])                            # embedder.py:88-89
+
+
+def test_full_convergence_cora_shape_counts_match_oracle():
+    n, src, dst, X = synth.make_graph("cora", seed=0)
+    g = Graph.from_arrays(n, src, dst, X)
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=10)
+    e.verbose = False
+    e.iterate()
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    Zo, spc, _ = O.iterate(X, rowptr, col, 0.76, 10)
+    assert e.sweeps_per_call == spc.tolist()
+    assert np.array_equal(g.Z.numpy(), Zo)

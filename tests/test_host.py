@@ -1,0 +1,233 @@
+"""Host-side logic (no GPU): loader semantics of graph.py, CSR build, row schedule, the C-ABI
+surface, CLI parser and plugin registry.  Known answers come from the reference's own tests
+(tests/test_graph.py) and from the golden files."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from clane_b200 import _lib, similarity
+from clane_b200.__main__ import get_parser
+from clane_b200.graph import Graph
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+def write_graph(root, ids, edges, X=None):
+    root.mkdir(parents=True, exist_ok=True)
+    (root / "V").write_text("\n".join(ids))
+    (root / "E").write_text("\n".join(f"{a}\t{b}" for a, b in edges))
+    if X is not None:
+        np.save(root / "C.npy", X)
+
+
+# ---- reference tests/test_graph.py restated ---------------------------------------------------
+def test_load_zachary(data_root):
+    g = Graph(data_root=data_root, embedding_dim=16)
+    assert len(g.vertex_ids) == 34 and len(g.V) == 34 and len(g.E) == 78 and len(g) == 34
+    for v in g.V:
+        assert isinstance(v.x, torch.Tensor) and v.x.shape[-1] == 16
+
+
+def test_build_A_and_neighbour_kat(data_root):
+    g = Graph(data_root=data_root, embedding_dim=16)
+    assert g.A.shape[0] == 34 and g.A.shape[1] == 34
+    assert g.get_nbrs(33).tolist() == [8, 9, 13, 14, 15, 18, 19, 20, 22, 23, 26, 27, 28, 29, 30, 31, 32]
+    for v in g.V:
+        nb = g.get_nbrs(v.idx)
+        assert nb.dim() == 1 and nb.dtype == torch.int64
+
+
+def test_same_random_features_as_reference(data_root):
+    G = np.load(GOLD / "ref_toy_d2.npz")
+    torch.manual_seed(int(G["seed"]))
+    g = Graph(data_root=data_root, embedding_dim=2)
+    assert np.array_equal(g.X.numpy(), G["X"])          # graph.py:56: identical torch.normal call
+    assert np.array_equal(g.A.indices().numpy(), G["A_indices"])
+
+
+# ---- loader semantics (graph.py:44-45, :73-81) ---------------------------------------------------
+def test_first_occurrence_wins_and_coalesce(tmp_path):
+    ids = ["a", "b", "a", "c"]                            # duplicate id: index() finds position 0
+    write_graph(tmp_path, ids, [("a", "b"), ("c", "a"), ("a", "b"), ("b", "b"), ("c", "c")],
+                np.zeros((4, 3), np.float32))
+    g = Graph(tmp_path, 3)
+    assert len(g) == 4 and len(g.E) == 5                 # raw count keeps duplicates and self-loops
+    assert g.A._nnz() == 4                               # (0,1) merged; self-loops kept
+    assert g.A.values().tolist() == [2.0, 1.0, 1.0, 1.0]
+    assert g.get_nbrs(0).tolist() == [1] and g.get_nbrs(1).tolist() == [1]
+    assert g.get_nbrs(2).tolist() == [] and g.get_nbrs(3).tolist() == [0, 3]
+    assert g.V[0].outgoing_indices == [1, 1] and g.V[1].incoming_indices == [0, 0, 1]
+    assert g.E[1].src.idx == 3 and g.E[1].dst.idx == 0
+
+
+def test_loader_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        Graph(tmp_path / "missing", 4)
+    write_graph(tmp_path / "noE", ["a", "b"], [("a", "b")])
+    (tmp_path / "noE" / "E").unlink()
+    with pytest.raises(FileNotFoundError):
+        Graph(tmp_path / "noE", 4)
+    write_graph(tmp_path / "bad", ["a", "b"], [("a", "b")])
+    (tmp_path / "bad" / "E").write_text("a b")           # no tab
+    with pytest.raises(ValueError):
+        Graph(tmp_path / "bad", 4)
+    (tmp_path / "bad" / "E").write_text("a\tb\tc")       # two tabs
+    with pytest.raises(ValueError):
+        Graph(tmp_path / "bad", 4)
+    (tmp_path / "bad" / "E").write_text("a\tzzz")        # unknown id
+    with pytest.raises(ValueError):
+        Graph(tmp_path / "bad", 4)
+    (tmp_path / "bad" / "E").write_text("")              # empty file: the reference fails to unpack
+    with pytest.raises(ValueError):
+        Graph(tmp_path / "bad", 4)
+
+
+def test_feature_file_precedence(tmp_path):
+    X = np.arange(6, dtype=np.float32).reshape(2, 3)
+    write_graph(tmp_path, ["a", "b"], [("a", "b")], X)
+    g = Graph(tmp_path, 99)                              # C.npy wins over embedding_dim (graph.py:51)
+    assert np.array_equal(g.X.numpy(), X) and g.V[1].x.tolist() == [3.0, 4.0, 5.0]
+    (tmp_path / "C.npy").unlink()
+    torch.save(torch.from_numpy(X) + 1, tmp_path / "C.pt")
+    assert np.array_equal(Graph(tmp_path, 99).X.numpy(), X + 1)
+
+
+def test_dataset_protocol(data_root):
+    g = Graph(data_root=data_root, embedding_dim=4)
+    assert g[5] == 5
+    g.dispense_pair = True
+    idx, other, is_nbr = g[33]
+    assert idx == 33 and 0 <= other < 34 and isinstance(is_nbr, bool)
+
+
+# ---- CSR build and schedule (C-ABI host functions) vs the oracle / golden --------------------------
+@pytest.mark.parametrize("case", sorted(p.stem for p in GOLD.glob("ref_*.npz")))
+def test_csr_bit_exact_with_reference(case):
+    G = np.load(GOLD / f"{case}.npz")
+    n = int(G["n"])
+    g = Graph.from_arrays(n, G["raw_src"], G["raw_dst"], G["X"])
+    rows = np.repeat(np.arange(n), np.diff(g._rowptr))
+    assert np.array_equal(rows, G["A_indices"][0]) and np.array_equal(g._col, G["A_indices"][1])
+    assert g._rowptr.dtype == np.int32 and g._col.dtype == np.int32
+    for v in (0, n // 2, n - 1):
+        a, b = G["nbr_ptr"][v], G["nbr_ptr"][v + 1]
+        assert g.get_nbrs(v).tolist() == G["nbr_idx"][a:b].tolist()
+
+
+def test_csr_random_multigraph_vs_oracle():
+    rng = np.random.default_rng(7)
+    n, e = 500, 20000
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    assert np.array_equal(g._rowptr, rowptr) and np.array_equal(g._col, col)
+    assert g._nnz == len(np.unique(src * n + dst))
+
+
+def test_csr_rejects_out_of_range():
+    L = _lib.lib()
+    src, dst = np.array([0, 5], np.int64), np.array([1, 1], np.int64)
+    rowptr, col = np.zeros(4, np.int32), np.zeros(2, np.int32)
+    assert L.clane_csr_from_edges(src.ctypes.data, dst.ctypes.data, 2, 3, rowptr.ctypes.data, col.ctypes.data) == -2
+    with pytest.raises(_lib.ClaneError):
+        Graph.from_arrays(3, src, dst, np.zeros((3, 2), np.float32))
+
+
+def test_row_schedule_bins():
+    rng = np.random.default_rng(3)
+    n = 2000
+    deg = np.minimum((rng.pareto(1.0, n) * 3).astype(np.int64), n - 1)
+    deg[:5] = [0, 1, 33, 257, 1500]
+    src = np.repeat(np.arange(n), deg)
+    dst = np.concatenate([rng.permutation(n)[:k] for k in deg])
+    g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
+    k = np.diff(g._rowptr)
+    assert sorted(g._hubs.tolist()) == np.nonzero(k > 256)[0].tolist()
+    assert sorted(g._light.tolist()) == np.nonzero((k > 0) & (k <= 256))[0].tolist()   # sinks dropped
+    assert np.all(np.diff(k[g._hubs]) <= 0)                                              # longest first
+    nmed = int(((k > 32) & (k <= 256)).sum())
+    assert np.all(k[g._light[:nmed]] > 32) and np.all(np.diff(k[g._light[:nmed]]) <= 0)
+    assert np.all(np.diff(g._light[nmed:]) > 0)                                          # the rest in id order
+
+
+# ---- C-ABI surface -------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "clane_b200.h").read_text()
+    declared = set(re.findall(r"\b(clane_[a-z0-9_]+)\s*\(", header))
+    declared -= {"clane_patience"}
+    assert len(declared) >= 20
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in clane_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes binding out of sync with the header"
+    assert ctypes.sizeof(_lib.Patience) == 32
+    assert _lib.lib().clane_version() >= 100
+    assert _lib.lib().clane_padded_ld(1433) == 1436 and _lib.lib().clane_padded_ld(128) == 128
+    assert b"invalid argument" in _lib.lib().clane_error_string(-1)
+
+
+def test_kernel_entry_points_reject_bad_arguments_without_a_device():
+    L = _lib.lib()
+    assert L.clane_sweep(0, 0, 0, 4, 4, 1, 0, 0, 0, 0.5, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert L.clane_row_softmax(0, 0, 1, 0, 0, 0) == -1
+    assert L.clane_scores_cosine(0, 4, 4, 1, 1, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert L.clane_workspace_bytes(10, 10, 0) == 0 and L.clane_workspace_bytes(169343, 1166243, 128) > 0
+
+
+def test_no_cpu_fallback_without_cuda(data_root):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    g = Graph(data_root=data_root, embedding_dim=4)
+    with pytest.raises(_lib.ClaneError):
+        g.build_P(similarity.CosineSimilarity())
+    with pytest.raises(_lib.ClaneError):
+        similarity.CosineSimilarity()(torch.ones(3), torch.ones(3))
+
+
+def test_product_never_imports_the_oracle():
+    for py in (ROOT / "clane_b200").rglob("*.py"):
+        text = py.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, py
+    for src in (ROOT / "clane_b200" / "csrc").iterdir():
+        assert "oracle" not in src.read_text().lower(), src
+
+
+# ---- CLI / registry ------------------------------------------------------------------------------
+def test_cli_flags_match_reference():
+    args = get_parser().parse_args(["--data_root", "a", "--output_root", "b", "--config_file", "c.yaml",
+                                    "--save_history", "--num_workers", "3", "--gpu"])
+    assert args.data_root == Path("a") and args.output_root == Path("b") and args.config_file == Path("c.yaml")
+    assert args.save_history and args.gpu and args.num_workers == 3
+    d = get_parser().parse_args([])
+    assert d.num_workers == 0 and not d.save_history and not d.gpu
+
+
+def test_plugin_registry():
+    assert hasattr(similarity, "CosineSimilarity") and hasattr(similarity, "AsymmertricSimilarity")
+    sim = similarity.CosineSimilarity(foo="bar")        # kwargs swallowed (tests/config.yaml:6-7)
+    assert not sim.is_trainable() and not hasattr(sim, "parameters")
+    assert similarity.AsymmertricSimilarity(n_dim=2).is_trainable()
+    from clane.graph import Graph as AliasGraph         # the drop-in alias package
+    from clane.embedder import Embedder, IterativeEmbedder  # noqa: F401
+    from clane.__main__ import embedding, get_parser as gp  # noqa: F401
+    assert AliasGraph is Graph
+
+
+def test_cli_missing_config_and_unknown_method(tmp_path, data_root):
+    from clane_b200.__main__ import embedding
+    args = get_parser().parse_args(["--data_root", str(data_root), "--output_root", str(tmp_path / "o"),
+                                    "--config_file", str(tmp_path / "nope.yaml")])
+    with pytest.raises(FileNotFoundError):
+        embedding(args)
+    cfg = tmp_path / "c.yaml"
+    cfg.write_text('graph:\n  embedding_dim: 2\nsimilarity:\n  method: "Nope"\n  kwargs: {}\nembedder: {}\n')
+    args = get_parser().parse_args(["--data_root", str(data_root), "--output_root", str(tmp_path / "o"),
+                                    "--config_file", str(cfg)])
+    with pytest.raises(AttributeError, match="Given similarity method Nope not found."):
+        embedding(args)
