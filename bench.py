@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec per sweep of the CLANE embedding update on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|products|pubmed|cora]
+    python bench.py --impl reference ...      # the CPU arm: oracle port on all host threads
+
+A "step" is one Jacobi sweep of Embedder.propagate (/root/reference/clane/embedder.py:84-108)
+over the whole graph with P frozen: the fused gather-SpMM + residual kernel(s), the exact
+(ATen-cascade-order) L1 change and the device-side patience update.  Inputs are resident in
+HBM when the timed region starts; `e2e` is the same metric through the host-buffer C-ABI
+(clane_session_*) with every host<->device copy inside the timed region.
+
+One JSON line is printed by rank 0.  See DESIGN.md section "Measurement" for the definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "edges_per_sec_per_sweep"
+UNIT = "edges/s"
+GAMMA = 0.76
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="clane_b200", choices=["clane_b200", "reference"])
+    ap.add_argument("--workload", default=None, help="cora | pubmed | arxiv | products (default: arxiv at 1 GPU, products at >1)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line invalid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-converge", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args) -> str:
+    if args.workload:
+        return args.workload
+    return "arxiv" if args.gpus == 1 else "products"
+
+
+def sweep_bytes(n, e, d):
+    """Algorithmic bytes of one sweep: X, Z_cur read, Z_next written, col, w, rowptr."""
+    return 12 * d * n + 8 * e + 4 * (n + 1)
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sweeps(n, src, dst, X, budget_s: float, min_sweeps: int, max_sweeps: int):
+    """Time whole CPU sweeps (row update + exact L1 change) of the oracle with all host threads."""
+    from oracle import oracle as O
+    threads = O.max_threads()
+    O.set_threads(threads)
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    w = O.build_p(X, rowptr, col)
+    Z = X
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < max_sweeps and (len(times) < min_sweeps or time.perf_counter() < t_end):
+        t0 = time.perf_counter()
+        Zn = O.sweep(X, Z, rowptr, col, w, GAMMA)
+        O.l1_diff(Zn, Z)
+        times.append(time.perf_counter() - t0)
+        Z = Zn
+    return len(col), threads, times
+
+
+def run_reference(args):
+    from clane_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = workload_name(args)
+    n, src, dst, X = synth.make_graph(name, seed=0, scale=args.scale)
+    d = X.shape[1]
+    # each step = one CPU sweep of the same workload (bounded: the whole run ends within minutes)
+    e, threads, times = cpu_sweeps(n, src, dst, X, budget_s=1e9, min_sweeps=args.warmup + args.steps,
+                                   max_sweeps=args.warmup + args.steps)
+    timed = times[args.warmup:]
+    ms = 1e3 * float(np.mean(timed))
+    value = e / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}-shape synthetic", "nodes": n, "edges": e, "dim": d, "gamma": GAMMA,
+                   "similarity": "CosineSimilarity", "scale": args.scale},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(timed)} whole sweeps (row update + exact L1) of the {name}-shape graph, "
+                                   f"oracle C port of the reference's path, OpenMP over rows"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference itself is pure Python (O(N*E) per sweep, ~210 edges/s at Cora shape, BASELINE.md) "
+                "and cannot run this shape; this arm times its bit-exact C restatement on all host threads",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from clane_b200 import _lib, similarity, synth
+    from clane_b200.embedder import Embedder
+    from clane_b200.graph import Graph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = workload_name(args)
+    n, src, dst, X = synth.make_graph(name, seed=0, scale=args.scale)
+    d = X.shape[1]
+    g = Graph.from_arrays(n, src, dst, X)
+    e = g._nnz
+    L = _lib.lib()
+    sim = similarity.CosineSimilarity()
+    emb = Embedder(g, sim, device=torch.device("cuda", local_rank), gamma=GAMMA, tolerence=10)
+    emb.verbose = False
+
+    if world > 1:
+        from clane_b200 import dist as cdist
+        runner = cdist.ShardedSweeper(g, sim, GAMMA)
+    else:
+        runner = None
+
+    S = g._device_state()
+    g._build_P_device(sim)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    gamma = ctypes.c_float(float(np.float32(GAMMA)))
+    launches_per_step = [0]
+
+    def one_step(i, with_l1=True):
+        if runner is not None:
+            launches_per_step[0] = runner.sweep(with_l1)
+            return
+        a, b = S.Z[(S.cur + i) & 1], S.Z[(S.cur + i + 1) & 1]
+        _lib.check(L.clane_sweep(S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.ld, S.d, S.n, S.rowptr.data_ptr(),
+                                 S.col.data_ptr(), S.w.data_ptr(), gamma, S.light.data_ptr(), S.n_light,
+                                 S.hubs.data_ptr(), S.n_hub, S.amount.data_ptr() if with_l1 else 0, 0, 0, 0,
+                                 S.ws.data_ptr(), S.ws_bytes, sh))
+        launches_per_step[0] = (1 if S.n_light else 0) + (1 if S.n_hub else 0) + (2 if with_l1 else 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(steps, with_l1):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for i in range(steps):
+            one_step(i, with_l1)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms = timed_loop(args.steps, True)                 # the metric: whole steps
+    kernel_ms = timed_loop(args.steps, False)               # the dominant kernel alone (roofline)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = e / (ms_per_step * 1e-3)
+    amount = float(S.amount.cpu()[0]) if runner is None else runner.last_amount()
+
+    peak, peak_src = measured_peak()
+    kern_ms = kernel_ms / args.steps
+    bytes_sweep = sweep_bytes(n, e, d)
+    achieved = bytes_sweep / world / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}-shape synthetic", "nodes": n, "edges": e, "dim": d, "gamma": GAMMA,
+                   "similarity": "CosineSimilarity", "scale": args.scale,
+                   "parallelism": "single GPU" if world == 1 else f"rows partitioned by contiguous id over {world} GPUs, "
+                                                                  "NCCL all-gather of Z per sweep",
+                   "l2": f"no flush: working set {(3 * n * d * 4 + 8 * e) / 1e6:.0f} MB exceeds the 126 MB L2"
+                         if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",
+                   "step": "sweep kernel(s) + exact L1 cascade + finish; P frozen"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(name), "kernel": "k_sweep_rows", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": bytes_sweep / world, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "whole_step_gbs": bytes_sweep / world / (ms_per_step * 1e-3) / 1e9},
+        "clocks": clocks,
+        "gpu_launches": launches_per_step[0] * args.steps,
+        "last_amount": amount,
+    }
+
+    if rank == 0 and world == 1:
+        line["e2e"] = e2e_session(L, g, X, n, e, d, args.steps)
+    elif rank == 0:
+        line["e2e"] = runner.e2e(args.steps) if hasattr(runner, "e2e") else None
+
+    if not args.no_converge and world == 1:
+        g.set_Z(g.X)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        emb.iterate()
+        torch.cuda.synchronize()
+        line["time_to_converge"] = {"seconds": time.perf_counter() - t0, "outer_iterations": len(emb.sweeps_per_call),
+                                    "sweeps": int(sum(emb.sweeps_per_call)), "sweeps_per_call": emb.sweeps_per_call,
+                                    "tolerence": 10}
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        ce, threads, times = cpu_sweeps(n, src, dst, X, budget_s=12.0, min_sweeps=3, max_sweeps=200)
+        timed = times[1:]
+        line["cpu_baseline"] = {"value": ce / float(np.mean(timed)), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{len(timed)} whole sweeps of the same {name}-shape graph (after 1 warm-up), "
+                                          "oracle C port, OpenMP over rows"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_session(L, g, X, n, e, d, steps):
+    """Same metric through the host-buffer C-ABI: upload CSR + X from pinned host memory, build P,
+    `steps` sweeps with the patience state machine live (its amounts come back), download Z."""
+    import torch
+    from clane_b200 import _lib
+    Xp = torch.from_numpy(np.ascontiguousarray(X)).pin_memory()
+    rp = torch.from_numpy(g._rowptr).pin_memory()
+    cp = torch.from_numpy(g._col).pin_memory()
+    Zout = torch.empty([n, d], dtype=torch.float32).pin_memory()
+    amounts = torch.empty(steps, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        h = ctypes.c_void_p()
+        _lib.check(L.clane_session_create(ctypes.byref(h), n, e, d, rp.data_ptr(), cp.data_ptr(), Xp.data_ptr(), 0))
+        k = ctypes.c_int32()
+        _lib.check(L.clane_session_propagate(h, ctypes.c_float(float(np.float32(GAMMA))), 1 << 30, steps, amounts.data_ptr(),
+                                             steps, ctypes.byref(k)))
+        _lib.check(L.clane_session_get_z(h, Zout.data_ptr()))
+        dt = time.perf_counter() - t0
+        L.clane_session_destroy(h)
+        assert k.value == steps
+        best = dt if best is None else min(best, dt)
+    h2d = n * d * 4 + 4 * (n + 1) + 4 * e
+    d2h = n * d * 4 + 4 * steps
+    return {"value": e * steps / best, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+            "seconds": best, "steps": steps,
+            "note": "clane_session_create + clane_session_propagate(max_sweeps=steps) + clane_session_get_z from pinned "
+                    "host buffers; the upload, build_P and the download are inside the timed region and amortised over "
+                    "the steps of the call, as in a real propagate()"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
