@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
         L.clane_oracle_softmax_rows.argtypes = [_f32p, C.c_int64, _i64p, _f32p]
         L.clane_oracle_build_p.argtypes = [_f32p, C.c_int64, C.c_int64, _i64p, _i32p, _f32p]
         L.clane_oracle_sweep.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_int64, _i64p, _i32p, _f32p, C.c_float]
+        L.clane_oracle_sweep_range.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_int64, _i64p, _i32p,
+                                               _f32p, C.c_float]
         L.clane_oracle_propagate.argtypes = [_f32p, _f32p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_float,
                                              C.c_int64, C.c_int64, _f32p, C.c_int64, _f32p]
         L.clane_oracle_propagate.restype = C.c_int64
@@ -164,6 +166,19 @@ def sweep(X, Zcur, rowptr, col, w, gamma: float):
     Zn = np.empty_like(Zcur)
     lib().clane_oracle_sweep(px, pz, Zn.ctypes.data_as(_f32p), n, d, pr, pc, pw, C.c_float(np.float32(gamma)))
     return Zn
+
+
+def sweep_range(X, Zcur, Znext, lo: int, hi: int, rowptr, col, w, gamma: float):
+    """Sweep rows [lo, hi) only, writing into the caller's Znext (float32, C-contiguous)."""
+    X, px = _f32(X)
+    Zcur, pz = _f32(Zcur)
+    rowptr, pr = _i64(rowptr)
+    col, pc = _i32(col)
+    w, pw = _f32(w)
+    assert Znext.dtype == np.float32 and Znext.flags.c_contiguous and Znext.shape == Zcur.shape
+    lib().clane_oracle_sweep_range(px, pz, Znext.ctypes.data_as(_f32p), lo, hi, X.shape[1], pr, pc, pw,
+                                   C.c_float(np.float32(gamma)))
+    return Znext
 
 
 def propagate(X, Z, rowptr, col, gamma: float, tol: int, max_sweeps: int = 0, cap: int = 100000):
