@@ -257,11 +257,10 @@ def run_gpu(args):
             launches_per_step[0] = runner.sweep(with_l1)
             return
         a, b = S.Z[(S.cur + i) & 1], S.Z[(S.cur + i + 1) & 1]
-        _lib.check(L.clane_sweep(S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.ld, S.d, S.n, S.rowptr.data_ptr(),
-                                 S.col.data_ptr(), S.w.data_ptr(), gamma, S.light.data_ptr(), S.n_light,
-                                 S.hubs.data_ptr(), S.n_hub, S.amount.data_ptr() if with_l1 else 0, 0, 0, 0,
-                                 S.ws.data_ptr(), S.ws_bytes, sh))
-        launches_per_step[0] = (1 if S.n_light else 0) + (1 if S.n_hub else 0) + (2 if with_l1 else 0)
+        _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.rowptr.data_ptr(),
+                                 S.col.data_ptr(), S.w.data_ptr(), gamma, S.amount.data_ptr() if with_l1 else 0, 0, 0, 0,
+                                 sh))
+        launches_per_step[0] = S.plan.launches_per_sweep if with_l1 else 1
 
     def barrier():
         if world > 1:
@@ -310,7 +309,7 @@ def run_gpu(args):
                          if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",
                    "step": "sweep kernel(s) + exact L1 cascade + finish; P frozen"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(name), "kernel": "k_sweep_rows", "kernel_ms": kern_ms,
+                     "traffic": ncu_traffic(name), "kernel": "k_sweep", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": bytes_sweep / world, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "whole_step_gbs": bytes_sweep / world / (ms_per_step * 1e-3) / 1e9},

@@ -35,18 +35,22 @@ SIGNATURES = {
     "clane_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "clane_padded_ld": (C.c_int32, [C.c_int32]),
     "clane_csr_from_edges": (C.c_int64, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
-    "clane_row_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_i32p, c_vp, c_i32p]),
-    "clane_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "clane_group_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, c_i32p, c_vp,
+                                       c_i32p, c_i32p, c_i32p]),
+    "clane_plan_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, C.c_int32, C.c_int32,
+                                    C.c_int32]),
+    "clane_plan_destroy": (C.c_int, [c_vp]),
+    "clane_plan_info": (C.c_int, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
+    "clane_cascade_shape": (C.c_int, [C.c_int64, c_i64p, c_i64p]),
     "clane_edge_rows": (C.c_int, [c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
-    "clane_scores_cosine": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                      C.c_size_t, c_vp]),
-    "clane_row_softmax": (C.c_int, [c_vp, c_vp, C.c_int32, c_vp, c_vp, c_vp]),
+    "clane_scores_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp, c_vp]),
+    "clane_row_softmax": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
     "clane_cosine_finalize": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
-    "clane_build_p_cosine": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                       c_vp, C.c_size_t, c_vp]),
-    "clane_sweep": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, c_vp, C.c_float,
-                              c_vp, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp, C.c_int32, c_vp, C.c_size_t, c_vp]),
-    "clane_l1_diff": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, C.c_size_t, c_vp]),
+    "clane_build_p_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "clane_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
+    "clane_l1_diff": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "clane_l1_partial": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "clane_l1_finish": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
     "clane_patience_reset": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp]),
     "clane_session_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, c_vp, c_vp, C.c_int32]),
     "clane_session_destroy": (C.c_int, [c_vp]),
@@ -102,3 +106,32 @@ def ptr(t) -> int:
 def stream_handle() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+class Plan:
+    """Owner of a ``clane_plan`` handle (device-side schedule + reduction scratch)."""
+
+    def __init__(self, n: int, e: int, d: int, rowptr_host=None, row_lo: int = 0, row_hi: int | None = None,
+                 hub_threshold: int = 0):
+        require_cuda()
+        self.handle = c_vp()
+        self.n, self.e, self.d = int(n), int(e), int(d)
+        rp = 0
+        if rowptr_host is not None:
+            self._rowptr = rowptr_host          # keep alive during the call
+            rp = rowptr_host.ctypes.data
+        hi = self.n if row_hi is None else int(row_hi)
+        check(lib().clane_plan_create(C.byref(self.handle), self.n, self.e, self.d, rp, int(row_lo), hi,
+                                      int(hub_threshold)), "clane_plan_create")
+        g, nr, nh, fu, la = (C.c_int32() for _ in range(5))
+        check(lib().clane_plan_info(self.handle, C.byref(g), C.byref(nr), C.byref(nh), C.byref(fu), C.byref(la)))
+        self.group_rows, self.n_row_groups, self.n_hub_groups = g.value, nr.value, nh.value
+        self.fused_l1, self.launches_per_sweep = bool(fu.value), la.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                lib().clane_plan_destroy(self.handle)
+                self.handle = c_vp()
+        except Exception:
+            pass

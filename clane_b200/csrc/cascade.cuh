@@ -68,15 +68,17 @@ struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + 
 
 constexpr int kCascadeWarps = 16;
 
-// workspace layout (floats): P1[(n1_nodes + 1)][NQ][32] | R0[NQ][32] | P2[(n2_full + 1)][NQ][32]
+// level-1 buffer layout (floats): P1[(n1_nodes + 1)][NQ][32] | R0[NQ][32]   (= n1_nodes + 2 slots)
+// level-2 scratch           : P2[(n2_full + 1)][NQ][32]
 template <class Elem>
 __global__ void __launch_bounds__(kCascadeWarps * 32)
-k_cascade_l01(Elem elem, CascadeShape sh, float* __restrict__ ws, const clane_patience* __restrict__ st) {
+k_cascade_l01(Elem elem, CascadeShape sh, float* __restrict__ ws, int64_t node_lo,
+              const clane_patience* __restrict__ st) {
     constexpr int NQ = Elem::NQ;
     extern __shared__ float part[];  // [step][NQ][32]
     if (st != nullptr && st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t node = blockIdx.x;
+    const int64_t node = node_lo + blockIdx.x;
     const int step = (int)sh.step;
     const int64_t row0 = node * sh.node1_rows;
     const bool full = node < sh.n1_full;
@@ -141,8 +143,9 @@ __device__ __forceinline__ void patience_step(clane_patience* st, float amount, 
 
 template <class Elem>
 __global__ void __launch_bounds__(1024)
-k_cascade_finish(Elem elem, CascadeShape sh, float* __restrict__ ws, float* __restrict__ out,
-                 clane_patience* __restrict__ st, float* __restrict__ log, int log_cap) {
+k_cascade_finish(Elem elem, CascadeShape sh, const float* __restrict__ ws, float* __restrict__ P2,
+                 float* __restrict__ out, clane_patience* __restrict__ st, float* __restrict__ log, int log_cap,
+                 unsigned* __restrict__ reset_counter) {
     constexpr int NQ = Elem::NQ;
     __shared__ float lanes[NQ][32];
     if (st != nullptr && st->stop) return;
@@ -150,7 +153,7 @@ k_cascade_finish(Elem elem, CascadeShape sh, float* __restrict__ ws, float* __re
     const int step = (int)sh.step;
     const float* P1 = ws;
     const float* R0 = ws + (size_t)(sh.n1_nodes + 1) * 32 * NQ;
-    float* P2 = ws + (size_t)(sh.n1_nodes + 2) * 32 * NQ;
+    if (threadIdx.x == 0 && reset_counter != nullptr) *reset_counter = 0u;
 
     // level 2: complete nodes in parallel (one warp per (node, quantity)); slot n2_full holds
     // the sum of the complete level-1 nodes after the last complete level-2 node.
@@ -233,20 +236,66 @@ k_cascade_finish(Elem elem, CascadeShape sh, float* __restrict__ ws, float* __re
     }
 }
 
-// enqueue a full cascade sum of n elements; result(s) -> out[0..NQ)
+// level-1 nodes [node_lo, node_hi) of the cascade over n elements -> p1
 template <class Elem>
-inline int cascade_launch(const Elem& elem, int64_t n, float* ws, size_t ws_bytes, float* out, clane_patience* st,
-                          float* log, int log_cap, cudaStream_t s) {
+inline int cascade_launch_l01(const Elem& elem, int64_t n, int64_t node_lo, int64_t node_hi, float* p1,
+                              const clane_patience* st, cudaStream_t s) {
     CascadeShape sh = cascade_shape(n);
-    if (ws_bytes < cascade_ws_floats(n, Elem::NQ) * sizeof(float)) return CLANE_EWORKSPACE;
-    if (sh.n1_nodes > 0) {
+    if (node_lo < 0 || node_hi > sh.n1_nodes || node_lo > node_hi) return CLANE_EINVAL;
+    if (node_hi > node_lo) {
         const size_t smem = (size_t)sh.step * Elem::NQ * 32 * sizeof(float);
-        k_cascade_l01<Elem><<<(unsigned)sh.n1_nodes, kCascadeWarps * 32, smem, s>>>(elem, sh, ws, st);
+        k_cascade_l01<Elem><<<(unsigned)(node_hi - node_lo), kCascadeWarps * 32, smem, s>>>(elem, sh, p1, node_lo, st);
         CLANE_LAUNCH_CHECK();
     }
-    k_cascade_finish<Elem><<<1, 1024, 0, s>>>(elem, sh, ws, out, st, log, log_cap);
+    return CLANE_OK;
+}
+
+// levels 2-3, tails, final combine (+ patience) from a complete p1
+template <class Elem>
+inline int cascade_launch_finish(const Elem& elem, int64_t n, const float* p1, float* p2, float* out,
+                                 clane_patience* st, float* log, int log_cap, unsigned* reset_counter,
+                                 cudaStream_t s) {
+    CascadeShape sh = cascade_shape(n);
+    k_cascade_finish<Elem><<<1, 1024, 0, s>>>(elem, sh, p1, p2, out, st, log, log_cap, reset_counter);
     CLANE_LAUNCH_CHECK();
     return CLANE_OK;
+}
+
+// enqueue a full cascade sum of n elements; result(s) -> out[0..NQ)
+template <class Elem>
+inline int cascade_launch(const Elem& elem, int64_t n, float* p1, float* p2, float* out, clane_patience* st,
+                          float* log, int log_cap, cudaStream_t s) {
+    CascadeShape sh = cascade_shape(n);
+    int rc = cascade_launch_l01(elem, n, 0, sh.n1_nodes, p1, st, s);
+    if (rc != CLANE_OK) return rc;
+    return cascade_launch_finish(elem, n, p1, p2, out, st, log, log_cap, nullptr, s);
+}
+
+// Fused path: the sweep kernel already produced one 32-lane partial per level-0 chunk
+// (P0[chunk][32], chunk = group of rows); reduce `step` consecutive chunks per level-1 node.
+__global__ void __launch_bounds__(256)
+k_level1_from_p0(CascadeShape sh, const float* __restrict__ P0, float* __restrict__ p1,
+                 const clane_patience* __restrict__ st) {
+    if (st != nullptr && st->stop) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (node >= sh.n1_nodes) return;
+    const int step = (int)sh.step;
+    const int cnt = node < sh.n1_full ? step : (int)sh.c_rem;
+    const float* src = P0 + (size_t)node * step * 32 + lane;
+    float acc = 0.0f;
+    int i = 0;
+    for (; i + 8 <= cnt; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(i + u) * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+    }
+    for (; i < cnt; ++i) acc = fadd(acc, __ldg(src + (size_t)i * 32));
+    p1[(size_t)node * 32 + lane] = acc;
+    if (node == sh.n1_nodes - 1 && sh.rem_rows > 0 && sh.r_rem > 0)   // leftover rows = the last, partial group
+        p1[(size_t)(sh.n1_nodes + 1) * 32 + lane] = __ldg(P0 + (size_t)(sh.n1_full * step + sh.c_rem) * 32 + lane);
 }
 
 }  // namespace clane

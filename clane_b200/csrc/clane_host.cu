@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "plan.cuh"
 
 extern "C" {
 
@@ -49,29 +50,121 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
     }
 }
 
-int clane_row_schedule(const int32_t* h_rowptr, int32_t n, int32_t hub_threshold, int32_t* h_light_order,
-                       int32_t* n_light, int32_t* h_hub_rows, int32_t* n_hub) {
-    if (!h_rowptr || n < 0 || !h_light_order || !n_light || !h_hub_rows || !n_hub || hub_threshold < 1)
+// ---------------------------------------------------------------------------------------------
+// plan: degree-sorted row blocks + cascade scratch
+// ---------------------------------------------------------------------------------------------
+int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
+                         int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
+                         int32_t* n_hub_groups, int32_t* group_rows, int32_t* fused_l1) {
+    if (!h_rowptr || n < 0 || d < 1 || row_lo < 0 || row_hi > n || row_lo > row_hi || hub_threshold < 8 ||
+        !h_row_groups || !n_row_groups || !h_hub_groups || !n_hub_groups || !group_rows || !fused_l1)
         return CLANE_EINVAL;
-    std::vector<int32_t> hubs, medium, rest;
-    for (int32_t v = 0; v < n; ++v) {
-        const int32_t k = h_rowptr[v + 1] - h_rowptr[v];
-        if (k == 0) continue;
-        if (k > hub_threshold) hubs.push_back(v);
-        else if (k > 32) medium.push_back(v);
-        else rest.push_back(v);
+    // fused L1: a group of G rows is exactly one level-0 chunk of the cascade over n*d
+    clane::CascadeShape sh = clane::cascade_shape((int64_t)n * d);
+    const int64_t chunk = sh.step * 32;
+    int32_t G = 8, fuse = 0;
+    if ((d == 32 || d == 64 || d == 128) && row_lo == 0 && row_hi == n && chunk % d == 0 && chunk / d <= 32 &&
+        chunk <= clane::kStashFloats) {
+        G = (int32_t)(chunk / d);
+        fuse = 1;
     }
-    auto by_degree_desc = [&](int32_t x, int32_t y) {
-        const int32_t kx = h_rowptr[x + 1] - h_rowptr[x], ky = h_rowptr[y + 1] - h_rowptr[y];
-        return kx != ky ? kx > ky : x < y;
-    };
-    std::sort(hubs.begin(), hubs.end(), by_degree_desc);
-    std::sort(medium.begin(), medium.end(), by_degree_desc);
-    std::copy(hubs.begin(), hubs.end(), h_hub_rows);
-    std::copy(medium.begin(), medium.end(), h_light_order);
-    std::copy(rest.begin(), rest.end(), h_light_order + medium.size());
-    *n_hub = (int32_t)hubs.size();
-    *n_light = (int32_t)(medium.size() + rest.size());
+    const int32_t n_groups = (row_hi - row_lo + G - 1) / G;
+    std::vector<int32_t> hub, light;
+    std::vector<int64_t> work((size_t)std::max(n_groups, 1), 0);
+    for (int32_t g = 0; g < n_groups; ++g) {
+        const int32_t r0 = row_lo + g * G, r1 = std::min(r0 + G, row_hi);
+        bool is_hub = false;
+        for (int32_t v = r0; v < r1; ++v) is_hub |= (h_rowptr[v + 1] - h_rowptr[v]) > hub_threshold;
+        work[g] = (int64_t)h_rowptr[r1] - h_rowptr[r0];
+        if (work[g] == 0) continue;               // sinks only: never updated (embedder.py:88-89)
+        (is_hub ? hub : light).push_back(g);
+    }
+    auto by_work_desc = [&](int32_t x, int32_t y) { return work[x] != work[y] ? work[x] > work[y] : x < y; };
+    std::sort(hub.begin(), hub.end(), by_work_desc);
+    std::sort(light.begin(), light.end(), by_work_desc);
+    std::copy(hub.begin(), hub.end(), h_hub_groups);
+    std::copy(light.begin(), light.end(), h_row_groups);
+    *n_hub_groups = (int32_t)hub.size();
+    *n_row_groups = (int32_t)light.size();
+    *group_rows = G;
+    *fused_l1 = fuse;
+    return CLANE_OK;
+}
+
+int clane_plan_destroy(clane_plan* plan) {
+    if (!plan) return CLANE_OK;
+    cudaFree(plan->d_row_groups); cudaFree(plan->d_hub_groups); cudaFree(plan->d_P0);
+    cudaFree(plan->d_p1); cudaFree(plan->d_p2);
+    delete plan;
+    return CLANE_OK;
+}
+
+#define PLAN_CUDA(x)                                               \
+    do {                                                           \
+        cudaError_t e__ = (x);                                     \
+        if (e__ != cudaSuccess) { clane_plan_destroy(plan); return (int)e__; } \
+    } while (0)
+
+int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr, int32_t row_lo,
+                      int32_t row_hi, int32_t hub_threshold) {
+    if (!out || n < 0 || e < 0 || d < 1) return CLANE_EINVAL;
+    if (h_rowptr && (row_lo < 0 || row_hi > n || row_lo > row_hi)) return CLANE_EINVAL;
+    if (h_rowptr && h_rowptr[n] != e) return CLANE_EINVAL;
+    int rc = clane_internal_prepare_kernels();
+    if (rc != CLANE_OK) return rc;
+    clane_plan* plan = new (std::nothrow) clane_plan();
+    if (!plan) return (int)cudaErrorMemoryAllocation;
+    plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
+    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 256;
+    plan->nslab = (plan->ld + 127) / 128;
+
+    // cascade scratch: L1 over n*d (one quantity) and the norms over e*d (two quantities)
+    const int64_t n_l1 = (int64_t)n * d, n_nrm = e * (int64_t)d;
+    plan->p1_floats = std::max(clane::cascade_p1_floats(n_l1, 1), clane::cascade_p1_floats(n_nrm, 2)) + 64;
+    plan->p2_floats = std::max(clane::cascade_p2_floats(n_l1, 1), clane::cascade_p2_floats(n_nrm, 2)) + 64;
+    PLAN_CUDA(cudaMalloc(&plan->d_p1, plan->p1_floats * sizeof(float)));
+    PLAN_CUDA(cudaMalloc(&plan->d_p2, plan->p2_floats * sizeof(float)));
+    PLAN_CUDA(cudaMemset(plan->d_p1, 0, plan->p1_floats * sizeof(float)));
+    PLAN_CUDA(cudaMemset(plan->d_p2, 0, plan->p2_floats * sizeof(float)));
+    if (!h_rowptr) { *out = plan; return CLANE_OK; }
+
+    plan->has_schedule = true;
+    plan->row_lo = row_lo; plan->row_hi = row_hi;
+    plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
+    const int32_t max_groups = (row_hi - row_lo + 1) / 1 + 1;
+    std::vector<int32_t> hub((size_t)max_groups), light((size_t)max_groups);
+    int32_t n_hub = 0, n_light = 0;
+    rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, plan->hub_threshold, light.data(), &n_light, hub.data(),
+                              &n_hub, &plan->G, &plan->fuse);
+    if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
+    hub.resize((size_t)n_hub);
+    light.resize((size_t)n_light);
+    plan->n_groups = (row_hi - row_lo + plan->G - 1) / plan->G;
+    plan->n_hub_groups = (int32_t)hub.size();
+    plan->n_row_groups = (int32_t)light.size();
+    PLAN_CUDA(cudaMalloc(&plan->d_hub_groups, std::max<size_t>(hub.size(), 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_row_groups, std::max<size_t>(light.size(), 1) * sizeof(int32_t)));
+    if (!hub.empty())
+        PLAN_CUDA(cudaMemcpy(plan->d_hub_groups, hub.data(), hub.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!light.empty())
+        PLAN_CUDA(cudaMemcpy(plan->d_row_groups, light.data(), light.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (plan->fuse) {
+        const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);
+        PLAN_CUDA(cudaMalloc(&plan->d_P0, p0));
+        PLAN_CUDA(cudaMemset(plan->d_P0, 0, p0));   // dropped (all-sink) groups contribute +0 forever
+    }
+    *out = plan;
+    return CLANE_OK;
+}
+
+int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_row_groups, int32_t* n_hub_groups,
+                    int32_t* fused_l1, int32_t* launches_per_sweep) {
+    if (!plan) return CLANE_EINVAL;
+    if (group_rows) *group_rows = plan->G;
+    if (n_row_groups) *n_row_groups = plan->n_row_groups;
+    if (n_hub_groups) *n_hub_groups = plan->n_hub_groups;
+    if (fused_l1) *fused_l1 = plan->fuse;
+    if (launches_per_sweep) *launches_per_sweep = 3;   // sweep, level-1, finish (fused or not)
     return CLANE_OK;
 }
 
@@ -81,13 +174,11 @@ int clane_row_schedule(const int32_t* h_rowptr, int32_t n, int32_t hub_threshold
 struct clane_session {
     int32_t n = 0, d = 0, ld = 0;
     int64_t e = 0;
-    int32_t n_light = 0, n_hub = 0;
-    int32_t *rowptr = nullptr, *col = nullptr, *erow = nullptr, *light = nullptr, *hubs = nullptr;
+    clane_plan* plan = nullptr;
+    int32_t *rowptr = nullptr, *col = nullptr, *erow = nullptr;
     float *X = nullptr, *Z[2] = {nullptr, nullptr}, *prev = nullptr, *w = nullptr, *norms2 = nullptr;
     float *amount = nullptr, *log = nullptr;
     clane_patience* state = nullptr;
-    void* ws = nullptr;
-    size_t ws_bytes = 0;
     int cur = 0;  // Z[cur] holds the current embeddings
     int32_t log_cap = 0;
     cudaStream_t stream = nullptr;
@@ -115,9 +206,10 @@ static int copy_rows_d2h(clane_session* s, float* h_dst, const float* d_src) {
 
 int clane_session_destroy(clane_session* s) {
     if (!s) return CLANE_OK;
-    cudaFree(s->rowptr); cudaFree(s->col); cudaFree(s->erow); cudaFree(s->light); cudaFree(s->hubs);
+    clane_plan_destroy(s->plan);
+    cudaFree(s->rowptr); cudaFree(s->col); cudaFree(s->erow);
     cudaFree(s->X); cudaFree(s->Z[0]); cudaFree(s->Z[1]); cudaFree(s->prev); cudaFree(s->w); cudaFree(s->norms2);
-    cudaFree(s->amount); cudaFree(s->log); cudaFree(s->state); cudaFree(s->ws);
+    cudaFree(s->amount); cudaFree(s->log); cudaFree(s->state);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -145,8 +237,6 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
     SESSION_CUDA(cudaMalloc(&s->rowptr, (size_t)(n + 1) * sizeof(int32_t)));
     SESSION_CUDA(cudaMalloc(&s->col, ebytes));
     SESSION_CUDA(cudaMalloc(&s->erow, ebytes));
-    SESSION_CUDA(cudaMalloc(&s->light, std::max<size_t>((size_t)n * sizeof(int32_t), 16)));
-    SESSION_CUDA(cudaMalloc(&s->hubs, std::max<size_t>((size_t)n * sizeof(int32_t), 16)));
     SESSION_CUDA(cudaMalloc(&s->X, zbytes));
     SESSION_CUDA(cudaMalloc(&s->Z[0], zbytes));
     SESSION_CUDA(cudaMalloc(&s->Z[1], zbytes));
@@ -156,19 +246,11 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
     SESSION_CUDA(cudaMalloc(&s->amount, sizeof(float)));
     SESSION_CUDA(cudaMalloc(&s->log, (size_t)s->log_cap * sizeof(float)));
     SESSION_CUDA(cudaMalloc(&s->state, sizeof(clane_patience)));
-    s->ws_bytes = clane_workspace_bytes(n, e, d);
-    SESSION_CUDA(cudaMalloc(&s->ws, s->ws_bytes));
+    SESSION_TRY(clane_plan_create(&s->plan, n, e, d, h_rowptr, 0, n, hub_threshold));
     SESSION_CUDA(cudaMallocHost(&s->h_state, sizeof(clane_patience)));
 
-    std::vector<int32_t> light((size_t)std::max(n, 1)), hubs((size_t)std::max(n, 1));
-    SESSION_TRY(clane_row_schedule(h_rowptr, n, hub_threshold > 0 ? hub_threshold : 256, light.data(), &s->n_light,
-                                   hubs.data(), &s->n_hub));
     SESSION_CUDA(cudaMemcpyAsync(s->rowptr, h_rowptr, (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (e > 0) SESSION_CUDA(cudaMemcpyAsync(s->col, h_col, (size_t)e * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
-    if (s->n_light > 0)
-        SESSION_CUDA(cudaMemcpyAsync(s->light, light.data(), (size_t)s->n_light * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
-    if (s->n_hub > 0)
-        SESSION_CUDA(cudaMemcpyAsync(s->hubs, hubs.data(), (size_t)s->n_hub * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (n > 0) {
         SESSION_TRY(copy_rows_h2d(s, s->X, h_X));
         SESSION_CUDA(cudaMemcpyAsync(s->Z[0], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
@@ -201,8 +283,7 @@ int clane_session_get_z(clane_session* s, float* h_Z) {
 }
 
 static int session_build_p(clane_session* s) {
-    int rc = clane_build_p_cosine(s->Z[s->cur], s->ld, s->d, s->n, s->e, s->rowptr, s->erow, s->col, s->w, s->norms2,
-                                  s->ws, s->ws_bytes, s->stream);
+    int rc = clane_build_p_cosine(s->plan, s->Z[s->cur], s->rowptr, s->erow, s->col, s->w, s->norms2, s->stream);
     if (rc == CLANE_OK) s->p_valid = true;
     return rc;
 }
@@ -218,9 +299,8 @@ int clane_session_build_p(clane_session* s, float* h_w) {
 }
 
 static int session_sweep(clane_session* s, float gamma, bool with_state, float* d_amount) {
-    int rc = clane_sweep(s->X, s->Z[s->cur], s->Z[s->cur ^ 1], s->ld, s->d, s->n, s->rowptr, s->col, s->w, gamma,
-                         s->light, s->n_light, s->hubs, s->n_hub, d_amount, with_state ? s->state : nullptr,
-                         with_state ? s->log : nullptr, s->log_cap, s->ws, s->ws_bytes, s->stream);
+    int rc = clane_sweep(s->plan, s->X, s->Z[s->cur], s->Z[s->cur ^ 1], s->rowptr, s->col, s->w, gamma, d_amount,
+                         with_state ? s->state : nullptr, with_state ? s->log : nullptr, s->log_cap, s->stream);
     s->cur ^= 1;
     return rc;
 }
@@ -266,7 +346,7 @@ int clane_session_iterate(clane_session* s, float gamma, int32_t tol, int32_t ma
         int sweeps = 0;
         int rc = clane_session_propagate(s, gamma, tol, 0, nullptr, 0, &sweeps);
         if (rc != CLANE_OK) return rc;
-        rc = clane_l1_diff(s->Z[s->cur], s->prev, s->ld, s->d, s->n, s->amount, s->ws, s->ws_bytes, s->stream);
+        rc = clane_l1_diff(s->plan, s->Z[s->cur], s->prev, s->amount, s->stream);
         if (rc != CLANE_OK) return rc;
         float amt = 0.0f;
         CLANE_CUDA(cudaMemcpyAsync(&amt, s->amount, sizeof(float), cudaMemcpyDeviceToHost, s->stream));

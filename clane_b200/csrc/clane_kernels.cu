@@ -4,12 +4,14 @@
 // Reference call sites replaced (all under /root/reference/clane/):
 //   graph.py:118-128  Graph.build_P          -> k_dots + cascade(ElemGatherSq2) + k_row_softmax
 //   similarity.py:26-37 CosineSimilarity     -> k_dots + cascade(ElemGatherSq2)
-//   embedder.py:84-94 Jacobi sweep + L1       -> k_sweep_rows (+ hub path) + cascade(ElemAbsDiff)
+//   embedder.py:84-94 Jacobi sweep + L1       -> k_sweep (sweep.cuh; fused L1 partials) + cascade levels 1-3
 //   embedder.py:98-108 patience               -> patience_step (cascade.cuh)
 #include <math_constants.h>
 
 #include "cascade.cuh"
 #include "common.cuh"
+#include "plan.cuh"
+#include "sweep.cuh"
 
 namespace clane {
 
@@ -35,9 +37,9 @@ __global__ void k_edge_rows(const int32_t* __restrict__ rowptr, int32_t n, int64
 template <bool kFma>
 __global__ void __launch_bounds__(256)
 k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ erow,
-       const int32_t* __restrict__ col, int64_t e_cnt, float* __restrict__ dots) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e_cnt) return;
+       const int32_t* __restrict__ col, int64_t e_lo, int64_t e_hi, float* __restrict__ dots) {
+    const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e_hi) return;
     const float* a = Z + (size_t)__ldg(erow + e) * ld;
     const float* b = Z + (size_t)__ldg(col + e) * ld;
     float acc = 0.0f;
@@ -98,11 +100,11 @@ __device__ __forceinline__ float sleef_expf_u10(float d) {
 // One warp per row.  Optional global divisor c = fl(sqrt(S1)) * fl(sqrt(S2)) (similarity.py:37).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2, int32_t n,
+k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2, int32_t row_lo, int32_t row_hi,
               const int32_t* __restrict__ rowptr, float* __restrict__ w) {
-    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int row = row_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= n) return;
+    if (row >= row_hi) return;
     const int a = __ldg(rowptr + row), k = __ldg(rowptr + row + 1) - a;
     if (k == 0) return;
     const bool div = norms2 != nullptr;
@@ -154,103 +156,6 @@ k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2
         if (lane < k) w[a + lane] = fmul(e_reg, inv);
     } else {
         for (int i = lane; i < k; i += 32) w[a + i] = fmul(w[a + i], inv);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Jacobi sweep, row update (embedder.py:92):  w[1,k] @ Z[k,d] in oneMKL sgemm order
-// (SURVEY 7.1 step 4 / Appendix A.1), then t = fl(gamma*acc), z = fl(x + t).
-//
-// One warp per (row, 128-column slab); lane = one float4 of columns.  A column group is
-// "blocked" (fixed 8-neighbour tree) iff it lies below 16*floor(d/16) and the row has >= 8
-// neighbours; otherwise a sequential fma chain over the neighbours in ascending column id.
-// A row's neighbours are never split across lanes: the summation order is the reference's.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
-    acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
-    acc.z = ffma(wv, z.z, acc.z); acc.w = ffma(wv, z.w, acc.w);
-}
-
-__device__ __forceinline__ float blocked8(float a, const float* w, float z0, float z1, float z2, float z3,
-                                          float z4, float z5, float z6, float z7) {
-    a = ffma(w[6], z6, a);
-    a = ffma(w[4], z4, a);
-    a = fadd(a, ffma(w[5], z5, fmul(w[7], z7)));
-    a = fadd(a, fadd(ffma(w[0], z0, fmul(w[2], z2)), ffma(w[1], z1, fmul(w[3], z3))));
-    return a;
-}
-
-__global__ void __launch_bounds__(256)
-k_sweep_rows(const float* __restrict__ X, const float* __restrict__ Zc, float* __restrict__ Zn, int ld, int d,
-             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ w,
-             float gamma, const int32_t* __restrict__ order, int n_rows, int nslab,
-             const clane_patience* __restrict__ st) {
-    if (st != nullptr && st->stop) return;
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int task = (int)(gw / nslab), slab = (int)(gw - (int64_t)task * nslab);
-    if (task >= n_rows) return;
-    const int row = __ldg(order + task);
-    const int a = __ldg(rowptr + row), k = __ldg(rowptr + row + 1) - a;
-    if (k == 0) return;
-    const int c = slab * 128 + lane * 4;
-    const bool active = c < ld;
-    const int cc = active ? c : 0;
-    const int dm = (d / 16) * 16;
-    const bool blk = (c < dm) && (k >= 8);
-    const float* zb = Zc + cc;
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-
-    for (int base = 0; base < k; base += 32) {
-        const int my = base + lane;
-        int cj = 0;
-        float wj = 0.0f;
-        if (my < k) { cj = __ldg(col + a + my); wj = __ldg(w + a + my); }
-        const int cnt = min(32, k - base);
-        int o = 0;
-        for (; o + 8 <= cnt; o += 8) {
-            float4 z[8];
-            float ww[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = __shfl_sync(kFull, cj, o + i);
-                ww[i] = __shfl_sync(kFull, wj, o + i);
-                z[i] = ldg4(zb + (size_t)r * ld);
-            }
-            if (blk) {
-                acc.x = blocked8(acc.x, ww, z[0].x, z[1].x, z[2].x, z[3].x, z[4].x, z[5].x, z[6].x, z[7].x);
-                acc.y = blocked8(acc.y, ww, z[0].y, z[1].y, z[2].y, z[3].y, z[4].y, z[5].y, z[6].y, z[7].y);
-                acc.z = blocked8(acc.z, ww, z[0].z, z[1].z, z[2].z, z[3].z, z[4].z, z[5].z, z[6].z, z[7].z);
-                acc.w = blocked8(acc.w, ww, z[0].w, z[1].w, z[2].w, z[3].w, z[4].w, z[5].w, z[6].w, z[7].w);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) fma4(ww[i], z[i], acc);
-            }
-        }
-        const int m = cnt - o;  // 0..7 leftover neighbours: sequential fma in both regimes
-        if (m > 0) {
-            float4 z[7];
-            float ww[7];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int r = __shfl_sync(kFull, cj, (o + i) & 31);
-                ww[i] = __shfl_sync(kFull, wj, (o + i) & 31);
-                if (i < m) z[i] = ldg4(zb + (size_t)r * ld);
-            }
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-                if (i < m) fma4(ww[i], z[i], acc);
-        }
-    }
-    if (active) {
-        const size_t off = (size_t)row * ld + c;
-        const float4 x = ld_stream4(X + off);
-        float4 out;
-        out.x = fadd(x.x, fmul(gamma, acc.x));
-        out.y = fadd(x.y, fmul(gamma, acc.y));
-        out.z = fadd(x.z, fmul(gamma, acc.z));
-        out.w = fadd(x.w, fmul(gamma, acc.w));
-        *reinterpret_cast<float4*>(Zn + off) = out;
     }
 }
 
@@ -308,11 +213,12 @@ int clane_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int32_t clane_padded_ld(int32_t d) { return (d + 3) & ~3; }
 
-size_t clane_workspace_bytes(int64_t n, int64_t e, int32_t d) {
-    if (n < 0 || e < 0 || d < 1) return 0;
-    size_t a = cascade_ws_floats(n * (int64_t)d, 1);
-    size_t b = cascade_ws_floats(e * (int64_t)d, 2);
-    return ((a > b ? a : b) + 64) * sizeof(float);
+int clane_cascade_shape(int64_t n_elems, int64_t* n1_nodes, int64_t* elems_per_node) {
+    if (n_elems < 0) return CLANE_EINVAL;
+    CascadeShape sh = cascade_shape(n_elems);
+    if (n1_nodes) *n1_nodes = sh.n1_nodes;
+    if (elems_per_node) *elems_per_node = sh.node1_rows * 32;
+    return CLANE_OK;
 }
 
 int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_erow, clane_stream_t s) {
@@ -323,28 +229,27 @@ int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_er
     return CLANE_OK;
 }
 
-int clane_scores_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e, const int32_t* d_erow,
-                        const int32_t* d_col, float* d_dots, float* d_norms2, void* d_ws, size_t ws_bytes,
-                        clane_stream_t s) {
-    if (!d_Z || !d_erow || !d_col || !d_dots || !d_norms2 || !d_ws || d < 1 || ld < d || (ld & 3) || n < 0 || e < 0)
-        return CLANE_EINVAL;
+int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col,
+                        int64_t edge_lo, int64_t edge_hi, float* d_dots, float* d_norms2, clane_stream_t s) {
+    if (!plan || !d_Z || !d_erow || !d_col || !d_dots || !d_norms2) return CLANE_EINVAL;
+    if (edge_lo < 0 || edge_hi > plan->e || edge_lo > edge_hi) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
-    if (e > 0) {
-        const unsigned grid = (unsigned)((e + 255) / 256);
-        if (d < 400) k_dots<false><<<grid, 256, 0, st>>>(d_Z, ld, d, d_erow, d_col, e, d_dots);
-        else k_dots<true><<<grid, 256, 0, st>>>(d_Z, ld, d, d_erow, d_col, e, d_dots);
+    if (edge_hi > edge_lo) {
+        const unsigned grid = (unsigned)((edge_hi - edge_lo + 255) / 256);
+        if (plan->d < 400) k_dots<false><<<grid, 256, 0, st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+        else k_dots<true><<<grid, 256, 0, st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
         CLANE_LAUNCH_CHECK();
     }
-    ElemGatherSq2 el{d_Z, d_erow, d_col, d, ld};
-    return cascade_launch(el, e * (int64_t)d, (float*)d_ws, ws_bytes, d_norms2, nullptr, nullptr, 0, st);
+    ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld};
+    return cascade_launch(el, plan->e * (int64_t)plan->d, plan->d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, st);
 }
 
-int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t n, const int32_t* d_rowptr, float* d_w,
-                      clane_stream_t s) {
-    if (!d_scores || !d_rowptr || !d_w || n < 0) return CLANE_EINVAL;
-    if (n == 0) return CLANE_OK;
-    const unsigned grid = (unsigned)(((int64_t)n * 32 + 255) / 256);
-    k_row_softmax<<<grid, 256, 0, (cudaStream_t)s>>>(d_scores, d_norms2, n, d_rowptr, d_w);
+int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t row_lo, int32_t row_hi,
+                      const int32_t* d_rowptr, float* d_w, clane_stream_t s) {
+    if (!d_scores || !d_rowptr || !d_w || row_lo < 0 || row_hi < row_lo) return CLANE_EINVAL;
+    if (row_hi == row_lo) return CLANE_OK;
+    const unsigned grid = (unsigned)(((int64_t)(row_hi - row_lo) * 32 + 255) / 256);
+    k_row_softmax<<<grid, 256, 0, (cudaStream_t)s>>>(d_scores, d_norms2, row_lo, row_hi, d_rowptr, d_w);
     CLANE_LAUNCH_CHECK();
     return CLANE_OK;
 }
@@ -357,57 +262,91 @@ int clane_cosine_finalize(const float* d_dots, const float* d_norms2, int64_t e,
     return CLANE_OK;
 }
 
-int clane_build_p_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e, const int32_t* d_rowptr,
-                         const int32_t* d_erow, const int32_t* d_col, float* d_w, float* d_norms2, void* d_ws,
-                         size_t ws_bytes, clane_stream_t s) {
-    if (!d_rowptr) return CLANE_EINVAL;
-    int rc = clane_scores_cosine(d_Z, ld, d, n, e, d_erow, d_col, d_w, d_norms2, d_ws, ws_bytes, s);
+int clane_build_p_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_rowptr, const int32_t* d_erow,
+                         const int32_t* d_col, float* d_w, float* d_norms2, clane_stream_t s) {
+    if (!plan || !d_rowptr || !plan->has_schedule) return CLANE_EINVAL;
+    // rows [row_lo, row_hi) own the contiguous edge range [rowptr[row_lo], rowptr[row_hi])
+    int rc = clane_scores_cosine(plan, d_Z, d_erow, d_col, plan->edge_lo, plan->edge_hi, d_w, d_norms2, s);
     if (rc != CLANE_OK) return rc;
-    return clane_row_softmax(d_w, d_norms2, n, d_rowptr, d_w, s);
+    return clane_row_softmax(d_w, d_norms2, plan->row_lo, plan->row_hi, d_rowptr, d_w, s);
 }
 
-int clane_sweep(const float* d_X, const float* d_Zcur, float* d_Znext, int32_t ld, int32_t d, int32_t n,
-                const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma,
-                const int32_t* d_light_order, int32_t n_light, const int32_t* d_hub_rows, int32_t n_hub,
-                float* d_amount, clane_patience* d_state, float* d_amounts_log, int32_t log_cap, void* d_ws,
-                size_t ws_bytes, clane_stream_t s) {
-    if (!d_X || !d_Zcur || !d_Znext || !d_rowptr || d < 1 || ld < d || (ld & 3) || n < 0 || n_light < 0 || n_hub < 0)
-        return CLANE_EINVAL;
-    if ((n_light > 0 && !d_light_order) || (n_hub > 0 && !d_hub_rows)) return CLANE_EINVAL;
-    if ((n_light > 0 || n_hub > 0) && (!d_col || !d_w)) return CLANE_EINVAL;
+int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext, const int32_t* d_rowptr,
+                const int32_t* d_col, const float* d_w, float gamma, float* d_amount, clane_patience* d_state,
+                float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_X || !d_Zcur || !d_Znext || !d_rowptr) return CLANE_EINVAL;
+    if (plan->e > 0 && (!d_col || !d_w)) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
-    const int nslab = (ld + 127) / 128;
-    if (n_hub > 0) {
-        const int64_t warps = (int64_t)n_hub * nslab;
-        k_sweep_rows<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-            d_X, d_Zcur, d_Znext, ld, d, d_rowptr, d_col, d_w, gamma, d_hub_rows, n_hub, nslab, d_state);
+    const bool want_l1 = d_amount != nullptr || d_state != nullptr;
+    SweepParams p;
+    p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
+    p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
+    p.rowptr = d_rowptr; p.col = d_col; p.w = d_w; p.gamma = gamma;
+    p.hub_groups = plan->d_hub_groups; p.n_hub_groups = plan->n_hub_groups;
+    p.row_groups = plan->d_row_groups; p.n_row_groups = plan->n_row_groups;
+    p.row_lo = plan->row_lo; p.row_hi = plan->row_hi;
+    p.G = plan->G; p.nslab = plan->nslab;
+    p.fuse = (plan->fuse && want_l1) ? 1 : 0;
+    p.P0 = plan->d_P0;
+    p.hub_threshold = plan->hub_threshold;
+    p.st = d_state;
+    const int64_t row_ctas = ((int64_t)plan->n_row_groups * plan->nslab + kSweepWarps - 1) / kSweepWarps;
+    const int64_t grid = (int64_t)plan->n_hub_groups * plan->nslab + row_ctas;
+    if (grid > 0) {
+        k_sweep<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
-    if (n_light > 0) {
-        const int64_t warps = (int64_t)n_light * nslab;
-        k_sweep_rows<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-            d_X, d_Zcur, d_Znext, ld, d, d_rowptr, d_col, d_w, gamma, d_light_order, n_light, nslab, d_state);
-        CLANE_LAUNCH_CHECK();
+    if (!want_l1) return CLANE_OK;
+    const int64_t n_elems = (int64_t)plan->n * plan->d;
+    ElemAbsDiff el{d_Znext, d_Zcur, plan->d, plan->ld};
+    if (p.fuse) {
+        CascadeShape sh = cascade_shape(n_elems);
+        if (sh.n1_nodes > 0) {
+            k_level1_from_p0<<<(unsigned)((sh.n1_nodes * 32 + 255) / 256), 256, 0, st>>>(sh, plan->d_P0, plan->d_p1, d_state);
+            CLANE_LAUNCH_CHECK();
+        }
+        return cascade_launch_finish(el, n_elems, plan->d_p1, plan->d_p2, d_amount, d_state, d_amounts_log, log_cap,
+                                     nullptr, st);
     }
-    if (d_amount != nullptr || d_state != nullptr) {
-        if (!d_ws) return CLANE_EINVAL;
-        ElemAbsDiff el{d_Znext, d_Zcur, d, ld};
-        return cascade_launch(el, (int64_t)n * d, (float*)d_ws, ws_bytes, d_amount, d_state, d_amounts_log, log_cap, st);
-    }
-    return CLANE_OK;
+    return cascade_launch(el, n_elems, plan->d_p1, plan->d_p2, d_amount, d_state, d_amounts_log, log_cap, st);
 }
 
-int clane_l1_diff(const float* d_Za, const float* d_Zb, int32_t ld, int32_t d, int32_t n, float* d_out, void* d_ws,
-                  size_t ws_bytes, clane_stream_t s) {
-    if (!d_Za || !d_Zb || !d_out || !d_ws || d < 1 || ld < d || n < 0) return CLANE_EINVAL;
-    ElemAbsDiff el{d_Za, d_Zb, d, ld};
-    return cascade_launch(el, (int64_t)n * d, (float*)d_ws, ws_bytes, d_out, nullptr, nullptr, 0, (cudaStream_t)s);
+int clane_l1_diff(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_out, clane_stream_t s) {
+    if (!plan || !d_Za || !d_Zb || !d_out) return CLANE_EINVAL;
+    ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
+    return cascade_launch(el, (int64_t)plan->n * plan->d, plan->d_p1, plan->d_p2, d_out, nullptr, nullptr, 0,
+                          (cudaStream_t)s);
+}
+
+int clane_l1_partial(clane_plan* plan, const float* d_Za, const float* d_Zb, int64_t node_lo, int64_t node_hi,
+                     float* d_p1, clane_stream_t s) {
+    if (!plan || !d_Za || !d_Zb || !d_p1) return CLANE_EINVAL;
+    ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
+    return cascade_launch_l01(el, (int64_t)plan->n * plan->d, node_lo, node_hi, d_p1, nullptr, (cudaStream_t)s);
+}
+
+int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_p1, float* d_out,
+                    clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !d_Za || !d_Zb || !d_p1) return CLANE_EINVAL;
+    ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
+    return cascade_launch_finish(el, (int64_t)plan->n * plan->d, d_p1, plan->d_p2, d_out, d_state, d_amounts_log,
+                                 log_cap, nullptr, (cudaStream_t)s);
 }
 
 int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweeps, clane_stream_t s) {
     if (!d_state) return CLANE_EINVAL;
     k_patience_reset<<<1, 1, 0, (cudaStream_t)s>>>(d_state, tol, max_sweeps);
     CLANE_LAUNCH_CHECK();
+    return CLANE_OK;
+}
+
+// one-time: opt in to > 48 KB dynamic shared memory for the sweep kernel
+int clane_internal_prepare_kernels(void) {
+    static bool done = false;
+    if (done) return CLANE_OK;
+    CLANE_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemBytes));
+    // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
+    done = true;
     return CLANE_OK;
 }
 

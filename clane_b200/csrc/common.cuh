@@ -78,10 +78,16 @@ __host__ __device__ inline CascadeShape cascade_shape(int64_t n) {
     return s;
 }
 
-// floats of scratch a cascade over n elements with nq simultaneous quantities needs
-__host__ inline size_t cascade_ws_floats(int64_t n, int nq) {
+constexpr int kStashFloats = 4096;  // |delta| of one group (one level-0 chunk: <= 32 * 2^7 floats)
+
+// floats of the two scratch regions for a cascade over n elements
+__host__ inline size_t cascade_p1_floats(int64_t n, int nq) {
     CascadeShape s = cascade_shape(n);
-    return (size_t)((s.n1_nodes + 1) + 1 + (s.n2_full + 1)) * 32 * nq;
+    return (size_t)(s.n1_nodes + 2) * 32 * nq;
+}
+__host__ inline size_t cascade_p2_floats(int64_t n, int nq) {
+    CascadeShape s = cascade_shape(n);
+    return (size_t)(s.n2_full + 1) * 32 * nq;
 }
 
 }  // namespace clane

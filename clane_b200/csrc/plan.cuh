@@ -1,0 +1,26 @@
+// clane_plan: device-side schedule + scratch of one (graph shape, row range).  See clane_b200.h.
+#pragma once
+#include "common.cuh"
+
+struct clane_plan {
+    int32_t n = 0, d = 0, ld = 0;
+    int64_t e = 0;
+    int32_t row_lo = 0, row_hi = 0;
+    int64_t edge_lo = 0, edge_hi = 0;   // rowptr[row_lo], rowptr[row_hi]
+    int32_t hub_threshold = 256;
+    bool has_schedule = false;
+    int32_t G = 8;              // rows per group
+    int32_t nslab = 1;
+    int32_t fuse = 0;           // L1 change fused into the sweep (d in {32, 64, 128}, whole graph)
+    int32_t n_groups = 0;       // groups covering [row_lo, row_hi)
+    int32_t n_row_groups = 0, n_hub_groups = 0;
+    int32_t* d_row_groups = nullptr;
+    int32_t* d_hub_groups = nullptr;
+    float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
+    // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
+    float* d_p1 = nullptr;
+    float* d_p2 = nullptr;
+    size_t p1_floats = 0, p2_floats = 0;
+};
+
+extern "C" int clane_internal_prepare_kernels(void);

@@ -1,0 +1,428 @@
+// Jacobi sweep of Embedder.propagate (/root/reference/clane/embedder.py:84-94) for sm_100a.
+//
+//   z_v <- fl(x_v + fl(gamma * (w_v[1,k] @ Zcur[nbrs(v)][k,d])))        for every row with k > 0
+//
+// with the [1,k]x[k,d] product in oneMKL sgemm's summation order (SURVEY 7.1 step 4 /
+// Appendix A.1): per output column, neighbours in ascending column id;
+//   k < 8 or column >= 16*floor(d/16): sequential fma chain;
+//   else per block of 8 neighbours:  a = fma(w6,z6,a); a = fma(w4,z4,a);
+//        a += fma(w5,z5, w7*z7);  a += fma(w0,z0, w2*z2) + fma(w1,z1, w3*z3);
+//   then the k mod 8 leftovers sequentially.
+// A row's neighbours are therefore never split across lanes: parallelism is over columns
+// (one float4 of columns per lane) and rows, and memory-level parallelism comes from issuing
+// the (address-independent) gathers ahead of the in-order chains.
+//
+// Scheduling unit: a GROUP of G consecutive rows.  When d is 32/64/128, G*d is exactly one
+// level-0 chunk of the ATen cascade sum, so the warp (or CTA) that owns a group also produces
+// that chunk's 32-lane partial of sum|Znext - Zcur| in the reference's order (fused L1).
+//
+//   row role : one warp per (group, 128-column slab).  Software pipeline over "batches" (one
+//              8-neighbour block of one row): col/w staged through a per-warp shared-memory
+//              ring, the gathers of batch b+1 (8 x LDG.128 per lane) are in flight while
+//              batch b is reduced; X row and own Zcur row ride with the row's last batch.
+//   hub role : one CTA per (group with a row of degree > hub_threshold, slab).  The hub row
+//              is streamed through a 4-stage cp.async ring (32 neighbours x 512 B per stage)
+//              by all 8 warps; 4 consumer warps (lane = column) run the in-order chains.
+#pragma once
+#include "common.cuh"
+
+namespace clane {
+
+struct SweepParams {
+    const float* X;
+    const float* Zc;
+    float* Zn;
+    int ld, d, n;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* w;
+    float gamma;
+    const int32_t* hub_groups;
+    int n_hub_groups;
+    const int32_t* row_groups;  // sorted by edge count, descending
+    int n_row_groups;
+    int row_lo, row_hi;         // rows covered by the plan; groups are cut from row_lo
+    int G;                      // rows per group (<= 32)
+    int nslab;                  // 128-column slabs per row
+    int fuse;                   // 1: write one 32-lane |delta| partial per group to P0
+    float* P0;
+    int hub_threshold;
+    const clane_patience* st;
+};
+
+constexpr int kSweepThreads = 256;
+constexpr int kSweepWarps = 8;
+constexpr int kMetaRing = 64;                  // (col, w) pairs per warp
+constexpr int kHubStage = 32;                  // neighbours per ring stage
+constexpr int kHubStages = 4;
+constexpr int kHubRingFloats = kHubStages * kHubStage * 128;
+// dynamic shared memory: meta rings | hub ring | stash
+constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaRing * sizeof(int2) +
+                                   (size_t)kHubRingFloats * sizeof(float) + (size_t)kStashFloats * sizeof(float);
+
+__device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
+    acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
+    acc.z = ffma(wv, z.z, acc.z); acc.w = ffma(wv, z.w, acc.w);
+}
+
+__device__ __forceinline__ float blocked8(float a, const float* w, float z0, float z1, float z2, float z3,
+                                          float z4, float z5, float z6, float z7) {
+    a = ffma(w[6], z6, a);
+    a = ffma(w[4], z4, a);
+    a = fadd(a, ffma(w[5], z5, fmul(w[7], z7)));
+    a = fadd(a, fadd(ffma(w[0], z0, fmul(w[2], z2)), ffma(w[1], z1, fmul(w[3], z3))));
+    return a;
+}
+
+__device__ __forceinline__ void blocked8x4(float4& acc, const float* ww, const float4* z) {
+    acc.x = blocked8(acc.x, ww, z[0].x, z[1].x, z[2].x, z[3].x, z[4].x, z[5].x, z[6].x, z[7].x);
+    acc.y = blocked8(acc.y, ww, z[0].y, z[1].y, z[2].y, z[3].y, z[4].y, z[5].y, z[6].y, z[7].y);
+    acc.z = blocked8(acc.z, ww, z[0].z, z[1].z, z[2].z, z[3].z, z[4].z, z[5].z, z[6].z, z[7].z);
+    acc.w = blocked8(acc.w, ww, z[0].w, z[1].w, z[2].w, z[3].w, z[4].w, z[5].w, z[6].w, z[7].w);
+}
+
+__device__ __forceinline__ float4 finish_row(const float4& x, const float4& acc, float gamma) {
+    float4 out;
+    out.x = fadd(x.x, fmul(gamma, acc.x));
+    out.y = fadd(x.y, fmul(gamma, acc.y));
+    out.z = fadd(x.z, fmul(gamma, acc.z));
+    out.w = fadd(x.w, fmul(gamma, acc.w));
+    return out;
+}
+
+__device__ __forceinline__ float4 absdiff4(const float4& a, const float4& b) {
+    return make_float4(fabsf(fsub(a.x, b.x)), fabsf(fsub(a.y, b.y)), fabsf(fsub(a.z, b.z)), fabsf(fsub(a.w, b.w)));
+}
+
+// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane
+// m owns cascade lane m: the row is d/32 consecutive cascade rows, taken in order.
+__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane) {
+    const int sub = lane >> 2, comp = lane & 3;
+    for (int seg = 0; seg < nseg; ++seg) {
+        const int src = seg * 8 + sub;
+        const float v0 = __shfl_sync(kFull, dl.x, src), v1 = __shfl_sync(kFull, dl.y, src);
+        const float v2 = __shfl_sync(kFull, dl.z, src), v3 = __shfl_sync(kFull, dl.w, src);
+        const float v = comp == 0 ? v0 : (comp == 1 ? v1 : (comp == 2 ? v2 : v3));
+        chunk_acc = fadd(chunk_acc, v);
+    }
+    return chunk_acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// row role
+// ------------------------------------------------------------------------------------------
+struct BatchInfo {   // warp-uniform description of one staged batch
+    int row;         // absolute row id
+    int m;           // neighbours in the batch (1..8)
+    int first;       // first batch of its row
+    int last;        // last batch of its row
+};
+
+struct RowCursor {
+    int i;       // row index inside the group
+    int a;       // first edge of that row
+    int k;       // its degree
+    int pos;     // next neighbour position
+};
+
+__device__ void row_group_task(const SweepParams& p, int g, int slab, int lane, int2* ring) {
+    const int r0 = p.row_lo + g * p.G;
+    const int nrows = min(p.G, p.row_hi - r0);
+    const int c = slab * 128 + lane * 4;
+    const bool active = c < p.ld;
+    const int cc = active ? c : 0;
+    const bool col_blocked = c < (p.d / 16) * 16;
+    const int nseg = p.d >> 5;
+    const float* __restrict__ zb = p.Zc + cc;
+
+    // row pointers of the group: lane i holds [start, end) of row r0 + i
+    int rp_a = 0, rp_b = 0;
+    if (lane < nrows) { rp_a = __ldg(p.rowptr + r0 + lane); rp_b = __ldg(p.rowptr + r0 + lane + 1); }
+    const int e_first = __shfl_sync(kFull, rp_a, 0);
+    const int e_total = __shfl_sync(kFull, rp_b, nrows - 1) - e_first;
+
+    // (col, w) windows of 32 edges: registers hold the window being fetched, the ring the two
+    // windows the load cursor can touch.
+    int win_q = 0;            // window currently in registers
+    int filled = 0;           // stream offset (exclusive) up to which the ring is valid
+    int pc = 0; float pw = 0.0f;
+    if (lane < e_total) { pc = __ldg(p.col + e_first + lane); pw = __ldg(p.w + e_first + lane); }
+
+    RowCursor cur;
+    cur.i = -1; cur.a = 0; cur.k = 0; cur.pos = 0;
+
+    float4 z0[8], z1[8];
+    float w0[8], w1[8];
+    float4 xs0, xs1, zo0, zo1;
+    BatchInfo b0, b1;
+    xs0 = xs1 = zo0 = zo1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    b0.row = b1.row = 0; b0.m = b1.m = 0; b0.first = b1.first = 0; b0.last = b1.last = 0;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float chunk_acc = 0.0f;
+
+    // -- stage the next batch of the stream into (z, ww, xs, zo, info); false when exhausted --
+    auto stage = [&](float4* z, float* ww, float4& xs, float4& zo, BatchInfo& bi) -> bool {
+        while (cur.i < nrows && cur.pos >= cur.k) {
+            ++cur.i;
+            if (cur.i < nrows) {
+                cur.a = __shfl_sync(kFull, rp_a, cur.i);
+                cur.k = __shfl_sync(kFull, rp_b, cur.i) - cur.a;
+                cur.pos = 0;
+            }
+        }
+        if (cur.i >= nrows) return false;
+        const int u = cur.a + cur.pos - e_first;          // stream offset of the batch
+        const int m = min(8, cur.k - cur.pos);
+        while (filled < u + m) {                          // publish the fetched window, fetch the next
+            __syncwarp();                                 // every lane is done reading the slot it replaces
+            ring[(win_q & 1) * 32 + lane] = make_int2(pc, __float_as_int(pw));
+            __syncwarp();
+            filled = (win_q + 1) * 32;
+            ++win_q;
+            const int off = win_q * 32 + lane;
+            if (off < e_total) { pc = __ldg(p.col + e_first + off); pw = __ldg(p.w + e_first + off); }
+        }
+        bi.row = r0 + cur.i;
+        bi.m = m;
+        bi.first = cur.pos == 0;
+        bi.last = cur.pos + m >= cur.k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < m) {
+                const int2 mv = ring[(u + i) & (kMetaRing - 1)];
+                ww[i] = __int_as_float(mv.y);
+                z[i] = ldg4(zb + (size_t)mv.x * p.ld);
+            }
+        }
+        if (bi.last && active) {
+            const size_t off = (size_t)bi.row * p.ld + c;
+            xs = ld_stream4(p.X + off);
+            zo = ldg4(p.Zc + off);
+        }
+        cur.pos += m;
+        return true;
+    };
+
+    // -- reduce a staged batch; on the row's last batch write the row and its |delta| --
+    auto reduce = [&](const float4* z, const float* ww, const float4& xs, const float4& zo, const BatchInfo& bi) {
+        if (bi.first) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bi.m == 8 && col_blocked) {
+            blocked8x4(acc, ww, z);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < bi.m) fma4(ww[i], z[i], acc);
+        }
+        if (bi.last) {
+            float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
+                const float4 out = finish_row(xs, acc, p.gamma);
+                *reinterpret_cast<float4*>(p.Zn + (size_t)bi.row * p.ld + c) = out;
+                dl = absdiff4(out, zo);
+            }
+            if (p.fuse) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
+        }
+    };
+
+    bool more = stage(z0, w0, xs0, zo0, b0);
+    while (more) {
+        const bool n1 = stage(z1, w1, xs1, zo1, b1);
+        reduce(z0, w0, xs0, zo0, b0);
+        if (!n1) break;
+        more = stage(z0, w0, xs0, zo0, b0);
+        reduce(z1, w1, xs1, zo1, b1);
+    }
+    if (p.fuse) p.P0[(size_t)g * 32 + lane] = chunk_acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// hub role
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one ordinary row of a hub group, one warp, no pipelining (a handful of rows per hub group)
+__device__ void simple_row(const SweepParams& p, int row, int slab, int lane, int i_in_group, float* stash) {
+    const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
+    const int c = slab * 128 + lane * 4;
+    const bool active = c < p.ld;
+    if (k == 0) {
+        if (p.fuse && active) *reinterpret_cast<float4*>(stash + i_in_group * p.d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int cc = active ? c : 0;
+    const bool blk = (c < (p.d / 16) * 16) && (k >= 8);
+    const float* __restrict__ zb = p.Zc + cc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < k; base += 32) {
+        const int my = base + lane;
+        int cj = 0;
+        float wj = 0.0f;
+        if (my < k) { cj = __ldg(p.col + a + my); wj = __ldg(p.w + a + my); }
+        const int cnt = min(32, k - base);
+        int o = 0;
+        for (; o + 8 <= cnt; o += 8) {
+            float4 z[8];
+            float ww[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = __shfl_sync(kFull, cj, o + i);
+                ww[i] = __shfl_sync(kFull, wj, o + i);
+                z[i] = ldg4(zb + (size_t)r * p.ld);
+            }
+            if (blk) blocked8x4(acc, ww, z);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fma4(ww[i], z[i], acc);
+            }
+        }
+        const int m = cnt - o;
+        if (m > 0) {
+            float4 z[7];
+            float ww[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int r = __shfl_sync(kFull, cj, (o + i) & 31);
+                ww[i] = __shfl_sync(kFull, wj, (o + i) & 31);
+                if (i < m) z[i] = ldg4(zb + (size_t)r * p.ld);
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+                if (i < m) fma4(ww[i], z[i], acc);
+        }
+    }
+    if (active) {
+        const size_t off = (size_t)row * p.ld + c;
+        const float4 out = finish_row(ld_stream4(p.X + off), acc, p.gamma);
+        *reinterpret_cast<float4*>(p.Zn + off) = out;
+        if (p.fuse) *reinterpret_cast<float4*>(stash + i_in_group * p.d + c) = absdiff4(out, ldg4(p.Zc + off));
+    }
+}
+
+// the hub row itself: all 8 warps feed the ring, warps 0-3 consume (lane = one column)
+__device__ void hub_row(const SweepParams& p, int row, int slab, int i_in_group, float* ringf, float* stash) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
+    const int nst = (k + kHubStage - 1) / kHubStage;
+    const int c4 = slab * 128 + lane * 4;            // producer view: one float4 per lane
+    const bool pact = c4 < p.ld;
+    const int ccol = slab * 128 + warp * 32 + lane;  // consumer view (warps 0-3): one column per lane
+    const bool blk = ccol < (p.d / 16) * 16;         // k > hub_threshold >= 8
+    float acc = 0.0f;
+
+    // producers: neighbours s*32 + warp*4 + j of stage s; the column ids are fetched one stage ahead
+    int cnext = 0;
+    float wnext = 0.0f;
+    if (lane < k) { cnext = __ldg(p.col + a + lane); wnext = __ldg(p.w + a + lane); }
+    float wq[kHubStages - 1];   // w of the stages in flight, consumed in order
+    auto issue = [&](int s, int slot) {
+        // cnext/wnext hold stage s; remember w for the consumers, refill for stage s + 1
+        const int cidx = cnext;
+        wq[slot] = wnext;
+        const int nx = (s + 1) * kHubStage + lane;
+        cnext = 0; wnext = 0.0f;
+        if (nx < k) { cnext = __ldg(p.col + a + nx); wnext = __ldg(p.w + a + nx); }
+        float* dst = ringf + (size_t)(s % kHubStages) * kHubStage * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = warp * 4 + j;
+            const int r = __shfl_sync(kFull, cidx, t);
+            if (s * kHubStage + t < k && pact) cp_async16(dst + t * 128 + lane * 4, p.Zc + (size_t)r * p.ld + c4);
+        }
+        cp_async_commit();
+    };
+
+    // prologue: kHubStages - 1 stages in flight
+#pragma unroll
+    for (int s = 0; s < kHubStages - 1; ++s) {
+        if (s < nst) issue(s, s);
+        else cp_async_commit();
+    }
+    for (int s = 0; s < nst; ++s) {
+        cp_async_wait<kHubStages - 2>();
+        __syncthreads();                               // stage s landed for everyone; stage s-1 consumed
+        const float wcur = wq[0];
+#pragma unroll
+        for (int q = 0; q + 1 < kHubStages - 1; ++q) wq[q] = wq[q + 1];
+        if (s + kHubStages - 1 < nst) issue(s + kHubStages - 1, kHubStages - 2);
+        else cp_async_commit();
+        if (warp < 4) {
+            const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 128 + warp * 32 + lane;
+            const int cnt = min(kHubStage, k - s * kHubStage);
+            int o = 0;
+            for (; o + 8 <= cnt; o += 8) {
+                float ww[8], z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { ww[i] = __shfl_sync(kFull, wcur, o + i); z[i] = src[(o + i) * 128]; }
+                if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
+                }
+            }
+            for (; o < cnt; ++o) acc = ffma(__shfl_sync(kFull, wcur, o), src[o * 128], acc);
+        }
+    }
+    cp_async_wait<0>();
+    if (warp < 4 && ccol < p.ld) {
+        const size_t off = (size_t)row * p.ld + ccol;
+        const float out = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
+        p.Zn[off] = out;
+        if (p.fuse) stash[i_in_group * p.d + ccol] = fabsf(fsub(out, __ldg(p.Zc + off)));
+    }
+    __syncthreads();   // ring free for the next hub row
+}
+
+__device__ void hub_group_task(const SweepParams& p, int g, int slab, float* ringf, float* stash) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = p.row_lo + g * p.G;
+    const int nrows = min(p.G, p.row_hi - r0);
+    // ordinary rows first, one warp each
+    for (int i = warp; i < nrows; i += kSweepWarps) {
+        const int row = r0 + i;
+        const int k = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
+        if (k <= p.hub_threshold) simple_row(p, row, slab, lane, i, stash);
+    }
+    for (int i = 0; i < nrows; ++i) {
+        const int row = r0 + i;
+        const int k = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
+        if (k > p.hub_threshold) hub_row(p, row, slab, i, ringf, stash);
+    }
+    if (p.fuse) {
+        __syncthreads();
+        if (warp == 0) {
+            // the group is one level-0 chunk: nrows * d / 32 cascade rows, summed in order per lane
+            const int ncr = nrows * (p.d >> 5);
+            float acc = 0.0f;
+            for (int r = 0; r < ncr; ++r) acc = fadd(acc, stash[r * 32 + lane]);
+            p.P0[(size_t)g * 32 + lane] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (p.st != nullptr && p.st->stop) return;
+    int2* rings = reinterpret_cast<int2*>(smem);
+    float* ringf = reinterpret_cast<float*>(smem + (size_t)kSweepWarps * kMetaRing * sizeof(int2));
+    float* stash = ringf + kHubRingFloats;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_hub_ctas = p.n_hub_groups * p.nslab;
+    if ((int)blockIdx.x < n_hub_ctas) {
+        const int hg = blockIdx.x / p.nslab, slab = blockIdx.x - hg * p.nslab;
+        hub_group_task(p, __ldg(p.hub_groups + hg), slab, ringf, stash);
+        return;
+    }
+    const int64_t task = (int64_t)(blockIdx.x - n_hub_ctas) * kSweepWarps + warp;
+    const int64_t gi = task / p.nslab;
+    if (gi >= p.n_row_groups) return;
+    row_group_task(p, __ldg(p.row_groups + gi), (int)(task - gi * p.nslab), lane, rings + warp * kMetaRing);
+}
+
+}  // namespace clane

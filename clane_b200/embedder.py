@@ -75,8 +75,8 @@ class Embedder(object):
         while True:
             prev.copy_(S.Z[S.cur])
             self.propagate()
-            _lib.check(L.clane_l1_diff(S.Z[S.cur].data_ptr(), prev.data_ptr(), S.ld, S.d, S.n, S.amount.data_ptr(),
-                                       S.ws.data_ptr(), S.ws_bytes, _lib.stream_handle()), "clane_l1_diff")
+            _lib.check(L.clane_l1_diff(S.plan.handle, S.Z[S.cur].data_ptr(), prev.data_ptr(), S.amount.data_ptr(),
+                                       _lib.stream_handle()), "clane_l1_diff")
             amount_updated_Z_current = float(S.amount.cpu()[0])
             if self.minimum_amount_updated_Z > amount_updated_Z_current:
                 self.tolerences['global'].reset()
@@ -107,11 +107,9 @@ class Embedder(object):
         while True:
             for _ in range(batch):
                 src, dst = S.Z[(start + enqueued) & 1], S.Z[(start + enqueued + 1) & 1]
-                _lib.check(L.clane_sweep(S.X.data_ptr(), src.data_ptr(), dst.data_ptr(), S.ld, S.d, S.n,
+                _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), src.data_ptr(), dst.data_ptr(),
                                          S.rowptr.data_ptr(), S.col.data_ptr(), S.w.data_ptr(), gamma,
-                                         S.light.data_ptr(), S.n_light, S.hubs.data_ptr(), S.n_hub,
-                                         0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap,
-                                         S.ws.data_ptr(), S.ws_bytes, stream), "clane_sweep")
+                                         0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream), "clane_sweep")
                 enqueued += 1
             S.state_host.copy_(S.state, non_blocking=True)
             torch.cuda.current_stream().synchronize()

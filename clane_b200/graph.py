@@ -8,7 +8,7 @@ on every access) and everything the iterative update touches lives in HBM:
 
     rowptr int32[N+1] | col int32[E] | erow int32[E] | w fp32[E]
     X fp32[N, ld] | Z fp32[2][N, ld]   (ld = d rounded up to 4 floats: 16-byte aligned rows)
-    light_order / hub_rows: the degree-binned row schedule (sinks dropped)
+    clane_plan: the degree-sorted row-block schedule (hub groups / row groups, sinks dropped)
 
 All arithmetic is done by libclane_b200.so through the C-ABI (clane_b200/_lib.py); torch
 only owns the device memory.  There is no CPU fallback: ``build_P`` and the Embedder raise
@@ -162,12 +162,6 @@ class Graph(Dataset):
             _lib.check(int(e), "clane_csr_from_edges")
         self._rowptr, self._col = rowptr, col[:e].copy()
         self._nnz = int(e)
-        light = np.zeros(max(n, 1), np.int32)
-        hubs = np.zeros(max(n, 1), np.int32)
-        nl, nh = _lib.C.c_int32(), _lib.C.c_int32()
-        _lib.check(L.clane_row_schedule(rowptr.ctypes.data, n, HUB_THRESHOLD, light.ctypes.data, _lib.C.byref(nl),
-                                        hubs.ctypes.data, _lib.C.byref(nh)), "clane_row_schedule")
-        self._light, self._hubs = light[:nl.value].copy(), hubs[:nh.value].copy()
         self._Z_host = self.X      # z aliases x until the first update (graph.py:18-19)
         self._dev = None
 
@@ -217,9 +211,7 @@ class Graph(Dataset):
             S.rowptr = torch.from_numpy(self._rowptr).to(dev)
             S.col = torch.from_numpy(self._col if e else np.zeros(1, np.int32)).to(dev)
             S.erow = torch.zeros(max(e, 1), dtype=torch.int32, device=dev)
-            S.light = torch.from_numpy(self._light if len(self._light) else np.zeros(1, np.int32)).to(dev)
-            S.hubs = torch.from_numpy(self._hubs if len(self._hubs) else np.zeros(1, np.int32)).to(dev)
-            S.n_light, S.n_hub = len(self._light), len(self._hubs)
+            S.plan = _lib.Plan(n, e, d, self._rowptr, 0, n, HUB_THRESHOLD)
             S.X = torch.zeros([max(n, 1), ld], dtype=torch.float32, device=dev)
             S.X[:n, :d] = self.X.to(dev)
             S.Z = [torch.zeros_like(S.X), torch.zeros_like(S.X)]
@@ -227,8 +219,6 @@ class Graph(Dataset):
             S.w = torch.zeros(max(e, 1), dtype=torch.float32, device=dev)
             S.norms2 = torch.zeros(2, dtype=torch.float32, device=dev)
             S.amount = torch.zeros(1, dtype=torch.float32, device=dev)
-            S.ws_bytes = int(L.clane_workspace_bytes(n, e, d))
-            S.ws = torch.zeros(S.ws_bytes // 4 + 1, dtype=torch.float32, device=dev)
             S.state = torch.zeros(8, dtype=torch.int32, device=dev)          # struct clane_patience
             S.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
             S.log_cap = 1 << 16
@@ -278,9 +268,9 @@ class Graph(Dataset):
         Zc = S.Z[S.cur]
         stream = _lib.stream_handle()
         if getattr(similarity, "_clane_kernel", None) == "cosine":
-            _lib.check(L.clane_build_p_cosine(Zc.data_ptr(), S.ld, S.d, S.n, S.e, S.rowptr.data_ptr(), S.erow.data_ptr(),
-                                              S.col.data_ptr(), S.w.data_ptr(), S.norms2.data_ptr(), S.ws.data_ptr(),
-                                              S.ws_bytes, stream), "clane_build_p_cosine")
+            _lib.check(L.clane_build_p_cosine(S.plan.handle, Zc.data_ptr(), S.rowptr.data_ptr(), S.erow.data_ptr(),
+                                              S.col.data_ptr(), S.w.data_ptr(), S.norms2.data_ptr(), stream),
+                       "clane_build_p_cosine")
         else:
             # user plugin: honour its scores, still on the device; the softmax stays fused
             Zv = Zc[:S.n, :S.d]
@@ -288,7 +278,7 @@ class Graph(Dataset):
             scores = similarity(src_Z, dst_Z).detach().to(device=S.device, dtype=torch.float32).reshape(-1).contiguous()
             if scores.numel() != S.e:
                 raise ValueError(f"similarity returned {scores.numel()} scores for {S.e} edges")
-            _lib.check(L.clane_row_softmax(scores.data_ptr(), 0, S.n, S.rowptr.data_ptr(), S.w.data_ptr(), stream),
+            _lib.check(L.clane_row_softmax(scores.data_ptr(), 0, 0, S.n, S.rowptr.data_ptr(), S.w.data_ptr(), stream),
                        "clane_row_softmax")
         return S.w[:S.e]
 

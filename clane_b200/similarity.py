@@ -51,14 +51,15 @@ class CosineSimilarity(Similarity):
         col = torch.arange(e, 2 * e, dtype=torch.int32, device=dev)
         out = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
         norms2 = torch.empty(2, dtype=torch.float32, device=dev)
-        ws_bytes = int(L.clane_workspace_bytes(2 * e, e, d))
-        ws = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=dev)
+        plan = _lib.Plan(2 * e, e, d)          # scores-only plan: reduction scratch, no schedule
         s = _lib.stream_handle()
-        _lib.check(L.clane_scores_cosine(Z.data_ptr(), ld, d, 2 * e, e, erow.data_ptr(), col.data_ptr(), out.data_ptr(),
-                                         norms2.data_ptr(), ws.data_ptr(), ws_bytes, s), "clane_scores_cosine")
+        _lib.check(L.clane_scores_cosine(plan.handle, Z.data_ptr(), erow.data_ptr(), col.data_ptr(), 0, e,
+                                         out.data_ptr(), norms2.data_ptr(), s), "clane_scores_cosine")
         _lib.check(L.clane_cosine_finalize(out.data_ptr(), norms2.data_ptr(), e, out.data_ptr(), s),
                    "clane_cosine_finalize")
-        return out[:e].to(out_device)
+        res = out[:e].to(out_device)
+        torch.cuda.current_stream().synchronize()   # the plan's scratch is freed when it goes out of scope
+        return res
 
 
 class AsymmertricSimilarity(nn.Module, Similarity):

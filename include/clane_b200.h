@@ -38,7 +38,7 @@ extern "C" {
 #define CLANE_OK 0
 #define CLANE_EINVAL (-1)      /* bad argument (null pointer, negative size, d < 1 ...) */
 #define CLANE_ERANGE (-2)      /* edge endpoint outside [0, n) / size exceeds int32 indexing */
-#define CLANE_EWORKSPACE (-3)  /* workspace too small (see clane_workspace_bytes) */
+#define CLANE_EWORKSPACE (-3)  /* caller-provided buffer too small */
 #define CLANE_ENODEVICE (-4)   /* no CUDA device / not an sm_100 class device */
 
 typedef void* clane_stream_t;  /* cudaStream_t */
@@ -71,65 +71,91 @@ int32_t     clane_padded_ld(int32_t d);
 int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t e_raw, int64_t n,
                              int32_t* h_rowptr, int32_t* h_col);
 
-/* Degree-binned row schedule (north_star: "degree-sorted row blocks").  Rows without
- * out-neighbours are dropped (embedder.py:88-89: they are never updated); rows with degree
- * > hub_threshold go to h_hub_rows (degree-descending); the others to h_light_order
- * (degree > 32 first, degree-descending, then the rest in ascending id order).
- * Both outputs have capacity n. */
-int clane_row_schedule(const int32_t* h_rowptr, int32_t n, int32_t hub_threshold,
-                       int32_t* h_light_order, int32_t* n_light, int32_t* h_hub_rows, int32_t* n_hub);
+/* ---- plan: degree-sorted row blocks + scratch ----------------------------------------- */
+/* A plan holds, on the device, the schedule of the sweep over rows [row_lo, row_hi) of an
+ * n-row CSR (north_star: "degree-sorted row blocks") and the scratch of the exact reductions:
+ *   - rows are cut into groups of `group_rows` consecutive rows (one level-0 chunk of the
+ *     ATen cascade sum when d is 32, 64 or 128 and the plan covers all rows -- then the L1
+ *     change is fused into the sweep; otherwise 8 rows and the L1 change is a second pass);
+ *   - groups holding a row of degree > hub_threshold are "hub groups" (one CTA each, the hub
+ *     row streamed through a shared-memory ring); the others are sorted by edge count,
+ *     descending, and handed to warps eight at a time; groups of sinks only are dropped
+ *     (embedder.py:88-89: such rows are never updated).
+ * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
+typedef struct clane_plan clane_plan;
+/* The schedule alone, on the host (what clane_plan_create uploads): group ids relative to
+ * row_lo; both outputs have capacity row_hi - row_lo + 1. */
+int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
+                         int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
+                         int32_t* n_hub_groups, int32_t* group_rows, int32_t* fused_l1);
+int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
+                      int32_t row_lo, int32_t row_hi, int32_t hub_threshold);
+int clane_plan_destroy(clane_plan* plan);
+/* any pointer may be NULL */
+int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_row_groups, int32_t* n_hub_groups,
+                    int32_t* fused_l1, int32_t* launches_per_sweep);
+/* Shape of the exact L1 / norm reductions over a flattened array of n_elems fp32 values:
+ * number of level-1 nodes of the ATen cascade and elements per node.  A caller that splits a
+ * reduction over ranks exchanges [n1_nodes + 2] slots of 32 floats (see clane_l1_partial). */
+int clane_cascade_shape(int64_t n_elems, int64_t* n1_nodes, int64_t* elems_per_node);
 
 /* ---- device kernels ------------------------------------------------------------------ */
-/* bytes of scratch the calls below need for a graph of n rows, e coalesced edges, width d */
-size_t clane_workspace_bytes(int64_t n, int64_t e, int32_t d);
-
 /* d_erow[e] = source row of coalesced edge e (the first row of A.indices(), graph.py:119) */
 int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_erow, clane_stream_t s);
 
 /* CosineSimilarity.__call__ on (Z[src], Z[dst]) (/root/reference/clane/similarity.py:26-37),
  * split where the reference has its global reduction:
  *   d_dots[e]   = <z_src(e), z_dst(e)>   sequential over the feature index (mul+add for
- *                 d < 400, fma for d >= 400 -- the ATen / MKL switch);
+ *                 d < 400, fma for d >= 400 -- the ATen / MKL switch), for edges
+ *                 [edge_lo, edge_hi);
  *   d_norms2[0] = sum(Z[src]^2), d_norms2[1] = sum(Z[dst]^2) over the flattened [E*d]
- *                 gathered arrays in ATen cascade-sum order. */
-int clane_scores_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e,
-                        const int32_t* d_erow, const int32_t* d_col, float* d_dots, float* d_norms2,
-                        void* d_ws, size_t ws_bytes, clane_stream_t s);
+ *                 gathered arrays in ATen cascade-sum order (all E edges). */
+int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col,
+                        int64_t edge_lo, int64_t edge_hi, float* d_dots, float* d_norms2, clane_stream_t s);
 
-/* The per-source softmax of Graph.build_P (/root/reference/clane/graph.py:122-123) for all
- * rows at once.  If d_norms2 != NULL each score is first divided by
+/* The per-source softmax of Graph.build_P (/root/reference/clane/graph.py:122-123) for rows
+ * [row_lo, row_hi).  If d_norms2 != NULL each score is first divided by
  * fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))) (similarity.py:37); pass NULL for scores
  * produced by a user plugin.  d_w may alias d_scores. */
-int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t n, const int32_t* d_rowptr,
-                      float* d_w, clane_stream_t s);
+int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t row_lo, int32_t row_hi,
+                      const int32_t* d_rowptr, float* d_w, clane_stream_t s);
 
 /* The final division of CosineSimilarity.__call__ (similarity.py:37) for standalone plugin
  * calls: d_out[i] = d_dots[i] / fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))).  May alias. */
 int clane_cosine_finalize(const float* d_dots, const float* d_norms2, int64_t e, float* d_out, clane_stream_t s);
 
-/* Graph.build_P with CosineSimilarity (graph.py:118-128): clane_scores_cosine + clane_row_softmax. */
-int clane_build_p_cosine(const float* d_Z, int32_t ld, int32_t d, int32_t n, int64_t e,
-                         const int32_t* d_rowptr, const int32_t* d_erow, const int32_t* d_col,
-                         float* d_w, float* d_norms2, void* d_ws, size_t ws_bytes, clane_stream_t s);
+/* Graph.build_P with CosineSimilarity (graph.py:118-128) for the plan's rows:
+ * clane_scores_cosine + clane_row_softmax. */
+int clane_build_p_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_rowptr, const int32_t* d_erow,
+                         const int32_t* d_col, float* d_w, float* d_norms2, clane_stream_t s);
 
 /* One Jacobi sweep of Embedder.propagate (/root/reference/clane/embedder.py:84-94) over the
- * scheduled rows:  Znext[v] = X[v] + gamma * (w_v @ Zcur[nbrs(v)]) in oneMKL's summation
- * order, gamma*(.) and x+(.) rounded separately; rows outside the schedule are not touched
- * (Znext must already hold their value).  If d_amount != NULL the L1 change
- * sum|Znext - Zcur| over the flattened [n*d] array (ATen cascade order, embedder.py:94) is
- * written to d_amount[0]; if d_state != NULL the patience state machine (embedder.py:98-108)
- * is advanced on the device, d_amounts_log[sweep] (capacity log_cap) receives the amount, and
- * the whole call is a no-op once d_state->stop is set. */
-int clane_sweep(const float* d_X, const float* d_Zcur, float* d_Znext, int32_t ld, int32_t d, int32_t n,
+ * plan's rows:  Znext[v] = X[v] + gamma * (w_v @ Zcur[nbrs(v)]) in oneMKL's summation order,
+ * gamma*(.) and x+(.) rounded separately; rows without out-neighbours are not touched (Znext
+ * must already hold their value).  If d_amount != NULL the L1 change sum|Znext - Zcur| over
+ * the flattened [n*d] array (ATen cascade order, embedder.py:94) is written to d_amount[0];
+ * if d_state != NULL the patience state machine (embedder.py:98-108) is advanced on the
+ * device, d_amounts_log[sweep] (capacity log_cap) receives the amount, and the whole call is
+ * a no-op once d_state->stop is set.  With both NULL only the row update runs (a rank of a
+ * row-partitioned run: see clane_l1_partial). */
+int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext,
                 const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma,
-                const int32_t* d_light_order, int32_t n_light, const int32_t* d_hub_rows, int32_t n_hub,
                 float* d_amount, clane_patience* d_state, float* d_amounts_log, int32_t log_cap,
-                void* d_ws, size_t ws_bytes, clane_stream_t s);
+                clane_stream_t s);
 
 /* (Za - Zb).abs().sum() over the flattened [n*d] array in ATen cascade order
  * (/root/reference/clane/embedder.py:60).  Result in d_out[0]. */
-int clane_l1_diff(const float* d_Za, const float* d_Zb, int32_t ld, int32_t d, int32_t n, float* d_out,
-                  void* d_ws, size_t ws_bytes, clane_stream_t s);
+int clane_l1_diff(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_out, clane_stream_t s);
+
+/* The same reduction split for a row-partitioned (multi-GPU) run.  The cascade's level-1
+ * nodes are independent: each rank reduces nodes [node_lo, node_hi) of the whole [n*d] array
+ * into d_p1 (layout [n1_nodes + 2][32] floats, see clane_cascade_shape; slot n1_nodes - 1 may
+ * be the trailing partial node, slot n1_nodes + 1 its leftover rows), the ranks all-gather
+ * their slots, and clane_l1_finish combines them in the one fixed order on every rank. */
+int clane_l1_partial(clane_plan* plan, const float* d_Za, const float* d_Zb, int64_t node_lo, int64_t node_hi,
+                     float* d_p1, clane_stream_t s);
+int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_p1, float* d_out,
+                    clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
 
 /* Reset the device patience state for a new propagate() call (embedder.py:78-79). */
 int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweeps, clane_stream_t s);

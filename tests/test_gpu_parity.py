@@ -38,10 +38,8 @@ def gpu_l1(a: np.ndarray, b: np.ndarray) -> np.float32:
     A = torch.zeros([n, ld], device="cuda"); A[:, :d] = torch.from_numpy(a).cuda()
     B = torch.zeros([n, ld], device="cuda"); B[:, :d] = torch.from_numpy(b).cuda()
     out = torch.zeros(1, device="cuda")
-    wsb = L.clane_workspace_bytes(n, 0, d)
-    ws = torch.zeros(wsb // 4 + 1, device="cuda")
-    _lib.check(L.clane_l1_diff(A.data_ptr(), B.data_ptr(), ld, d, n, out.data_ptr(), ws.data_ptr(), wsb,
-                               _lib.stream_handle()))
+    plan = _lib.Plan(n, 0, d)
+    _lib.check(L.clane_l1_diff(plan.handle, A.data_ptr(), B.data_ptr(), out.data_ptr(), _lib.stream_handle()))
     return np.float32(out.cpu().numpy()[0])
 
 
@@ -89,9 +87,9 @@ def test_row_softmax_generic_plugin_and_long_rows():
         L = _lib.lib()
         sd, rp = torch.from_numpy(s).cuda(), torch.from_numpy(rowptr).cuda()
         w = torch.zeros_like(sd)
-        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, len(ks), rp.data_ptr(), w.data_ptr(), _lib.stream_handle()))
+        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, 0, len(ks), rp.data_ptr(), w.data_ptr(), _lib.stream_handle()))
         assert np.array_equal(w.cpu().numpy(), want)
-        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, len(ks), rp.data_ptr(), sd.data_ptr(), _lib.stream_handle()))
+        _lib.check(L.clane_row_softmax(sd.data_ptr(), 0, 0, len(ks), rp.data_ptr(), sd.data_ptr(), _lib.stream_handle()))
         assert np.array_equal(sd.cpu().numpy(), want)      # in place
 
 
@@ -255,6 +253,61 @@ def test_baseline_shapes_against_oracle(shape, scale):
     assert within_tolerance(Z, Zo) and np.array_equal(Z, Zo)
     sinks = np.diff(rowptr) == 0
     assert np.array_equal(Z[sinks], X[sinks])                            # embedder.py:88-89
+
+
+@pytest.mark.parametrize("n,d,hub_deg,tol", [(3000, 128, 900, 2), (3000, 64, 400, 2), (5000, 32, 300, 2), (3000, 100, 700, 2),
+                                             (700, 500, 600, 1), (300, 1433, 290, 1), (140003, 128, 9000, 1)])
+def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol):
+    """Power-law graphs with hub rows (shared-memory ring path), every d regime: fused L1
+    (d = 32/64/128, level step 16 and 32), padded / multi-slab rows (100, 500, 1433)."""
+    rng = np.random.default_rng(n + d)
+    e = n * 6
+    src, dst = synth.make_edges(n, e, "powerlaw", rng)
+    hubs = rng.permutation(n)[:3]
+    extra_src = np.repeat(hubs, [hub_deg, hub_deg // 2 + 3, 257])
+    extra_dst = np.concatenate([rng.permutation(n)[:k] for k in (hub_deg, hub_deg // 2 + 3, 257)])
+    src, dst = np.concatenate([src, extra_src]), np.concatenate([dst, extra_dst])
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    g = Graph.from_arrays(n, src, dst, X)
+    emb = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=tol)
+    emb.verbose = False
+    emb.propagate(max_sweeps=4)
+    S = g._device_state()
+    assert S.plan.n_hub_groups >= 1 and S.plan.fused_l1 == (d in (32, 64, 128))
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    Zo, amounts, w = O.propagate(X, X, rowptr, col, 0.76, tol, max_sweeps=4)
+    assert np.array_equal(S.w[:S.e].cpu().numpy(), w)
+    assert np.array_equal(emb.amounts_per_call[0], amounts)
+    assert np.array_equal(g.Z.numpy(), Zo)
+
+
+def test_split_l1_reduction_matches_whole():
+    """clane_l1_partial over disjoint node ranges + clane_l1_finish == clane_l1_diff (multi-GPU path)."""
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    for n, d in [(50000, 100), (169343, 128), (3000, 500), (10, 3)]:
+        a = rng.standard_normal((n, d)).astype(np.float32)
+        b = rng.standard_normal((n, d)).astype(np.float32)
+        ld = L.clane_padded_ld(d)
+        A = torch.zeros([n, ld], device="cuda"); A[:, :d] = torch.from_numpy(a).cuda()
+        B = torch.zeros([n, ld], device="cuda"); B[:, :d] = torch.from_numpy(b).cuda()
+        plan = _lib.Plan(n, 0, d)
+        nodes = ctypes.c_int64()
+        _lib.check(L.clane_cascade_shape(n * d, ctypes.byref(nodes), None))
+        k = nodes.value
+        parts = []
+        cuts = [0, k // 3, k // 3, (2 * k) // 3 + (1 if k else 0), k]     # includes an empty range
+        cuts = sorted(min(c, k) for c in cuts)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            p1 = torch.zeros((k + 2) * 32, device="cuda")
+            _lib.check(L.clane_l1_partial(plan.handle, A.data_ptr(), B.data_ptr(), lo, hi, p1.data_ptr(), _lib.stream_handle()))
+            parts.append(p1)
+        total = torch.stack(parts).sum(0)              # what an all-reduce(SUM) of disjoint slots gives
+        out = torch.zeros(1, device="cuda")
+        _lib.check(L.clane_l1_finish(plan.handle, A.data_ptr(), B.data_ptr(), total.data_ptr(), out.data_ptr(), 0, 0, 0,
+                                     _lib.stream_handle()))
+        assert np.float32(out.cpu().numpy()[0]) == O.l1_diff(a, b)
 
 
 def test_full_convergence_cora_shape_counts_match_oracle():

@@ -139,28 +139,57 @@ def test_csr_rejects_out_of_range():
         Graph.from_arrays(3, src, dst, np.zeros((3, 2), np.float32))
 
 
-def test_row_schedule_bins():
+def group_schedule(rowptr, n, d, lo, hi, hub=256):
+    L = _lib.lib()
+    cap = hi - lo + 1
+    rg, hg = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    nr, nh, G, fu = (ctypes.c_int32() for _ in range(4))
+    _lib.check(L.clane_group_schedule(rowptr.ctypes.data, n, d, lo, hi, hub, rg.ctypes.data, ctypes.byref(nr),
+                                      hg.ctypes.data, ctypes.byref(nh), ctypes.byref(G), ctypes.byref(fu)))
+    return rg[:nr.value], hg[:nh.value], G.value, bool(fu.value)
+
+
+def test_group_schedule_degree_sorted_row_blocks():
     rng = np.random.default_rng(3)
-    n = 2000
+    n = 2003
     deg = np.minimum((rng.pareto(1.0, n) * 3).astype(np.int64), n - 1)
     deg[:5] = [0, 1, 33, 257, 1500]
+    deg[64:80] = 0                                    # two whole groups of sinks
     src = np.repeat(np.arange(n), deg)
     dst = np.concatenate([rng.permutation(n)[:k] for k in deg])
     g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
     k = np.diff(g._rowptr)
-    assert sorted(g._hubs.tolist()) == np.nonzero(k > 256)[0].tolist()
-    assert sorted(g._light.tolist()) == np.nonzero((k > 0) & (k <= 256))[0].tolist()   # sinks dropped
-    assert np.all(np.diff(k[g._hubs]) <= 0)                                              # longest first
-    nmed = int(((k > 32) & (k <= 256)).sum())
-    assert np.all(k[g._light[:nmed]] > 32) and np.all(np.diff(k[g._light[:nmed]]) <= 0)
-    assert np.all(np.diff(g._light[nmed:]) > 0)                                          # the rest in id order
+    for d, lo, hi in [(100, 0, n), (128, 0, n), (128, 500, 1700), (1433, 0, n)]:
+        rg, hg, G, fused = group_schedule(g._rowptr, n, d, lo, hi)
+        assert fused == (d == 128 and lo == 0 and hi == n)
+        assert G == (4 if fused else 8)               # n*d < 2^24: level step 16 -> 512-element chunks
+        ng = (hi - lo + G - 1) // G
+        work = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].sum() for i in range(ng)])
+        hubby = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].max() > 256 for i in range(ng)])
+        assert sorted(hg.tolist()) == np.nonzero(hubby)[0].tolist()
+        assert sorted(rg.tolist()) == np.nonzero(~hubby & (work > 0))[0].tolist()    # all-sink groups dropped
+        assert np.all(np.diff(work[rg]) <= 0) and np.all(np.diff(work[hg]) <= 0)       # longest first
+    # a graph large enough for level step 32: 1024-element chunks = 8 rows of 128
+    rp = np.zeros(140001, np.int32)
+    assert group_schedule(rp, 140000, 128, 0, 140000)[2:] == (8, True)
+    assert group_schedule(rp, 140000, 64, 0, 140000)[2:] == (8, True)      # 8.96M elements: step 16, 512 / 64
+    assert group_schedule(rp, 140000, 100, 0, 140000)[2:] == (8, False)
+
+
+def test_cascade_shape():
+    L = _lib.lib()
+    nodes, per = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(L.clane_cascade_shape(169343 * 128, ctypes.byref(nodes), ctypes.byref(per)))
+    assert (nodes.value, per.value) == (662, 32768)
+    _lib.check(L.clane_cascade_shape(2708 * 1433, ctypes.byref(nodes), ctypes.byref(per)))
+    assert (nodes.value, per.value) == (474, 8192)
 
 
 # ---- C-ABI surface -------------------------------------------------------------------------------
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "clane_b200.h").read_text()
     declared = set(re.findall(r"\b(clane_[a-z0-9_]+)\s*\(", header))
-    declared -= {"clane_patience"}
+    declared -= {"clane_patience", "clane_plan", "clane_session"}
     assert len(declared) >= 20
     L = ctypes.CDLL(str(_lib.LIB_PATH))
     for name in declared:
@@ -174,10 +203,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_kernel_entry_points_reject_bad_arguments_without_a_device():
     L = _lib.lib()
-    assert L.clane_sweep(0, 0, 0, 4, 4, 1, 0, 0, 0, 0.5, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == -1
-    assert L.clane_row_softmax(0, 0, 1, 0, 0, 0) == -1
-    assert L.clane_scores_cosine(0, 4, 4, 1, 1, 0, 0, 0, 0, 0, 0, 0) == -1
-    assert L.clane_workspace_bytes(10, 10, 0) == 0 and L.clane_workspace_bytes(169343, 1166243, 128) > 0
+    assert L.clane_sweep(0, 0, 0, 0, 0, 0, 0, 0.5, 0, 0, 0, 0, 0) == -1
+    assert L.clane_row_softmax(0, 0, 0, 1, 0, 0, 0) == -1
+    assert L.clane_scores_cosine(0, 0, 0, 0, 0, 1, 0, 0, 0) == -1
+    assert L.clane_l1_diff(0, 0, 0, 0, 0) == -1 and L.clane_plan_info(0, None, None, None, None, None) == -1
+    assert L.clane_plan_destroy(0) == 0
+    assert L.clane_group_schedule(0, 1, 1, 0, 1, 256, 0, None, 0, None, None, None) == -1
 
 
 def test_no_cpu_fallback_without_cuda(data_root):
