@@ -55,37 +55,47 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
 // ---------------------------------------------------------------------------------------------
 int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
                          int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
-                         int32_t* n_hub_groups, int32_t* group_rows, int32_t* fused_l1) {
+                         int32_t* n_hub_groups, int32_t* h_hub_rows, int32_t* n_hub_rows, int32_t* group_rows,
+                         int32_t* fused_l1) {
     if (!h_rowptr || n < 0 || d < 1 || row_lo < 0 || row_hi > n || row_lo > row_hi || hub_threshold < 8 ||
-        !h_row_groups || !n_row_groups || !h_hub_groups || !n_hub_groups || !group_rows || !fused_l1)
+        !h_row_groups || !n_row_groups || !h_hub_groups || !n_hub_groups || !h_hub_rows || !n_hub_rows ||
+        !group_rows || !fused_l1)
         return CLANE_EINVAL;
     // fused L1: a group of G rows is exactly one level-0 chunk of the cascade over n*d
     clane::CascadeShape sh = clane::cascade_shape((int64_t)n * d);
     const int64_t chunk = sh.step * 32;
     int32_t G = 8, fuse = 0;
-    if ((d == 32 || d == 64 || d == 128) && row_lo == 0 && row_hi == n && chunk % d == 0 && chunk / d <= 32 &&
-        chunk <= clane::kStashFloats) {
+    if ((d == 32 || d == 64 || d == 128) && row_lo == 0 && row_hi == n && chunk % d == 0 && chunk / d <= 32) {
         G = (int32_t)(chunk / d);
         fuse = 1;
     }
     const int32_t n_groups = (row_hi - row_lo + G - 1) / G;
-    std::vector<int32_t> hub, light;
+    std::vector<int32_t> hub_groups, row_groups, hub_rows;
     std::vector<int64_t> work((size_t)std::max(n_groups, 1), 0);
     for (int32_t g = 0; g < n_groups; ++g) {
         const int32_t r0 = row_lo + g * G, r1 = std::min(r0 + G, row_hi);
-        bool is_hub = false;
-        for (int32_t v = r0; v < r1; ++v) is_hub |= (h_rowptr[v + 1] - h_rowptr[v]) > hub_threshold;
-        work[g] = (int64_t)h_rowptr[r1] - h_rowptr[r0];
-        if (work[g] == 0) continue;               // sinks only: never updated (embedder.py:88-89)
-        (is_hub ? hub : light).push_back(g);
+        bool has_hub = false;
+        for (int32_t v = r0; v < r1; ++v) {
+            const int32_t k = h_rowptr[v + 1] - h_rowptr[v];
+            if (k > hub_threshold) { has_hub = true; hub_rows.push_back(v); }
+            else work[g] += k;
+        }
+        if (has_hub) hub_groups.push_back(g);
+        if (work[g] > 0) row_groups.push_back(g);     // groups of sinks only are never updated (embedder.py:88-89)
     }
     auto by_work_desc = [&](int32_t x, int32_t y) { return work[x] != work[y] ? work[x] > work[y] : x < y; };
-    std::sort(hub.begin(), hub.end(), by_work_desc);
-    std::sort(light.begin(), light.end(), by_work_desc);
-    std::copy(hub.begin(), hub.end(), h_hub_groups);
-    std::copy(light.begin(), light.end(), h_row_groups);
-    *n_hub_groups = (int32_t)hub.size();
-    *n_row_groups = (int32_t)light.size();
+    auto by_degree_desc = [&](int32_t x, int32_t y) {
+        const int32_t kx = h_rowptr[x + 1] - h_rowptr[x], ky = h_rowptr[y + 1] - h_rowptr[y];
+        return kx != ky ? kx > ky : x < y;
+    };
+    std::sort(row_groups.begin(), row_groups.end(), by_work_desc);
+    std::sort(hub_rows.begin(), hub_rows.end(), by_degree_desc);
+    std::copy(hub_groups.begin(), hub_groups.end(), h_hub_groups);
+    std::copy(row_groups.begin(), row_groups.end(), h_row_groups);
+    std::copy(hub_rows.begin(), hub_rows.end(), h_hub_rows);
+    *n_hub_groups = (int32_t)hub_groups.size();
+    *n_row_groups = (int32_t)row_groups.size();
+    *n_hub_rows = (int32_t)hub_rows.size();
     *group_rows = G;
     *fused_l1 = fuse;
     return CLANE_OK;
@@ -93,7 +103,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_row_groups); cudaFree(plan->d_hub_groups); cudaFree(plan->d_P0);
+    cudaFree(plan->d_row_groups); cudaFree(plan->d_hub_groups); cudaFree(plan->d_hub_rows); cudaFree(plan->d_P0);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -131,23 +141,23 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->has_schedule = true;
     plan->row_lo = row_lo; plan->row_hi = row_hi;
     plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
-    const int32_t max_groups = (row_hi - row_lo + 1) / 1 + 1;
-    std::vector<int32_t> hub((size_t)max_groups), light((size_t)max_groups);
-    int32_t n_hub = 0, n_light = 0;
+    const size_t cap = (size_t)(row_hi - row_lo) + 1;
+    std::vector<int32_t> hub(cap), light(cap), hrows(cap);
+    int32_t n_hub = 0, n_light = 0, n_hrows = 0;
     rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, plan->hub_threshold, light.data(), &n_light, hub.data(),
-                              &n_hub, &plan->G, &plan->fuse);
+                              &n_hub, hrows.data(), &n_hrows, &plan->G, &plan->fuse);
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
-    hub.resize((size_t)n_hub);
-    light.resize((size_t)n_light);
     plan->n_groups = (row_hi - row_lo + plan->G - 1) / plan->G;
-    plan->n_hub_groups = (int32_t)hub.size();
-    plan->n_row_groups = (int32_t)light.size();
-    PLAN_CUDA(cudaMalloc(&plan->d_hub_groups, std::max<size_t>(hub.size(), 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaMalloc(&plan->d_row_groups, std::max<size_t>(light.size(), 1) * sizeof(int32_t)));
-    if (!hub.empty())
-        PLAN_CUDA(cudaMemcpy(plan->d_hub_groups, hub.data(), hub.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (!light.empty())
-        PLAN_CUDA(cudaMemcpy(plan->d_row_groups, light.data(), light.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    plan->n_hub_groups = n_hub;
+    plan->n_row_groups = n_light;
+    plan->n_hub_rows = n_hrows;
+    plan->nslab32 = (plan->ld + 31) / 32;
+    PLAN_CUDA(cudaMalloc(&plan->d_hub_groups, std::max<size_t>(n_hub, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_row_groups, std::max<size_t>(n_light, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
+    if (n_hub) PLAN_CUDA(cudaMemcpy(plan->d_hub_groups, hub.data(), n_hub * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (n_light) PLAN_CUDA(cudaMemcpy(plan->d_row_groups, light.data(), n_light * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (n_hrows) PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (plan->fuse) {
         const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);
         PLAN_CUDA(cudaMalloc(&plan->d_P0, p0));
@@ -164,7 +174,8 @@ int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_row_
     if (n_row_groups) *n_row_groups = plan->n_row_groups;
     if (n_hub_groups) *n_hub_groups = plan->n_hub_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    if (launches_per_sweep) *launches_per_sweep = 3;   // sweep, level-1, finish (fused or not)
+    // sweep, [hub-chunk fix-up], level-1, finish
+    if (launches_per_sweep) *launches_per_sweep = 3 + ((plan->fuse && plan->n_hub_groups > 0) ? 1 : 0);
     return CLANE_OK;
 }
 

@@ -13,9 +13,11 @@ struct clane_plan {
     int32_t nslab = 1;
     int32_t fuse = 0;           // L1 change fused into the sweep (d in {32, 64, 128}, whole graph)
     int32_t n_groups = 0;       // groups covering [row_lo, row_hi)
-    int32_t n_row_groups = 0, n_hub_groups = 0;
-    int32_t* d_row_groups = nullptr;
-    int32_t* d_hub_groups = nullptr;
+    int32_t n_row_groups = 0, n_hub_groups = 0, n_hub_rows = 0;
+    int32_t nslab32 = 1;        // 32-column slabs per row (hub role)
+    int32_t* d_row_groups = nullptr;   // groups with ordinary rows, by edge count descending
+    int32_t* d_hub_groups = nullptr;   // groups holding a hub row (fused mode: chunk partial fixed up from memory)
+    int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;

@@ -20,9 +20,12 @@
 //              8-neighbour block of one row): col/w staged through a per-warp shared-memory
 //              ring, the gathers of batch b+1 (8 x LDG.128 per lane) are in flight while
 //              batch b is reduced; X row and own Zcur row ride with the row's last batch.
-//   hub role : one CTA per (group with a row of degree > hub_threshold, slab).  The hub row
-//              is streamed through a 4-stage cp.async ring (32 neighbours x 512 B per stage)
-//              by all 8 warps; 4 consumer warps (lane = column) run the in-order chains.
+//   hub role : one CTA per (row of degree > hub_threshold, 32-column slab).  The neighbour rows'
+//              128-byte slab pieces are streamed through a 16-stage cp.async ring (32 neighbours
+//              per stage, 60 KB in flight) by all 8 warps; warp 0 (lane = column) runs the
+//              in-order chain out of shared memory.  A hub row is thus spread over d/32 SMs.
+//              Row-role warps skip hub rows; in fused mode the level-0 partial of a group that
+//              holds a hub row is recomputed from Znext/Zcur by k_fix_hub_chunks.
 #pragma once
 #include "common.cuh"
 
@@ -37,9 +40,10 @@ struct SweepParams {
     const int32_t* col;
     const float* w;
     float gamma;
-    const int32_t* hub_groups;
-    int n_hub_groups;
-    const int32_t* row_groups;  // sorted by edge count, descending
+    const int32_t* hub_rows;    // rows of degree > hub_threshold, degree-descending
+    int n_hub_rows;
+    int nslab32;                // 32-column slabs per row (hub role)
+    const int32_t* row_groups;  // sorted by edge count (hub rows excluded), descending
     int n_row_groups;
     int row_lo, row_hi;         // rows covered by the plan; groups are cut from row_lo
     int G;                      // rows per group (<= 32)
@@ -54,11 +58,13 @@ constexpr int kSweepThreads = 256;
 constexpr int kSweepWarps = 8;
 constexpr int kMetaRing = 64;                  // (col, w) pairs per warp
 constexpr int kHubStage = 32;                  // neighbours per ring stage
-constexpr int kHubStages = 4;
-constexpr int kHubRingFloats = kHubStages * kHubStage * 128;
-// dynamic shared memory: meta rings | hub ring | stash
+constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
+constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
+constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
+// dynamic shared memory: meta rings (row role) | hub ring | hub w ring
 constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaRing * sizeof(int2) +
-                                   (size_t)kHubRingFloats * sizeof(float) + (size_t)kStashFloats * sizeof(float);
+                                   (size_t)kHubRingFloats * sizeof(float) +
+                                   (size_t)kHubStages * kHubStage * sizeof(float);
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -169,6 +175,7 @@ __device__ void row_group_task(const SweepParams& p, int g, int slab, int lane, 
                 cur.a = __shfl_sync(kFull, rp_a, cur.i);
                 cur.k = __shfl_sync(kFull, rp_b, cur.i) - cur.a;
                 cur.pos = 0;
+                if (cur.k > p.hub_threshold) cur.pos = cur.k;   // hub rows belong to the hub role
             }
         }
         if (cur.i >= nrows) return false;
@@ -247,163 +254,106 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// one ordinary row of a hub group, one warp, no pipelining (a handful of rows per hub group)
-__device__ void simple_row(const SweepParams& p, int row, int slab, int lane, int i_in_group, float* stash) {
-    const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
-    const int c = slab * 128 + lane * 4;
-    const bool active = c < p.ld;
-    if (k == 0) {
-        if (p.fuse && active) *reinterpret_cast<float4*>(stash + i_in_group * p.d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
-    const int cc = active ? c : 0;
-    const bool blk = (c < (p.d / 16) * 16) && (k >= 8);
-    const float* __restrict__ zb = p.Zc + cc;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = 0; base < k; base += 32) {
-        const int my = base + lane;
-        int cj = 0;
-        float wj = 0.0f;
-        if (my < k) { cj = __ldg(p.col + a + my); wj = __ldg(p.w + a + my); }
-        const int cnt = min(32, k - base);
-        int o = 0;
-        for (; o + 8 <= cnt; o += 8) {
-            float4 z[8];
-            float ww[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = __shfl_sync(kFull, cj, o + i);
-                ww[i] = __shfl_sync(kFull, wj, o + i);
-                z[i] = ldg4(zb + (size_t)r * p.ld);
-            }
-            if (blk) blocked8x4(acc, ww, z);
-            else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) fma4(ww[i], z[i], acc);
-            }
-        }
-        const int m = cnt - o;
-        if (m > 0) {
-            float4 z[7];
-            float ww[7];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int r = __shfl_sync(kFull, cj, (o + i) & 31);
-                ww[i] = __shfl_sync(kFull, wj, (o + i) & 31);
-                if (i < m) z[i] = ldg4(zb + (size_t)r * p.ld);
-            }
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-                if (i < m) fma4(ww[i], z[i], acc);
-        }
-    }
-    if (active) {
-        const size_t off = (size_t)row * p.ld + c;
-        const float4 out = finish_row(ld_stream4(p.X + off), acc, p.gamma);
-        *reinterpret_cast<float4*>(p.Zn + off) = out;
-        if (p.fuse) *reinterpret_cast<float4*>(stash + i_in_group * p.d + c) = absdiff4(out, ldg4(p.Zc + off));
-    }
-}
-
-// the hub row itself: all 8 warps feed the ring, warps 0-3 consume (lane = one column)
-__device__ void hub_row(const SweepParams& p, int row, int slab, int i_in_group, float* ringf, float* stash) {
+// One (hub row, 32-column slab): all 8 warps copy, warp 0 reduces.
+__device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
     const int nst = (k + kHubStage - 1) / kHubStage;
-    const int c4 = slab * 128 + lane * 4;            // producer view: one float4 per lane
-    const bool pact = c4 < p.ld;
-    const int ccol = slab * 128 + warp * 32 + lane;  // consumer view (warps 0-3): one column per lane
-    const bool blk = ccol < (p.d / 16) * 16;         // k > hub_threshold >= 8
-    float acc = 0.0f;
+    // copy view: this lane moves 16 bytes (4 columns) of neighbour `nb` of every stage
+    const int nb = warp * 4 + (lane >> 3);
+    const int pcol = slab32 * 32 + (lane & 7) * 4;
+    const bool pact = pcol < p.ld;
+    // reduce view (warp 0): one column per lane
+    const int ccol = slab32 * 32 + lane;
+    const bool blk = ccol < (p.d / 16) * 16;           // k > hub_threshold >= 8
 
-    // producers: neighbours s*32 + warp*4 + j of stage s; the column ids are fetched one stage ahead
-    int cnext = 0;
-    float wnext = 0.0f;
-    if (lane < k) { cnext = __ldg(p.col + a + lane); wnext = __ldg(p.w + a + lane); }
-    float wq[kHubStages - 1];   // w of the stages in flight, consumed in order
-    auto issue = [&](int s, int slot) {
-        // cnext/wnext hold stage s; remember w for the consumers, refill for stage s + 1
-        const int cidx = cnext;
-        wq[slot] = wnext;
-        const int nx = (s + 1) * kHubStage + lane;
-        cnext = 0; wnext = 0.0f;
-        if (nx < k) { cnext = __ldg(p.col + a + nx); wnext = __ldg(p.w + a + nx); }
-        float* dst = ringf + (size_t)(s % kHubStages) * kHubStage * 128;
+    int cq[kHubMeta];
+    float wq[kHubMeta];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t = warp * 4 + j;
-            const int r = __shfl_sync(kFull, cidx, t);
-            if (s * kHubStage + t < k && pact) cp_async16(dst + t * 128 + lane * 4, p.Zc + (size_t)r * p.ld + c4);
-        }
+    for (int i = 0; i < kHubMeta; ++i) {
+        const int idx = i * kHubStage + nb, widx = i * kHubStage + lane;
+        cq[i] = idx < k ? __ldg(p.col + a + idx) : 0;
+        wq[i] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
+    }
+    int si = 0;                                         // next stage to issue
+    auto issue = [&]() {
+        const int slot = si % kHubStages;
+        if (si * kHubStage + nb < k && pact)
+            cp_async16(ringf + (size_t)slot * kHubStage * 32 + nb * 32 + (lane & 7) * 4,
+                       p.Zc + (size_t)cq[0] * p.ld + pcol);
+        if (warp == 0) wsm[slot * kHubStage + lane] = wq[0];
         cp_async_commit();
+#pragma unroll
+        for (int i = 0; i + 1 < kHubMeta; ++i) { cq[i] = cq[i + 1]; wq[i] = wq[i + 1]; }
+        const int idx = (si + kHubMeta) * kHubStage + nb, widx = (si + kHubMeta) * kHubStage + lane;
+        cq[kHubMeta - 1] = idx < k ? __ldg(p.col + a + idx) : 0;
+        wq[kHubMeta - 1] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
+        ++si;
     };
 
-    // prologue: kHubStages - 1 stages in flight
-#pragma unroll
     for (int s = 0; s < kHubStages - 1; ++s) {
-        if (s < nst) issue(s, s);
+        if (s < nst) issue();
         else cp_async_commit();
     }
+    float acc = 0.0f;
     for (int s = 0; s < nst; ++s) {
         cp_async_wait<kHubStages - 2>();
-        __syncthreads();                               // stage s landed for everyone; stage s-1 consumed
-        const float wcur = wq[0];
-#pragma unroll
-        for (int q = 0; q + 1 < kHubStages - 1; ++q) wq[q] = wq[q + 1];
-        if (s + kHubStages - 1 < nst) issue(s + kHubStages - 1, kHubStages - 2);
+        __syncthreads();                               // stage s landed for everyone; stage s-1 reduced
+        if (si < nst) issue();
         else cp_async_commit();
-        if (warp < 4) {
-            const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 128 + warp * 32 + lane;
+        if (warp == 0) {
+            const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + (s % kHubStages) * kHubStage);
             const int cnt = min(kHubStage, k - s * kHubStage);
             int o = 0;
             for (; o + 8 <= cnt; o += 8) {
-                float ww[8], z[8];
+                const float4 wa = w4[o >> 2], wb = w4[(o >> 2) + 1];
+                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                float z[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { ww[i] = __shfl_sync(kFull, wcur, o + i); z[i] = src[(o + i) * 128]; }
+                for (int i = 0; i < 8; ++i) z[i] = src[(o + i) * 32];
                 if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
                 }
             }
-            for (; o < cnt; ++o) acc = ffma(__shfl_sync(kFull, wcur, o), src[o * 128], acc);
+            for (; o < cnt; ++o) acc = ffma(wsm[(s % kHubStages) * kHubStage + o], src[o * 32], acc);
         }
     }
     cp_async_wait<0>();
-    if (warp < 4 && ccol < p.ld) {
+    if (warp == 0 && ccol < p.ld) {
         const size_t off = (size_t)row * p.ld + ccol;
-        const float out = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
-        p.Zn[off] = out;
-        if (p.fuse) stash[i_in_group * p.d + ccol] = fabsf(fsub(out, __ldg(p.Zc + off)));
+        p.Zn[off] = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
     }
-    __syncthreads();   // ring free for the next hub row
 }
 
-__device__ void hub_group_task(const SweepParams& p, int g, int slab, float* ringf, float* stash) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r0 = p.row_lo + g * p.G;
-    const int nrows = min(p.G, p.row_hi - r0);
-    // ordinary rows first, one warp each
-    for (int i = warp; i < nrows; i += kSweepWarps) {
-        const int row = r0 + i;
-        const int k = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
-        if (k <= p.hub_threshold) simple_row(p, row, slab, lane, i, stash);
-    }
-    for (int i = 0; i < nrows; ++i) {
-        const int row = r0 + i;
-        const int k = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
-        if (k > p.hub_threshold) hub_row(p, row, slab, i, ringf, stash);
-    }
-    if (p.fuse) {
-        __syncthreads();
-        if (warp == 0) {
-            // the group is one level-0 chunk: nrows * d / 32 cascade rows, summed in order per lane
-            const int ncr = nrows * (p.d >> 5);
-            float acc = 0.0f;
-            for (int r = 0; r < ncr; ++r) acc = fadd(acc, stash[r * 32 + lane]);
-            p.P0[(size_t)g * 32 + lane] = acc;
+// Fused mode: the level-0 partial of every group that holds a hub row, from memory.
+__global__ void __launch_bounds__(256)
+k_fix_hub_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, int n, int G,
+                 const int32_t* __restrict__ hub_groups, int n_hub_groups, float* __restrict__ P0,
+                 const clane_patience* __restrict__ st) {
+    if (st != nullptr && st->stop) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= n_hub_groups) return;
+    const int g = __ldg(hub_groups + i);
+    const int r0 = g * G, nrows = min(G, n - r0);
+    const int ncr = nrows * (d >> 5);                   // cascade rows of the chunk (ld == d here)
+    const size_t base = (size_t)r0 * d + lane;
+    float acc = 0.0f;
+    for (int r = 0; r < ncr; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const size_t t = base + (size_t)(r + u) * 32;
+            v[u] = (r + u < ncr) ? fabsf(fsub(__ldcg(Zn + t), __ldg(Zc + t))) : 0.0f;
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (r + u < ncr) acc = fadd(acc, v[u]);
     }
+    P0[(size_t)g * 32 + lane] = acc;
 }
 
 __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(SweepParams p) {
@@ -411,12 +361,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(SweepParams p) {
     if (p.st != nullptr && p.st->stop) return;
     int2* rings = reinterpret_cast<int2*>(smem);
     float* ringf = reinterpret_cast<float*>(smem + (size_t)kSweepWarps * kMetaRing * sizeof(int2));
-    float* stash = ringf + kHubRingFloats;
+    float* wsm = ringf + kHubRingFloats;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_hub_ctas = p.n_hub_groups * p.nslab;
+    const int n_hub_ctas = p.n_hub_rows * p.nslab32;
     if ((int)blockIdx.x < n_hub_ctas) {
-        const int hg = blockIdx.x / p.nslab, slab = blockIdx.x - hg * p.nslab;
-        hub_group_task(p, __ldg(p.hub_groups + hg), slab, ringf, stash);
+        const int hr = blockIdx.x / p.nslab32;
+        hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm);
         return;
     }
     const int64_t task = (int64_t)(blockIdx.x - n_hub_ctas) * kSweepWarps + warp;

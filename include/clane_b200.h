@@ -77,17 +77,22 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
  *   - rows are cut into groups of `group_rows` consecutive rows (one level-0 chunk of the
  *     ATen cascade sum when d is 32, 64 or 128 and the plan covers all rows -- then the L1
  *     change is fused into the sweep; otherwise 8 rows and the L1 change is a second pass);
- *   - groups holding a row of degree > hub_threshold are "hub groups" (one CTA each, the hub
- *     row streamed through a shared-memory ring); the others are sorted by edge count,
- *     descending, and handed to warps eight at a time; groups of sinks only are dropped
- *     (embedder.py:88-89: such rows are never updated).
+ *   - rows of degree > hub_threshold are "hub rows": one CTA per 32-column slab of the row,
+ *     the neighbour rows streamed through a shared-memory ring, longest first;
+ *   - the groups are sorted by the edge count of their ordinary rows, descending, and handed
+ *     to warps eight at a time; groups of sinks only are dropped (embedder.py:88-89: such
+ *     rows are never updated).
  * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
 typedef struct clane_plan clane_plan;
 /* The schedule alone, on the host (what clane_plan_create uploads): group ids relative to
- * row_lo; both outputs have capacity row_hi - row_lo + 1. */
+ * row_lo, row ids absolute; the three outputs have capacity row_hi - row_lo + 1.
+ *   h_row_groups: groups with ordinary rows, by their edge count (hub rows excluded) descending
+ *   h_hub_groups: groups holding at least one hub row, ascending
+ *   h_hub_rows  : rows of degree > hub_threshold, degree-descending */
 int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
                          int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
-                         int32_t* n_hub_groups, int32_t* group_rows, int32_t* fused_l1);
+                         int32_t* n_hub_groups, int32_t* h_hub_rows, int32_t* n_hub_rows, int32_t* group_rows,
+                         int32_t* fused_l1);
 int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
                       int32_t row_lo, int32_t row_hi, int32_t hub_threshold);
 int clane_plan_destroy(clane_plan* plan);

@@ -142,11 +142,12 @@ def test_csr_rejects_out_of_range():
 def group_schedule(rowptr, n, d, lo, hi, hub=256):
     L = _lib.lib()
     cap = hi - lo + 1
-    rg, hg = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
-    nr, nh, G, fu = (ctypes.c_int32() for _ in range(4))
+    rg, hg, hr = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    nr, nh, nhr, G, fu = (ctypes.c_int32() for _ in range(5))
     _lib.check(L.clane_group_schedule(rowptr.ctypes.data, n, d, lo, hi, hub, rg.ctypes.data, ctypes.byref(nr),
-                                      hg.ctypes.data, ctypes.byref(nh), ctypes.byref(G), ctypes.byref(fu)))
-    return rg[:nr.value], hg[:nh.value], G.value, bool(fu.value)
+                                      hg.ctypes.data, ctypes.byref(nh), hr.ctypes.data, ctypes.byref(nhr),
+                                      ctypes.byref(G), ctypes.byref(fu)))
+    return rg[:nr.value], hg[:nh.value], hr[:nhr.value], G.value, bool(fu.value)
 
 
 def test_group_schedule_degree_sorted_row_blocks():
@@ -155,25 +156,29 @@ def test_group_schedule_degree_sorted_row_blocks():
     deg = np.minimum((rng.pareto(1.0, n) * 3).astype(np.int64), n - 1)
     deg[:5] = [0, 1, 33, 257, 1500]
     deg[64:80] = 0                                    # two whole groups of sinks
+    deg[96:104] = [0, 0, 0, 300, 0, 0, 0, 0]          # a group whose only non-sink row is a hub
     src = np.repeat(np.arange(n), deg)
     dst = np.concatenate([rng.permutation(n)[:k] for k in deg])
     g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
     k = np.diff(g._rowptr)
     for d, lo, hi in [(100, 0, n), (128, 0, n), (128, 500, 1700), (1433, 0, n)]:
-        rg, hg, G, fused = group_schedule(g._rowptr, n, d, lo, hi)
+        rg, hg, hr, G, fused = group_schedule(g._rowptr, n, d, lo, hi)
         assert fused == (d == 128 and lo == 0 and hi == n)
         assert G == (4 if fused else 8)               # n*d < 2^24: level step 16 -> 512-element chunks
         ng = (hi - lo + G - 1) // G
-        work = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].sum() for i in range(ng)])
+        kk = np.where(k > 256, 0, k)                  # hub rows are not part of a group's own work
+        work = np.array([kk[lo + i * G: min(lo + (i + 1) * G, hi)].sum() for i in range(ng)])
         hubby = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].max() > 256 for i in range(ng)])
-        assert sorted(hg.tolist()) == np.nonzero(hubby)[0].tolist()
-        assert sorted(rg.tolist()) == np.nonzero(~hubby & (work > 0))[0].tolist()    # all-sink groups dropped
-        assert np.all(np.diff(work[rg]) <= 0) and np.all(np.diff(work[hg]) <= 0)       # longest first
+        assert hg.tolist() == np.nonzero(hubby)[0].tolist()
+        assert sorted(rg.tolist()) == np.nonzero(work > 0)[0].tolist()                 # all-sink groups dropped
+        assert np.all(np.diff(work[rg]) <= 0)                                           # longest first
+        want_hr = [v for v in range(lo, hi) if k[v] > 256]
+        assert sorted(hr.tolist()) == want_hr and np.all(np.diff(k[hr]) <= 0)
     # a graph large enough for level step 32: 1024-element chunks = 8 rows of 128
     rp = np.zeros(140001, np.int32)
-    assert group_schedule(rp, 140000, 128, 0, 140000)[2:] == (8, True)
-    assert group_schedule(rp, 140000, 64, 0, 140000)[2:] == (8, True)      # 8.96M elements: step 16, 512 / 64
-    assert group_schedule(rp, 140000, 100, 0, 140000)[2:] == (8, False)
+    assert group_schedule(rp, 140000, 128, 0, 140000)[3:] == (8, True)
+    assert group_schedule(rp, 140000, 64, 0, 140000)[3:] == (8, True)      # 8.96M elements: step 16, 512 / 64
+    assert group_schedule(rp, 140000, 100, 0, 140000)[3:] == (8, False)
 
 
 def test_cascade_shape():
@@ -208,7 +213,7 @@ def test_kernel_entry_points_reject_bad_arguments_without_a_device():
     assert L.clane_scores_cosine(0, 0, 0, 0, 0, 1, 0, 0, 0) == -1
     assert L.clane_l1_diff(0, 0, 0, 0, 0) == -1 and L.clane_plan_info(0, None, None, None, None, None) == -1
     assert L.clane_plan_destroy(0) == 0
-    assert L.clane_group_schedule(0, 1, 1, 0, 1, 256, 0, None, 0, None, None, None) == -1
+    assert L.clane_group_schedule(0, 1, 1, 0, 1, 256, 0, None, 0, None, 0, None, None, None) == -1
 
 
 def test_no_cpu_fallback_without_cuda(data_root):
