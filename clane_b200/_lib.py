@@ -35,12 +35,12 @@ SIGNATURES = {
     "clane_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "clane_padded_ld": (C.c_int32, [C.c_int32]),
     "clane_csr_from_edges": (C.c_int64, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
-    "clane_group_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, c_i32p, c_vp,
-                                       c_i32p, c_vp, c_i32p, c_i32p, c_i32p]),
+    "clane_group_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp,
+                                       c_i32p, c_vp, c_i32p, c_vp, c_i32p, c_i32p, c_i32p]),
     "clane_plan_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, C.c_int32, C.c_int32,
                                     C.c_int32]),
     "clane_plan_destroy": (C.c_int, [c_vp]),
-    "clane_plan_info": (C.c_int, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
+    "clane_plan_info": (C.c_int, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
     "clane_cascade_shape": (C.c_int, [C.c_int64, c_i64p, c_i64p]),
     "clane_edge_rows": (C.c_int, [c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "clane_scores_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp, c_vp]),
@@ -123,9 +123,10 @@ class Plan:
         hi = self.n if row_hi is None else int(row_hi)
         check(lib().clane_plan_create(C.byref(self.handle), self.n, self.e, self.d, rp, int(row_lo), hi,
                                       int(hub_threshold)), "clane_plan_create")
-        g, nr, nh, fu, la = (C.c_int32() for _ in range(5))
-        check(lib().clane_plan_info(self.handle, C.byref(g), C.byref(nr), C.byref(nh), C.byref(fu), C.byref(la)))
-        self.group_rows, self.n_row_groups, self.n_hub_groups = g.value, nr.value, nh.value
+        g, ns, nh, nf, fu, la = (C.c_int32() for _ in range(6))
+        check(lib().clane_plan_info(self.handle, C.byref(g), C.byref(ns), C.byref(nh), C.byref(nf), C.byref(fu),
+                                    C.byref(la)))
+        self.group_rows, self.n_spans, self.n_hub_rows, self.n_fix_groups = g.value, ns.value, nh.value, nf.value
         self.fused_l1, self.launches_per_sweep = bool(fu.value), la.value
 
     def __del__(self):

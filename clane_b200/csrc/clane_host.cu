@@ -54,47 +54,62 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
 // plan: degree-sorted row blocks + cascade scratch
 // ---------------------------------------------------------------------------------------------
 int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
-                         int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
-                         int32_t* n_hub_groups, int32_t* h_hub_rows, int32_t* n_hub_rows, int32_t* group_rows,
-                         int32_t* fused_l1) {
+                         int32_t hub_threshold, int32_t span_edges, int32_t* h_span_row, int32_t* h_span_meta,
+                         int32_t* n_spans, int32_t* h_fix_groups, int32_t* n_fix_groups, int32_t* h_hub_rows,
+                         int32_t* n_hub_rows, int32_t* group_rows, int32_t* fused_l1) {
     if (!h_rowptr || n < 0 || d < 1 || row_lo < 0 || row_hi > n || row_lo > row_hi || hub_threshold < 8 ||
-        !h_row_groups || !n_row_groups || !h_hub_groups || !n_hub_groups || !h_hub_rows || !n_hub_rows ||
-        !group_rows || !fused_l1)
+        span_edges < 8 || !h_span_row || !h_span_meta || !n_spans || !h_fix_groups || !n_fix_groups || !h_hub_rows ||
+        !n_hub_rows || !group_rows || !fused_l1)
         return CLANE_EINVAL;
     // fused L1: a group of G rows is exactly one level-0 chunk of the cascade over n*d
     clane::CascadeShape sh = clane::cascade_shape((int64_t)n * d);
     const int64_t chunk = sh.step * 32;
     int32_t G = 8, fuse = 0;
-    if ((d == 32 || d == 64 || d == 128) && row_lo == 0 && row_hi == n && chunk % d == 0 && chunk / d <= 32) {
+    if ((d == 32 || d == 64 || d == 128) && row_lo == 0 && row_hi == n && chunk % d == 0 && chunk / d <= 32 &&
+        chunk <= 1024) {   // a warp parks one chunk of |delta| in 4 KB of shared memory
         G = (int32_t)(chunk / d);
         fuse = 1;
     }
     const int32_t n_groups = (row_hi - row_lo + G - 1) / G;
-    std::vector<int32_t> hub_groups, row_groups, hub_rows;
-    std::vector<int64_t> work((size_t)std::max(n_groups, 1), 0);
+    struct Span { int32_t row, nrows, direct; int64_t work; };
+    std::vector<Span> spans;
+    std::vector<int32_t> fix, hub_rows;
     for (int32_t g = 0; g < n_groups; ++g) {
         const int32_t r0 = row_lo + g * G, r1 = std::min(r0 + G, row_hi);
         bool has_hub = false;
+        const size_t first_span = spans.size();
+        Span cur{r0, 0, 0, 0};
         for (int32_t v = r0; v < r1; ++v) {
-            const int32_t k = h_rowptr[v + 1] - h_rowptr[v];
-            if (k > hub_threshold) { has_hub = true; hub_rows.push_back(v); }
-            else work[g] += k;
+            int32_t k = h_rowptr[v + 1] - h_rowptr[v];
+            if (k > hub_threshold) { has_hub = true; hub_rows.push_back(v); k = 0; }
+            if (cur.work > 0 && cur.work + k > span_edges) {   // close the span before this row
+                spans.push_back(cur);
+                cur = Span{v, 0, 0, 0};
+            }
+            cur.nrows++;
+            cur.work += k;
         }
-        if (has_hub) hub_groups.push_back(g);
-        if (work[g] > 0) row_groups.push_back(g);     // groups of sinks only are never updated (embedder.py:88-89)
+        if (cur.work > 0) spans.push_back(cur);
+        const size_t made = spans.size() - first_span;
+        // one span covering the whole group and no hub row: the warp produces the chunk partial itself
+        if (made == 1 && !has_hub && spans.back().row == r0 && spans.back().nrows == r1 - r0) spans.back().direct = 1;
+        else if (fuse && (made > 0 || has_hub)) fix.push_back(g);
+        // groups of sinks only are never updated (embedder.py:88-89): no span, partial stays +0
     }
-    auto by_work_desc = [&](int32_t x, int32_t y) { return work[x] != work[y] ? work[x] > work[y] : x < y; };
+    std::stable_sort(spans.begin(), spans.end(), [](const Span& x, const Span& y) { return x.work > y.work; });
     auto by_degree_desc = [&](int32_t x, int32_t y) {
         const int32_t kx = h_rowptr[x + 1] - h_rowptr[x], ky = h_rowptr[y + 1] - h_rowptr[y];
         return kx != ky ? kx > ky : x < y;
     };
-    std::sort(row_groups.begin(), row_groups.end(), by_work_desc);
     std::sort(hub_rows.begin(), hub_rows.end(), by_degree_desc);
-    std::copy(hub_groups.begin(), hub_groups.end(), h_hub_groups);
-    std::copy(row_groups.begin(), row_groups.end(), h_row_groups);
+    for (size_t i = 0; i < spans.size(); ++i) {
+        h_span_row[i] = spans[i].row;
+        h_span_meta[i] = spans[i].nrows | (spans[i].direct << 8);
+    }
+    std::copy(fix.begin(), fix.end(), h_fix_groups);
     std::copy(hub_rows.begin(), hub_rows.end(), h_hub_rows);
-    *n_hub_groups = (int32_t)hub_groups.size();
-    *n_row_groups = (int32_t)row_groups.size();
+    *n_spans = (int32_t)spans.size();
+    *n_fix_groups = (int32_t)fix.size();
     *n_hub_rows = (int32_t)hub_rows.size();
     *group_rows = G;
     *fused_l1 = fuse;
@@ -103,7 +118,8 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_row_groups); cudaFree(plan->d_hub_groups); cudaFree(plan->d_hub_rows); cudaFree(plan->d_P0);
+    cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_P0);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -125,7 +141,8 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     clane_plan* plan = new (std::nothrow) clane_plan();
     if (!plan) return (int)cudaErrorMemoryAllocation;
     plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
-    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 256;
+    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 128;
+    plan->span_edges = 128;
     plan->nslab = (plan->ld + 127) / 128;
 
     // cascade scratch: L1 over n*d (one quantity) and the norms over e*d (two quantities)
@@ -142,21 +159,25 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->row_lo = row_lo; plan->row_hi = row_hi;
     plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
     const size_t cap = (size_t)(row_hi - row_lo) + 1;
-    std::vector<int32_t> hub(cap), light(cap), hrows(cap);
-    int32_t n_hub = 0, n_light = 0, n_hrows = 0;
-    rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, plan->hub_threshold, light.data(), &n_light, hub.data(),
-                              &n_hub, hrows.data(), &n_hrows, &plan->G, &plan->fuse);
+    std::vector<int32_t> srow(cap), smeta(cap), fix(cap), hrows(cap);
+    int32_t n_spans = 0, n_fix = 0, n_hrows = 0;
+    rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, plan->hub_threshold, plan->span_edges, srow.data(),
+                              smeta.data(), &n_spans, fix.data(), &n_fix, hrows.data(), &n_hrows, &plan->G, &plan->fuse);
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
     plan->n_groups = (row_hi - row_lo + plan->G - 1) / plan->G;
-    plan->n_hub_groups = n_hub;
-    plan->n_row_groups = n_light;
+    plan->n_spans = n_spans;
+    plan->n_fix_groups = n_fix;
     plan->n_hub_rows = n_hrows;
     plan->nslab32 = (plan->ld + 31) / 32;
-    PLAN_CUDA(cudaMalloc(&plan->d_hub_groups, std::max<size_t>(n_hub, 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaMalloc(&plan->d_row_groups, std::max<size_t>(n_light, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_span_row, std::max<size_t>(n_spans, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_span_meta, std::max<size_t>(n_spans, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
-    if (n_hub) PLAN_CUDA(cudaMemcpy(plan->d_hub_groups, hub.data(), n_hub * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (n_light) PLAN_CUDA(cudaMemcpy(plan->d_row_groups, light.data(), n_light * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (n_spans) {
+        PLAN_CUDA(cudaMemcpy(plan->d_span_row, srow.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PLAN_CUDA(cudaMemcpy(plan->d_span_meta, smeta.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (n_fix) PLAN_CUDA(cudaMemcpy(plan->d_fix_groups, fix.data(), n_fix * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_hrows) PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (plan->fuse) {
         const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);
@@ -167,15 +188,16 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     return CLANE_OK;
 }
 
-int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_row_groups, int32_t* n_hub_groups,
-                    int32_t* fused_l1, int32_t* launches_per_sweep) {
+int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_spans, int32_t* n_hub_rows,
+                    int32_t* n_fix_groups, int32_t* fused_l1, int32_t* launches_per_sweep) {
     if (!plan) return CLANE_EINVAL;
     if (group_rows) *group_rows = plan->G;
-    if (n_row_groups) *n_row_groups = plan->n_row_groups;
-    if (n_hub_groups) *n_hub_groups = plan->n_hub_groups;
+    if (n_spans) *n_spans = plan->n_spans;
+    if (n_hub_rows) *n_hub_rows = plan->n_hub_rows;
+    if (n_fix_groups) *n_fix_groups = plan->n_fix_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    // sweep, [hub-chunk fix-up], level-1, finish
-    if (launches_per_sweep) *launches_per_sweep = 3 + ((plan->fuse && plan->n_hub_groups > 0) ? 1 : 0);
+    // sweep, [chunk fix-up], level-1, finish
+    if (launches_per_sweep) *launches_per_sweep = 3 + ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
     return CLANE_OK;
 }
 

@@ -283,14 +283,14 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
     p.rowptr = d_rowptr; p.col = d_col; p.w = d_w; p.gamma = gamma;
     p.hub_rows = plan->d_hub_rows; p.n_hub_rows = plan->n_hub_rows; p.nslab32 = plan->nslab32;
-    p.row_groups = plan->d_row_groups; p.n_row_groups = plan->n_row_groups;
+    p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.n_spans = plan->n_spans;
     p.row_lo = plan->row_lo; p.row_hi = plan->row_hi;
     p.G = plan->G; p.nslab = plan->nslab;
     p.fuse = (plan->fuse && want_l1) ? 1 : 0;
     p.P0 = plan->d_P0;
     p.hub_threshold = plan->hub_threshold;
     p.st = d_state;
-    const int64_t row_ctas = ((int64_t)plan->n_row_groups * plan->nslab + kSweepWarps - 1) / kSweepWarps;
+    const int64_t row_ctas = ((int64_t)plan->n_spans * plan->nslab + kSweepWarps - 1) / kSweepWarps;
     const int64_t grid = (int64_t)plan->n_hub_rows * plan->nslab32 + row_ctas;
     if (grid > 0) {
         k_sweep<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(p);
@@ -301,9 +301,9 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     ElemAbsDiff el{d_Znext, d_Zcur, plan->d, plan->ld};
     if (p.fuse) {
         CascadeShape sh = cascade_shape(n_elems);
-        if (plan->n_hub_groups > 0) {
-            k_fix_hub_chunks<<<(unsigned)(((int64_t)plan->n_hub_groups * 32 + 255) / 256), 256, 0, st>>>(
-                d_Znext, d_Zcur, plan->d, plan->n, plan->G, plan->d_hub_groups, plan->n_hub_groups, plan->d_P0, d_state);
+        if (plan->n_fix_groups > 0) {
+            k_fix_chunks<<<(unsigned)(((int64_t)plan->n_fix_groups * 32 + 255) / 256), 256, 0, st>>>(
+                d_Znext, d_Zcur, plan->d, plan->n, plan->G, plan->d_fix_groups, plan->n_fix_groups, plan->d_P0, d_state);
             CLANE_LAUNCH_CHECK();
         }
         if (sh.n1_nodes > 0) {

@@ -7,16 +7,18 @@ struct clane_plan {
     int64_t e = 0;
     int32_t row_lo = 0, row_hi = 0;
     int64_t edge_lo = 0, edge_hi = 0;   // rowptr[row_lo], rowptr[row_hi]
-    int32_t hub_threshold = 256;
+    int32_t hub_threshold = 128;
     bool has_schedule = false;
     int32_t G = 8;              // rows per group
     int32_t nslab = 1;
     int32_t fuse = 0;           // L1 change fused into the sweep (d in {32, 64, 128}, whole graph)
     int32_t n_groups = 0;       // groups covering [row_lo, row_hi)
-    int32_t n_row_groups = 0, n_hub_groups = 0, n_hub_rows = 0;
+    int32_t span_edges = 128;   // edge budget of a span
+    int32_t n_spans = 0, n_fix_groups = 0, n_hub_rows = 0;
     int32_t nslab32 = 1;        // 32-column slabs per row (hub role)
-    int32_t* d_row_groups = nullptr;   // groups with ordinary rows, by edge count descending
-    int32_t* d_hub_groups = nullptr;   // groups holding a hub row (fused mode: chunk partial fixed up from memory)
+    int32_t* d_span_row = nullptr;     // spans (runs of ordinary rows inside one group), by edge count descending
+    int32_t* d_span_meta = nullptr;    // rows | direct << 8
+    int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)

@@ -16,16 +16,16 @@
 // level-0 chunk of the ATen cascade sum, so the warp (or CTA) that owns a group also produces
 // that chunk's 32-lane partial of sum|Znext - Zcur| in the reference's order (fused L1).
 //
-//   row role : one warp per (group, 128-column slab).  Software pipeline over "batches" (one
-//              8-neighbour block of one row): col/w staged through a per-warp shared-memory
-//              ring, the gathers of batch b+1 (8 x LDG.128 per lane) are in flight while
-//              batch b is reduced; X row and own Zcur row ride with the row's last batch.
+//   row role : one warp per (span, 128-column slab); a span is a run of rows of one group with
+//              a bounded edge count.  Per "batch" (one 8-neighbour block of one row): col/w from
+//              a per-warp shared-memory ring, 8 x LDG.128 gathers per lane, in-order reduction;
+//              the X row and the own Zcur row ride with the row's last batch.
 //   hub role : one CTA per (row of degree > hub_threshold, 32-column slab).  The neighbour rows'
 //              128-byte slab pieces are streamed through a 16-stage cp.async ring (32 neighbours
 //              per stage, 60 KB in flight) by all 8 warps; warp 0 (lane = column) runs the
 //              in-order chain out of shared memory.  A hub row is thus spread over d/32 SMs.
 //              Row-role warps skip hub rows; in fused mode the level-0 partial of a group that
-//              holds a hub row is recomputed from Znext/Zcur by k_fix_hub_chunks.
+//              holds a hub row (or was cut into several spans) is recomputed by k_fix_chunks.
 #pragma once
 #include "common.cuh"
 
@@ -43,8 +43,9 @@ struct SweepParams {
     const int32_t* hub_rows;    // rows of degree > hub_threshold, degree-descending
     int n_hub_rows;
     int nslab32;                // 32-column slabs per row (hub role)
-    const int32_t* row_groups;  // sorted by edge count (hub rows excluded), descending
-    int n_row_groups;
+    const int32_t* span_row;    // first row of each span; spans sorted by edge count, descending
+    const int32_t* span_meta;   // rows in the span | (1 << 8 if the span is a whole fused chunk)
+    int n_spans;
     int row_lo, row_hi;         // rows covered by the plan; groups are cut from row_lo
     int G;                      // rows per group (<= 32)
     int nslab;                  // 128-column slabs per row
@@ -61,10 +62,12 @@ constexpr int kHubStage = 32;                  // neighbours per ring stage
 constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
-// dynamic shared memory: meta rings (row role) | hub ring | hub w ring
+constexpr int kWarpStash = 1024;               // |delta| of one fused group (G*d <= 1024 floats) per warp
+// dynamic shared memory: meta rings (row role) | hub ring + hub w ring, reused as the row role's stashes
 constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaRing * sizeof(int2) +
                                    (size_t)kHubRingFloats * sizeof(float) +
                                    (size_t)kHubStages * kHubStage * sizeof(float);
+static_assert((size_t)kSweepWarps * kWarpStash <= (size_t)kHubRingFloats, "stashes alias the hub ring");
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -100,147 +103,94 @@ __device__ __forceinline__ float4 absdiff4(const float4& a, const float4& b) {
     return make_float4(fabsf(fsub(a.x, b.x)), fabsf(fsub(a.y, b.y)), fabsf(fsub(a.z, b.z)), fabsf(fsub(a.w, b.w)));
 }
 
-// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane
-// m owns cascade lane m: the row is d/32 consecutive cascade rows, taken in order.
-__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane) {
-    const int sub = lane >> 2, comp = lane & 3;
-    for (int seg = 0; seg < nseg; ++seg) {
-        const int src = seg * 8 + sub;
-        const float v0 = __shfl_sync(kFull, dl.x, src), v1 = __shfl_sync(kFull, dl.y, src);
-        const float v2 = __shfl_sync(kFull, dl.z, src), v3 = __shfl_sync(kFull, dl.w, src);
-        const float v = comp == 0 ? v0 : (comp == 1 ? v1 : (comp == 2 ? v2 : v3));
-        chunk_acc = fadd(chunk_acc, v);
-    }
-    return chunk_acc;
-}
-
 // ------------------------------------------------------------------------------------------
-// row role
+// row role: one warp per (span, 128-column slab)
 // ------------------------------------------------------------------------------------------
-struct BatchInfo {   // warp-uniform description of one staged batch
-    int row;         // absolute row id
-    int m;           // neighbours in the batch (1..8)
-    int first;       // first batch of its row
-    int last;        // last batch of its row
-};
-
-struct RowCursor {
-    int i;       // row index inside the group
-    int a;       // first edge of that row
-    int k;       // its degree
-    int pos;     // next neighbour position
-};
-
-__device__ void row_group_task(const SweepParams& p, int g, int slab, int lane, int2* ring) {
-    const int r0 = p.row_lo + g * p.G;
-    const int nrows = min(p.G, p.row_hi - r0);
+// A span is a run of consecutive rows of one group with a bounded edge count (hub rows are
+// skipped).  Per batch (one 8-neighbour block of one row) the warp reads (col, w) from its
+// shared-memory ring, issues up to 8 independent 512-byte gathers (LDG.128 per lane) and
+// reduces them in the reference's order; latency is hidden by the other resident warps
+// (24 per SM), not by software pipelining, which keeps the kernel at <= 85 registers.
+// Unused slots of a short batch keep their previous (finite) register contents and get
+// weight 0: fma(0, z, acc) == acc exactly.
+__device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int nrows, bool direct, int slab,
+                                              int lane, int2* ring, float* stash) {
     const int c = slab * 128 + lane * 4;
     const bool active = c < p.ld;
-    const int cc = active ? c : 0;
     const bool col_blocked = c < (p.d / 16) * 16;
-    const int nseg = p.d >> 5;
-    const float* __restrict__ zb = p.Zc + cc;
+    const float* __restrict__ zb = p.Zc + (active ? c : 0);
 
-    // row pointers of the group: lane i holds [start, end) of row r0 + i
+    // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
     if (lane < nrows) { rp_a = __ldg(p.rowptr + r0 + lane); rp_b = __ldg(p.rowptr + r0 + lane + 1); }
     const int e_first = __shfl_sync(kFull, rp_a, 0);
     const int e_total = __shfl_sync(kFull, rp_b, nrows - 1) - e_first;
-
-    // (col, w) windows of 32 edges: registers hold the window being fetched, the ring the two
-    // windows the load cursor can touch.
-    int win_q = 0;            // window currently in registers
-    int filled = 0;           // stream offset (exclusive) up to which the ring is valid
-    int pc = 0; float pw = 0.0f;
+    int pc = 0;
+    float pw = 0.0f;
     if (lane < e_total) { pc = __ldg(p.col + e_first + lane); pw = __ldg(p.w + e_first + lane); }
+    int win_q = 0, filled = 0;   // (col, w) window held in registers / stream offset published to the ring
 
-    RowCursor cur;
-    cur.i = -1; cur.a = 0; cur.k = 0; cur.pos = 0;
-
-    float4 z0[8], z1[8];
-    float w0[8], w1[8];
-    float4 xs0, xs1, zo0, zo1;
-    BatchInfo b0, b1;
-    xs0 = xs1 = zo0 = zo1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    b0.row = b1.row = 0; b0.m = b1.m = 0; b0.first = b1.first = 0; b0.last = b1.last = 0;
-
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float chunk_acc = 0.0f;
-
-    // -- stage the next batch of the stream into (z, ww, xs, zo, info); false when exhausted --
-    auto stage = [&](float4* z, float* ww, float4& xs, float4& zo, BatchInfo& bi) -> bool {
-        while (cur.i < nrows && cur.pos >= cur.k) {
-            ++cur.i;
-            if (cur.i < nrows) {
-                cur.a = __shfl_sync(kFull, rp_a, cur.i);
-                cur.k = __shfl_sync(kFull, rp_b, cur.i) - cur.a;
-                cur.pos = 0;
-                if (cur.k > p.hub_threshold) cur.pos = cur.k;   // hub rows belong to the hub role
-            }
-        }
-        if (cur.i >= nrows) return false;
-        const int u = cur.a + cur.pos - e_first;          // stream offset of the batch
-        const int m = min(8, cur.k - cur.pos);
-        while (filled < u + m) {                          // publish the fetched window, fetch the next
-            __syncwarp();                                 // every lane is done reading the slot it replaces
-            ring[(win_q & 1) * 32 + lane] = make_int2(pc, __float_as_int(pw));
-            __syncwarp();
-            filled = (win_q + 1) * 32;
-            ++win_q;
-            const int off = win_q * 32 + lane;
-            if (off < e_total) { pc = __ldg(p.col + e_first + off); pw = __ldg(p.w + e_first + off); }
-        }
-        bi.row = r0 + cur.i;
-        bi.m = m;
-        bi.first = cur.pos == 0;
-        bi.last = cur.pos + m >= cur.k;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i < m) {
-                const int2 mv = ring[(u + i) & (kMetaRing - 1)];
-                ww[i] = __int_as_float(mv.y);
-                z[i] = ldg4(zb + (size_t)mv.x * p.ld);
-            }
-        }
-        if (bi.last && active) {
-            const size_t off = (size_t)bi.row * p.ld + c;
-            xs = ld_stream4(p.X + off);
-            zo = ldg4(p.Zc + off);
-        }
-        cur.pos += m;
-        return true;
-    };
-
-    // -- reduce a staged batch; on the row's last batch write the row and its |delta| --
-    auto reduce = [&](const float4* z, const float* ww, const float4& xs, const float4& zo, const BatchInfo& bi) {
-        if (bi.first) acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bi.m == 8 && col_blocked) {
-            blocked8x4(acc, ww, z);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < bi.m) fma4(ww[i], z[i], acc);
-        }
-        if (bi.last) {
-            float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) {
-                const float4 out = finish_row(xs, acc, p.gamma);
-                *reinterpret_cast<float4*>(p.Zn + (size_t)bi.row * p.ld + c) = out;
-                dl = absdiff4(out, zo);
-            }
-            if (p.fuse) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
-        }
-    };
-
-    bool more = stage(z0, w0, xs0, zo0, b0);
-    while (more) {
-        const bool n1 = stage(z1, w1, xs1, zo1, b1);
-        reduce(z0, w0, xs0, zo0, b0);
-        if (!n1) break;
-        more = stage(z0, w0, xs0, zo0, b0);
-        reduce(z1, w1, xs1, zo1, b1);
+    if (direct) {   // rows that are skipped (sinks) contribute +0 to the chunk partial
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lane * 4; i < nrows * p.d; i += 128) *reinterpret_cast<float4*>(stash + i) = zero;
     }
-    if (p.fuse) p.P0[(size_t)g * 32 + lane] = chunk_acc;
+
+    float4 z[8];
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int a = __shfl_sync(kFull, rp_a, ri);
+        const int k = __shfl_sync(kFull, rp_b, ri) - a;
+        if (k == 0 || k > p.hub_threshold) continue;    // sinks are never updated; hub rows have their own role
+        const int row = r0 + ri;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xs = acc, zo = acc;
+        for (int pos = 0; pos < k; pos += 8) {
+            const int u = a + pos - e_first;            // stream offset of the batch
+            const int m = min(8, k - pos);
+            while (filled < u + m) {                    // publish the fetched window, fetch the next
+                __syncwarp();                           // every lane is done reading the slot it replaces
+                ring[(win_q & 1) * 32 + lane] = make_int2(pc, __float_as_int(pw));
+                __syncwarp();
+                filled = (++win_q) * 32;
+                const int off = filled + lane;
+                if (off < e_total) { pc = __ldg(p.col + e_first + off); pw = __ldg(p.w + e_first + off); }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int2 mv = ring[(u + i) & (kMetaRing - 1)];
+                const bool valid = i < m;
+                w[i] = valid ? __int_as_float(mv.y) : 0.0f;
+                if (valid) z[i] = ldg4(zb + (size_t)mv.x * p.ld);
+            }
+            if (pos + 8 >= k && active) {               // last batch: the row's X and own Zcur ride along
+                const size_t off = (size_t)row * p.ld + c;
+                xs = ld_stream4(p.X + off);
+                if (direct) zo = ldg4(p.Zc + off);
+            }
+            if (m == 8 && col_blocked) {
+                blocked8x4(acc, w, z);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fma4(w[i], z[i], acc);
+            }
+        }
+        if (active) {
+            const float4 out = finish_row(xs, acc, p.gamma);
+            *reinterpret_cast<float4*>(p.Zn + (size_t)row * p.ld + c) = out;
+            if (direct) *reinterpret_cast<float4*>(stash + ri * p.d + c) = absdiff4(out, zo);
+        }
+    }
+    if (direct) {
+        // the span is one whole level-0 chunk: nrows*d/32 cascade rows, summed in order per cascade lane
+        __syncwarp();
+        const int ncr = nrows * (p.d >> 5);
+        float sum = 0.0f;
+        for (int r = 0; r < ncr; ++r) sum = fadd(sum, stash[r * 32 + lane]);
+        p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = sum;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,16 +278,17 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     }
 }
 
-// Fused mode: the level-0 partial of every group that holds a hub row, from memory.
+// Fused mode: the level-0 partial of every group that was not swept by a single warp (it holds
+// a hub row or was cut into several spans), recomputed from memory.
 __global__ void __launch_bounds__(256)
-k_fix_hub_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, int n, int G,
-                 const int32_t* __restrict__ hub_groups, int n_hub_groups, float* __restrict__ P0,
-                 const clane_patience* __restrict__ st) {
+k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, int n, int G,
+             const int32_t* __restrict__ fix_groups, int n_fix_groups, float* __restrict__ P0,
+             const clane_patience* __restrict__ st) {
     if (st != nullptr && st->stop) return;
     const int lane = threadIdx.x & 31;
     const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (i >= n_hub_groups) return;
-    const int g = __ldg(hub_groups + i);
+    if (i >= n_fix_groups) return;
+    const int g = __ldg(fix_groups + i);
     const int r0 = g * G, nrows = min(G, n - r0);
     const int ncr = nrows * (d >> 5);                   // cascade rows of the chunk (ld == d here)
     const size_t base = (size_t)r0 * d + lane;
@@ -356,7 +307,7 @@ k_fix_hub_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int
     P0[(size_t)g * 32 + lane] = acc;
 }
 
-__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(SweepParams p) {
+__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     int2* rings = reinterpret_cast<int2*>(smem);
@@ -370,9 +321,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(SweepParams p) {
         return;
     }
     const int64_t task = (int64_t)(blockIdx.x - n_hub_ctas) * kSweepWarps + warp;
-    const int64_t gi = task / p.nslab;
-    if (gi >= p.n_row_groups) return;
-    row_group_task(p, __ldg(p.row_groups + gi), (int)(task - gi * p.nslab), lane, rings + warp * kMetaRing);
+    const int64_t si = task / p.nslab;
+    if (si >= p.n_spans) return;
+    const int meta = __ldg(p.span_meta + si);
+    row_span_task(p, __ldg(p.span_row + si), meta & 0xff, (meta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
+                  rings + warp * kMetaRing, ringf + warp * kWarpStash);
 }
 
 }  // namespace clane

@@ -79,26 +79,31 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
  *     change is fused into the sweep; otherwise 8 rows and the L1 change is a second pass);
  *   - rows of degree > hub_threshold are "hub rows": one CTA per 32-column slab of the row,
  *     the neighbour rows streamed through a shared-memory ring, longest first;
- *   - the groups are sorted by the edge count of their ordinary rows, descending, and handed
- *     to warps eight at a time; groups of sinks only are dropped (embedder.py:88-89: such
- *     rows are never updated).
+ *   - the ordinary rows of a group are cut into spans of bounded edge count, sorted by edge
+ *     count descending and handed to warps eight at a time; groups of sinks only are dropped
+ *     (embedder.py:88-89: such rows are never updated).
+ * hub_threshold <= 0 selects the default (128).
  * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
 typedef struct clane_plan clane_plan;
-/* The schedule alone, on the host (what clane_plan_create uploads): group ids relative to
- * row_lo, row ids absolute; the three outputs have capacity row_hi - row_lo + 1.
- *   h_row_groups: groups with ordinary rows, by their edge count (hub rows excluded) descending
- *   h_hub_groups: groups holding at least one hub row, ascending
+/* The schedule alone, on the host (what clane_plan_create uploads); every output has capacity
+ * row_hi - row_lo + 1.
+ *   spans       : runs of consecutive ordinary rows inside one group holding at most
+ *                 span_edges edges (a single row may exceed it), sorted by edge count
+ *                 descending; h_span_meta = rows | (1 << 8 when the span is the whole group and
+ *                 the group has no hub row, i.e. its warp also produces the fused L1 partial)
+ *   h_fix_groups: fused mode only -- groups (relative to row_lo) whose L1 partial is
+ *                 recomputed from memory because they hold a hub row or several spans
  *   h_hub_rows  : rows of degree > hub_threshold, degree-descending */
 int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
-                         int32_t hub_threshold, int32_t* h_row_groups, int32_t* n_row_groups, int32_t* h_hub_groups,
-                         int32_t* n_hub_groups, int32_t* h_hub_rows, int32_t* n_hub_rows, int32_t* group_rows,
-                         int32_t* fused_l1);
+                         int32_t hub_threshold, int32_t span_edges, int32_t* h_span_row, int32_t* h_span_meta,
+                         int32_t* n_spans, int32_t* h_fix_groups, int32_t* n_fix_groups, int32_t* h_hub_rows,
+                         int32_t* n_hub_rows, int32_t* group_rows, int32_t* fused_l1);
 int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
                       int32_t row_lo, int32_t row_hi, int32_t hub_threshold);
 int clane_plan_destroy(clane_plan* plan);
 /* any pointer may be NULL */
-int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_row_groups, int32_t* n_hub_groups,
-                    int32_t* fused_l1, int32_t* launches_per_sweep);
+int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_spans, int32_t* n_hub_rows,
+                    int32_t* n_fix_groups, int32_t* fused_l1, int32_t* launches_per_sweep);
 /* Shape of the exact L1 / norm reductions over a flattened array of n_elems fp32 values:
  * number of level-1 nodes of the ATen cascade and elements per node.  A caller that splits a
  * reduction over ranks exchanges [n1_nodes + 2] slots of 32 floats (see clane_l1_partial). */

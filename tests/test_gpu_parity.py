@@ -273,7 +273,8 @@ def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol):
     emb.verbose = False
     emb.propagate(max_sweeps=4)
     S = g._device_state()
-    assert S.plan.n_hub_groups >= 1 and S.plan.fused_l1 == (d in (32, 64, 128))
+    assert S.plan.n_hub_rows >= 3 and S.plan.fused_l1 == (d in (32, 64, 128))
+    assert (S.plan.n_fix_groups >= 3) == S.plan.fused_l1
     O.set_threads(O.max_threads())
     rowptr, col = O.csr_from_edges(src, dst, n)
     Zo, amounts, w = O.propagate(X, X, rowptr, col, 0.76, tol, max_sweeps=4)

@@ -139,15 +139,15 @@ def test_csr_rejects_out_of_range():
         Graph.from_arrays(3, src, dst, np.zeros((3, 2), np.float32))
 
 
-def group_schedule(rowptr, n, d, lo, hi, hub=256):
+def group_schedule(rowptr, n, d, lo, hi, hub=128, span_edges=128):
     L = _lib.lib()
     cap = hi - lo + 1
-    rg, hg, hr = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
-    nr, nh, nhr, G, fu = (ctypes.c_int32() for _ in range(5))
-    _lib.check(L.clane_group_schedule(rowptr.ctypes.data, n, d, lo, hi, hub, rg.ctypes.data, ctypes.byref(nr),
-                                      hg.ctypes.data, ctypes.byref(nh), hr.ctypes.data, ctypes.byref(nhr),
-                                      ctypes.byref(G), ctypes.byref(fu)))
-    return rg[:nr.value], hg[:nh.value], hr[:nhr.value], G.value, bool(fu.value)
+    sr, sm, fx, hr = (np.zeros(cap, np.int32) for _ in range(4))
+    ns, nf, nhr, G, fu = (ctypes.c_int32() for _ in range(5))
+    _lib.check(L.clane_group_schedule(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, sr.ctypes.data, sm.ctypes.data,
+                                      ctypes.byref(ns), fx.ctypes.data, ctypes.byref(nf), hr.ctypes.data,
+                                      ctypes.byref(nhr), ctypes.byref(G), ctypes.byref(fu)))
+    return sr[:ns.value], sm[:ns.value], fx[:nf.value], hr[:nhr.value], G.value, bool(fu.value)
 
 
 def test_group_schedule_degree_sorted_row_blocks():
@@ -157,28 +157,54 @@ def test_group_schedule_degree_sorted_row_blocks():
     deg[:5] = [0, 1, 33, 257, 1500]
     deg[64:80] = 0                                    # two whole groups of sinks
     deg[96:104] = [0, 0, 0, 300, 0, 0, 0, 0]          # a group whose only non-sink row is a hub
+    deg[200:208] = [100, 100, 20, 5, 90, 90, 0, 120]  # a group that must be cut into several spans
     src = np.repeat(np.arange(n), deg)
     dst = np.concatenate([rng.permutation(n)[:k] for k in deg])
     g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
     k = np.diff(g._rowptr)
+    hub, budget = 128, 128
     for d, lo, hi in [(100, 0, n), (128, 0, n), (128, 500, 1700), (1433, 0, n)]:
-        rg, hg, hr, G, fused = group_schedule(g._rowptr, n, d, lo, hi)
+        sr, sm, fx, hr, G, fused = group_schedule(g._rowptr, n, d, lo, hi, hub, budget)
         assert fused == (d == 128 and lo == 0 and hi == n)
         assert G == (4 if fused else 8)               # n*d < 2^24: level step 16 -> 512-element chunks
-        ng = (hi - lo + G - 1) // G
-        kk = np.where(k > 256, 0, k)                  # hub rows are not part of a group's own work
-        work = np.array([kk[lo + i * G: min(lo + (i + 1) * G, hi)].sum() for i in range(ng)])
-        hubby = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].max() > 256 for i in range(ng)])
-        assert hg.tolist() == np.nonzero(hubby)[0].tolist()
-        assert sorted(rg.tolist()) == np.nonzero(work > 0)[0].tolist()                 # all-sink groups dropped
-        assert np.all(np.diff(work[rg]) <= 0)                                           # longest first
-        want_hr = [v for v in range(lo, hi) if k[v] > 256]
+        nrows, direct = sm & 0xff, sm >> 8
+        kk = np.where(k > hub, 0, k)                  # hub rows are not part of a span's work
+        work = np.array([kk[r:r + m].sum() for r, m in zip(sr, nrows)])
+        assert np.all(work > 0) and np.all(np.diff(work) <= 0)                        # longest first, no empty span
+        covered = np.zeros(n, bool)
+        for r, m, w_, dr in zip(sr, nrows, work, direct):
+            assert (r - lo) // G == (r + m - 1 - lo) // G                              # a span stays inside one group
+            assert not covered[r:r + m].any()
+            covered[r:r + m] = True
+            assert w_ <= budget or (kk[r:r + m] > 0).sum() == 1 or kk[r:r + m - 1].sum() + 0 <= budget
+            if dr:                                                                      # whole group, no hub row
+                g0 = lo + (r - lo) // G * G
+                assert r == g0 and m == min(G, hi - g0) and k[r:r + m].max() <= hub
+        ordinary = (k > 0) & (k <= hub)
+        ordinary[:lo] = False
+        ordinary[hi:] = False
+        assert np.all(covered[ordinary])                                                # every ordinary row is swept
+        want_hr = [v for v in range(lo, hi) if k[v] > hub]
         assert sorted(hr.tolist()) == want_hr and np.all(np.diff(k[hr]) <= 0)
+        if fused:
+            ng = (hi - lo + G - 1) // G
+            nd = np.zeros(ng, int)
+            for r, dr in zip(sr, direct):
+                nd[(r - lo) // G] += 1
+            has_hub = np.array([k[lo + i * G: min(lo + (i + 1) * G, hi)].max() > hub for i in range(ng)])
+            is_direct = np.zeros(ng, bool)
+            is_direct[[(r - lo) // G for r, dr in zip(sr, direct) if dr]] = True
+            assert fx.tolist() == np.nonzero(((nd > 0) | has_hub) & ~is_direct)[0].tolist()
+        else:
+            assert len(fx) == 0
+    sr, sm, fx, hr, G, fused = group_schedule(g._rowptr, n, 100, 0, n, hub, budget)
+    rows200 = sorted((int(r), int(m & 0xff)) for r, m in zip(sr, sm) if 200 <= r < 208)
+    assert rows200 == [(200, 1), (201, 3), (204, 1), (205, 2), (207, 1)]
     # a graph large enough for level step 32: 1024-element chunks = 8 rows of 128
     rp = np.zeros(140001, np.int32)
-    assert group_schedule(rp, 140000, 128, 0, 140000)[3:] == (8, True)
-    assert group_schedule(rp, 140000, 64, 0, 140000)[3:] == (8, True)      # 8.96M elements: step 16, 512 / 64
-    assert group_schedule(rp, 140000, 100, 0, 140000)[3:] == (8, False)
+    assert group_schedule(rp, 140000, 128, 0, 140000)[4:] == (8, True)
+    assert group_schedule(rp, 140000, 64, 0, 140000)[4:] == (8, True)      # 8.96M elements: step 16, 512 / 64
+    assert group_schedule(rp, 140000, 100, 0, 140000)[4:] == (8, False)
 
 
 def test_cascade_shape():
@@ -211,9 +237,9 @@ def test_kernel_entry_points_reject_bad_arguments_without_a_device():
     assert L.clane_sweep(0, 0, 0, 0, 0, 0, 0, 0.5, 0, 0, 0, 0, 0) == -1
     assert L.clane_row_softmax(0, 0, 0, 1, 0, 0, 0) == -1
     assert L.clane_scores_cosine(0, 0, 0, 0, 0, 1, 0, 0, 0) == -1
-    assert L.clane_l1_diff(0, 0, 0, 0, 0) == -1 and L.clane_plan_info(0, None, None, None, None, None) == -1
+    assert L.clane_l1_diff(0, 0, 0, 0, 0) == -1 and L.clane_plan_info(0, None, None, None, None, None, None) == -1
     assert L.clane_plan_destroy(0) == 0
-    assert L.clane_group_schedule(0, 1, 1, 0, 1, 256, 0, None, 0, None, 0, None, None, None) == -1
+    assert L.clane_group_schedule(0, 1, 1, 0, 1, 128, 128, 0, 0, None, 0, None, 0, None, None, None) == -1
 
 
 def test_no_cpu_fallback_without_cuda(data_root):
