@@ -119,7 +119,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
-    cudaFree(plan->d_P0);
+    cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -155,7 +155,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     PLAN_CUDA(cudaMemset(plan->d_p2, 0, plan->p2_floats * sizeof(float)));
     if (!h_rowptr) { *out = plan; return CLANE_OK; }
 
+    if ((int64_t)n * plan->ld > (int64_t)INT32_MAX) { clane_plan_destroy(plan); return CLANE_ERANGE; }   // int32 row offsets
     plan->has_schedule = true;
+    PLAN_CUDA(cudaMalloc(&plan->d_coloff, std::max<size_t>((size_t)e, 1) * sizeof(int32_t)));
     plan->row_lo = row_lo; plan->row_hi = row_hi;
     plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
     const size_t cap = (size_t)(row_hi - row_lo) + 1;

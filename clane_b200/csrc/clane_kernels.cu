@@ -8,6 +8,8 @@
 //   embedder.py:98-108 patience               -> patience_step (cascade.cuh)
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "cascade.cuh"
 #include "common.cuh"
 #include "plan.cuh"
@@ -159,6 +161,12 @@ k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2
     }
 }
 
+// col[e] * ld: the element offset the sweep gathers from (one multiply per edge, once per graph)
+__global__ void k_col_offsets(const int32_t* __restrict__ col, int64_t e, int ld, int32_t* __restrict__ off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e) off[i] = col[i] * ld;
+}
+
 __global__ void k_cosine_finalize(const float* __restrict__ dots, const float* __restrict__ norms2, int64_t e,
                                   float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,7 +289,12 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     SweepParams p;
     p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
     p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
-    p.rowptr = d_rowptr; p.col = d_col; p.w = d_w; p.gamma = gamma;
+    if (plan->e > 0 && plan->coloff_src != d_col) {   // first sweep with this column array
+        k_col_offsets<<<(unsigned)((plan->e + 255) / 256), 256, 0, st>>>(d_col, plan->e, plan->ld, plan->d_coloff);
+        CLANE_LAUNCH_CHECK();
+        plan->coloff_src = d_col;
+    }
+    p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
     p.hub_rows = plan->d_hub_rows; p.n_hub_rows = plan->n_hub_rows; p.nslab32 = plan->nslab32;
     p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.n_spans = plan->n_spans;
     p.row_lo = plan->row_lo; p.row_hi = plan->row_hi;
@@ -290,8 +303,13 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     p.P0 = plan->d_P0;
     p.hub_threshold = plan->hub_threshold;
     p.st = d_state;
-    const int64_t row_ctas = ((int64_t)plan->n_spans * plan->nslab + kSweepWarps - 1) / kSweepWarps;
-    const int64_t grid = (int64_t)plan->n_hub_rows * plan->nslab32 + row_ctas;
+    {   // profiling aid only (results are incomplete): CLANE_DEBUG_ROLE=row | hub isolates one role
+        static const char* dbg = getenv("CLANE_DEBUG_ROLE");
+        if (dbg && dbg[0] == 'r') p.n_hub_rows = 0;
+        if (dbg && dbg[0] == 'h') p.n_spans = 0;
+    }
+    const int64_t row_ctas = ((int64_t)p.n_spans * plan->nslab + kSweepWarps - 1) / kSweepWarps;
+    const int64_t grid = (int64_t)p.n_hub_rows * plan->nslab32 + row_ctas;
     if (grid > 0) {
         k_sweep<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();

@@ -20,6 +20,8 @@ struct clane_plan {
     int32_t* d_span_meta = nullptr;    // rows | direct << 8
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
+    int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
+    const int32_t* coloff_src = nullptr;
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;

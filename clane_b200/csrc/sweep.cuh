@@ -37,7 +37,7 @@ struct SweepParams {
     float* Zn;
     int ld, d, n;
     const int32_t* rowptr;
-    const int32_t* col;
+    const int32_t* coloff;      // col[e] * ld: element offset of the neighbour's row
     const float* w;
     float gamma;
     const int32_t* hub_rows;    // rows of degree > hub_threshold, degree-descending
@@ -57,14 +57,15 @@ struct SweepParams {
 
 constexpr int kSweepThreads = 256;
 constexpr int kSweepWarps = 8;
-constexpr int kMetaRing = 64;                  // (col, w) pairs per warp
+constexpr int kMetaRing = 64;                  // (offset, w) pairs per warp, + 8 mirrored entries
+constexpr int kMetaSlots = kMetaRing + 8;
 constexpr int kHubStage = 32;                  // neighbours per ring stage
 constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 constexpr int kWarpStash = 1024;               // |delta| of one fused group (G*d <= 1024 floats) per warp
 // dynamic shared memory: meta rings (row role) | hub ring + hub w ring, reused as the row role's stashes
-constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaRing * sizeof(int2) +
+constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaSlots * sizeof(int2) +
                                    (size_t)kHubRingFloats * sizeof(float) +
                                    (size_t)kHubStages * kHubStage * sizeof(float);
 static_assert((size_t)kSweepWarps * kWarpStash <= (size_t)kHubRingFloats, "stashes alias the hub ring");
@@ -107,79 +108,95 @@ __device__ __forceinline__ float4 absdiff4(const float4& a, const float4& b) {
 // row role: one warp per (span, 128-column slab)
 // ------------------------------------------------------------------------------------------
 // A span is a run of consecutive rows of one group with a bounded edge count (hub rows are
-// skipped).  Per batch (one 8-neighbour block of one row) the warp reads (col, w) from its
-// shared-memory ring, issues up to 8 independent 512-byte gathers (LDG.128 per lane) and
-// reduces them in the reference's order; latency is hidden by the other resident warps
+// skipped).  Per batch (one 8-neighbour block of one row) the warp reads (offset, w) pairs
+// from its shared-memory ring, issues up to 8 independent 512-byte gathers (LDG.128 per lane)
+// and reduces them in the reference's order; latency is hidden by the other resident warps
 // (24 per SM), not by software pipelining, which keeps the kernel at <= 85 registers.
-// Unused slots of a short batch keep their previous (finite) register contents and get
-// weight 0: fma(0, z, acc) == acc exactly.
+// The batch body is instantiated for every length 1..8 (no predication, no padding).
+template <int M>
+__device__ __forceinline__ void reduce_batch(const int2* __restrict__ mp, const float* __restrict__ zb, float4& acc,
+                                             bool col_blocked) {
+    float4 z[M];
+    float w[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const int2 mv = mp[i];
+        w[i] = __int_as_float(mv.y);
+        z[i] = ldg4(zb + mv.x);          // mv.x = col * ld (element offset of the neighbour's row)
+    }
+    if (M == 8 && col_blocked) {
+        blocked8x4(acc, w, z);
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) fma4(w[i], z[i], acc);
+    }
+}
+
 __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int nrows, bool direct, int slab,
                                               int lane, int2* ring, float* stash) {
     const int c = slab * 128 + lane * 4;
     const bool active = c < p.ld;
     const bool col_blocked = c < (p.d / 16) * 16;
-    const float* __restrict__ zb = p.Zc + (active ? c : 0);
+    const float* zb = p.Zc + (active ? c : 0);
+    asm volatile("" : "+l"(zb));         // keep the lane's column base in registers (no rematerialisation)
 
     // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
     if (lane < nrows) { rp_a = __ldg(p.rowptr + r0 + lane); rp_b = __ldg(p.rowptr + r0 + lane + 1); }
     const int e_first = __shfl_sync(kFull, rp_a, 0);
     const int e_total = __shfl_sync(kFull, rp_b, nrows - 1) - e_first;
+    const int* __restrict__ offp = p.coloff + e_first;
+    const float* __restrict__ wp = p.w + e_first;
     int pc = 0;
     float pw = 0.0f;
-    if (lane < e_total) { pc = __ldg(p.col + e_first + lane); pw = __ldg(p.w + e_first + lane); }
-    int win_q = 0, filled = 0;   // (col, w) window held in registers / stream offset published to the ring
+    if (lane < e_total) { pc = __ldg(offp + lane); pw = __ldg(wp + lane); }
+    int win_q = 0, filled = 0;   // window held in registers / stream offset published to the ring
 
     if (direct) {   // rows that are skipped (sinks) contribute +0 to the chunk partial
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = lane * 4; i < nrows * p.d; i += 128) *reinterpret_cast<float4*>(stash + i) = zero;
     }
-
-    float4 z[8];
-    float w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xs = make_float4(0.f, 0.f, 0.f, 0.f), zo = xs;
 
     for (int ri = 0; ri < nrows; ++ri) {
         const int a = __shfl_sync(kFull, rp_a, ri);
         const int k = __shfl_sync(kFull, rp_b, ri) - a;
         if (k == 0 || k > p.hub_threshold) continue;    // sinks are never updated; hub rows have their own role
-        const int row = r0 + ri;
+        const size_t row_off = (size_t)(r0 + ri) * p.ld + c;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 xs = acc, zo = acc;
         for (int pos = 0; pos < k; pos += 8) {
             const int u = a + pos - e_first;            // stream offset of the batch
             const int m = min(8, k - pos);
             while (filled < u + m) {                    // publish the fetched window, fetch the next
-                __syncwarp();                           // every lane is done reading the slot it replaces
-                ring[(win_q & 1) * 32 + lane] = make_int2(pc, __float_as_int(pw));
+                const int base = (win_q & 1) * 32;
+                __syncwarp();                           // every lane is done reading the slots it replaces
+                const int2 v = make_int2(pc, __float_as_int(pw));
+                ring[base + lane] = v;
+                if (base == 0 && lane < 8) ring[kMetaRing + lane] = v;   // mirror: a batch never wraps
                 __syncwarp();
                 filled = (++win_q) * 32;
                 const int off = filled + lane;
-                if (off < e_total) { pc = __ldg(p.col + e_first + off); pw = __ldg(p.w + e_first + off); }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int2 mv = ring[(u + i) & (kMetaRing - 1)];
-                const bool valid = i < m;
-                w[i] = valid ? __int_as_float(mv.y) : 0.0f;
-                if (valid) z[i] = ldg4(zb + (size_t)mv.x * p.ld);
+                if (off < e_total) { pc = __ldg(offp + off); pw = __ldg(wp + off); }
             }
             if (pos + 8 >= k && active) {               // last batch: the row's X and own Zcur ride along
-                const size_t off = (size_t)row * p.ld + c;
-                xs = ld_stream4(p.X + off);
-                if (direct) zo = ldg4(p.Zc + off);
+                xs = ld_stream4(p.X + row_off);
+                if (direct) zo = ldg4(p.Zc + row_off);
             }
-            if (m == 8 && col_blocked) {
-                blocked8x4(acc, w, z);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) fma4(w[i], z[i], acc);
+            const int2* mp = ring + (u & (kMetaRing - 1));
+            switch (m) {
+                case 8: reduce_batch<8>(mp, zb, acc, col_blocked); break;
+                case 7: reduce_batch<7>(mp, zb, acc, col_blocked); break;
+                case 6: reduce_batch<6>(mp, zb, acc, col_blocked); break;
+                case 5: reduce_batch<5>(mp, zb, acc, col_blocked); break;
+                case 4: reduce_batch<4>(mp, zb, acc, col_blocked); break;
+                case 3: reduce_batch<3>(mp, zb, acc, col_blocked); break;
+                case 2: reduce_batch<2>(mp, zb, acc, col_blocked); break;
+                default: reduce_batch<1>(mp, zb, acc, col_blocked); break;
             }
         }
         if (active) {
             const float4 out = finish_row(xs, acc, p.gamma);
-            *reinterpret_cast<float4*>(p.Zn + (size_t)row * p.ld + c) = out;
+            *reinterpret_cast<float4*>(p.Zn + row_off) = out;
             if (direct) *reinterpret_cast<float4*>(stash + ri * p.d + c) = absdiff4(out, zo);
         }
     }
@@ -222,7 +239,7 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
 #pragma unroll
     for (int i = 0; i < kHubMeta; ++i) {
         const int idx = i * kHubStage + nb, widx = i * kHubStage + lane;
-        cq[i] = idx < k ? __ldg(p.col + a + idx) : 0;
+        cq[i] = idx < k ? __ldg(p.coloff + a + idx) : 0;
         wq[i] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
     }
     int si = 0;                                         // next stage to issue
@@ -230,13 +247,13 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
         const int slot = si % kHubStages;
         if (si * kHubStage + nb < k && pact)
             cp_async16(ringf + (size_t)slot * kHubStage * 32 + nb * 32 + (lane & 7) * 4,
-                       p.Zc + (size_t)cq[0] * p.ld + pcol);
+                       p.Zc + (size_t)cq[0] + pcol);
         if (warp == 0) wsm[slot * kHubStage + lane] = wq[0];
         cp_async_commit();
 #pragma unroll
         for (int i = 0; i + 1 < kHubMeta; ++i) { cq[i] = cq[i + 1]; wq[i] = wq[i + 1]; }
         const int idx = (si + kHubMeta) * kHubStage + nb, widx = (si + kHubMeta) * kHubStage + lane;
-        cq[kHubMeta - 1] = idx < k ? __ldg(p.col + a + idx) : 0;
+        cq[kHubMeta - 1] = idx < k ? __ldg(p.coloff + a + idx) : 0;
         wq[kHubMeta - 1] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
         ++si;
     };
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     int2* rings = reinterpret_cast<int2*>(smem);
-    float* ringf = reinterpret_cast<float*>(smem + (size_t)kSweepWarps * kMetaRing * sizeof(int2));
+    float* ringf = reinterpret_cast<float*>(smem + (size_t)kSweepWarps * kMetaSlots * sizeof(int2));
     float* wsm = ringf + kHubRingFloats;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_hub_ctas = p.n_hub_rows * p.nslab32;
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(SweepParams p) {
     if (si >= p.n_spans) return;
     const int meta = __ldg(p.span_meta + si);
     row_span_task(p, __ldg(p.span_row + si), meta & 0xff, (meta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
-                  rings + warp * kMetaRing, ringf + warp * kWarpStash);
+                  rings + warp * kMetaSlots, ringf + warp * kWarpStash);
 }
 
 }  // namespace clane
