@@ -7,6 +7,7 @@
 //   embedder.py:56-69  Embedder.iterate                -> clane_session_iterate
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -143,6 +144,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
     plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 128;
     plan->span_edges = 128;
+    // tuning aids (benchmark sweeps only)
+    if (const char* v = getenv("CLANE_HUB_THRESHOLD")) plan->hub_threshold = std::max(atoi(v), 8);
+    if (const char* v = getenv("CLANE_SPAN_EDGES")) plan->span_edges = std::max(atoi(v), 8);
     plan->nslab = (plan->ld + 127) / 128;
 
     // cascade scratch: L1 over n*d (one quantity) and the norms over e*d (two quantities)

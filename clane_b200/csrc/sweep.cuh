@@ -234,6 +234,10 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     const int ccol = slab32 * 32 + lane;
     const bool blk = ccol < (p.d / 16) * 16;           // k > hub_threshold >= 8
 
+    // (offset, w) of stage s live in cq[s % kHubMeta] / wq[s % kHubMeta]; a slot is refilled for stage
+    // s + kHubMeta right after stage s is issued.  The stage loop is unrolled kHubMeta times so the
+    // slot index is static: nothing reads a prefetched register before it is needed (a rotating
+    // register queue would wait on the newest load every iteration).
     int cq[kHubMeta];
     float wq[kHubMeta];
 #pragma unroll
@@ -242,50 +246,58 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
         cq[i] = idx < k ? __ldg(p.coloff + a + idx) : 0;
         wq[i] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
     }
-    int si = 0;                                         // next stage to issue
-    auto issue = [&]() {
+    auto issue = [&](int si, int& cslot, float& wslot) {   // si: stage to issue; its meta sits in (cslot, wslot)
         const int slot = si % kHubStages;
         if (si * kHubStage + nb < k && pact)
-            cp_async16(ringf + (size_t)slot * kHubStage * 32 + nb * 32 + (lane & 7) * 4,
-                       p.Zc + (size_t)cq[0] + pcol);
-        if (warp == 0) wsm[slot * kHubStage + lane] = wq[0];
+            cp_async16(ringf + (size_t)slot * kHubStage * 32 + nb * 32 + (lane & 7) * 4, p.Zc + (size_t)cslot + pcol);
+        if (warp == 0) wsm[slot * kHubStage + lane] = wslot;
         cp_async_commit();
-#pragma unroll
-        for (int i = 0; i + 1 < kHubMeta; ++i) { cq[i] = cq[i + 1]; wq[i] = wq[i + 1]; }
         const int idx = (si + kHubMeta) * kHubStage + nb, widx = (si + kHubMeta) * kHubStage + lane;
-        cq[kHubMeta - 1] = idx < k ? __ldg(p.coloff + a + idx) : 0;
-        wq[kHubMeta - 1] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
-        ++si;
+        cslot = idx < k ? __ldg(p.coloff + a + idx) : 0;
+        wslot = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
+    };
+    auto consume = [&](int s, float& acc) {
+        const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
+        const float* wrow = wsm + (s % kHubStages) * kHubStage;
+        const float4* w4 = reinterpret_cast<const float4*>(wrow);
+        const int cnt = min(kHubStage, k - s * kHubStage);
+        int o = 0;
+        for (; o + 8 <= cnt; o += 8) {
+            const float4 wa = w4[o >> 2], wb = w4[(o >> 2) + 1];
+            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            float z[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = src[(o + i) * 32];
+            if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
+            }
+        }
+        for (; o < cnt; ++o) acc = ffma(wrow[o], src[o * 32], acc);
     };
 
+    static_assert(kHubStages - 1 == 2 * kHubMeta - 1 || (kHubStages - 1) % kHubMeta == kHubMeta - 1,
+                  "prologue must end on a slot boundary");
+    // prologue: stages 0 .. kHubStages-2 in flight (kHubStages - 1 = 15 = 8 + 7 issues)
+#pragma unroll
     for (int s = 0; s < kHubStages - 1; ++s) {
-        if (s < nst) issue();
+        if (s < nst) issue(s, cq[s % kHubMeta], wq[s % kHubMeta]);
         else cp_async_commit();
     }
     float acc = 0.0f;
-    for (int s = 0; s < nst; ++s) {
-        cp_async_wait<kHubStages - 2>();
-        __syncthreads();                               // stage s landed for everyone; stage s-1 reduced
-        if (si < nst) issue();
-        else cp_async_commit();
-        if (warp == 0) {
-            const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
-            const float4* w4 = reinterpret_cast<const float4*>(wsm + (s % kHubStages) * kHubStage);
-            const int cnt = min(kHubStage, k - s * kHubStage);
-            int o = 0;
-            for (; o + 8 <= cnt; o += 8) {
-                const float4 wa = w4[o >> 2], wb = w4[(o >> 2) + 1];
-                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                float z[8];
+    for (int sb = 0; sb < nst; sb += kHubMeta) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) z[i] = src[(o + i) * 32];
-                if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
-                }
+        for (int j = 0; j < kHubMeta; ++j) {
+            const int s = sb + j;
+            if (s < nst) {                                  // CTA-uniform
+                cp_async_wait<kHubStages - 2>();
+                __syncthreads();                           // stage s landed for everyone; stage s-1 reduced
+                const int si = s + kHubStages - 1;         // (sb + j + 15) % 8 == (j + 7) % 8: static slot
+                if (si < nst) issue(si, cq[(j + kHubStages - 1) % kHubMeta], wq[(j + kHubStages - 1) % kHubMeta]);
+                else cp_async_commit();
+                if (warp == 0) consume(s, acc);
             }
-            for (; o < cnt; ++o) acc = ffma(wsm[(s % kHubStages) * kHubStage + o], src[o * 32], acc);
         }
     }
     cp_async_wait<0>();
