@@ -121,6 +121,9 @@ int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+    if (plan->side) cudaStreamDestroy(plan->side);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -162,6 +165,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     if ((int64_t)n * plan->ld > (int64_t)INT32_MAX) { clane_plan_destroy(plan); return CLANE_ERANGE; }   // int32 row offsets
     plan->has_schedule = true;
     PLAN_CUDA(cudaMalloc(&plan->d_coloff, std::max<size_t>((size_t)e, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+    PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
     plan->row_lo = row_lo; plan->row_hi = row_hi;
     plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
     const size_t cap = (size_t)(row_hi - row_lo) + 1;
@@ -202,8 +208,9 @@ int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_span
     if (n_hub_rows) *n_hub_rows = plan->n_hub_rows;
     if (n_fix_groups) *n_fix_groups = plan->n_fix_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    // sweep, [chunk fix-up], level-1, finish
-    if (launches_per_sweep) *launches_per_sweep = 3 + ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
+    // row sweep, [hub sweep], [chunk fix-up], level-1, finish
+    if (launches_per_sweep)
+        *launches_per_sweep = 3 + (plan->n_hub_rows > 0 ? 1 : 0) + ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
     return CLANE_OK;
 }
 

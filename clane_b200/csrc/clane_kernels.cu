@@ -8,6 +8,7 @@
 //   embedder.py:98-108 patience               -> patience_step (cascade.cuh)
 #include <math_constants.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "cascade.cuh"
@@ -308,12 +309,21 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
         if (dbg && dbg[0] == 'r') p.n_hub_rows = 0;
         if (dbg && dbg[0] == 'h') p.n_spans = 0;
     }
-    const int64_t row_ctas = ((int64_t)p.n_spans * plan->nslab + kSweepWarps - 1) / kSweepWarps;
-    const int64_t grid = (int64_t)p.n_hub_rows * plan->nslab32 + row_ctas;
-    if (grid > 0) {
-        k_sweep<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(p);
+    // The hub rows (few, long in-order chains) run on the plan's side stream next to the row kernel.
+    const int64_t hub_ctas = (int64_t)p.n_hub_rows * plan->nslab32;
+    const int64_t row_ctas = ((int64_t)p.n_spans * plan->nslab + kRowWarps - 1) / kRowWarps;
+    if (hub_ctas > 0) {
+        CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
+        CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        k_sweep_hubs<<<(unsigned)hub_ctas, kHubThreads, kHubSmemBytes, plan->side>>>(p);
+        CLANE_LAUNCH_CHECK();
+        CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
+    }
+    if (row_ctas > 0) {
+        k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, kRowSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
+    if (hub_ctas > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
     if (!want_l1) return CLANE_OK;
     const int64_t n_elems = (int64_t)plan->n * plan->d;
     ElemAbsDiff el{d_Znext, d_Zcur, plan->d, plan->ld};
@@ -367,7 +377,8 @@ int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweep
 int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
-    CLANE_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_sweep_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHubSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

@@ -22,6 +22,8 @@ struct clane_plan {
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
+    cudaStream_t side = nullptr;       // hub kernel runs here, forked from / joined to the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;

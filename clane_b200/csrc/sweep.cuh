@@ -55,8 +55,9 @@ struct SweepParams {
     const clane_patience* st;
 };
 
-constexpr int kSweepThreads = 256;
-constexpr int kSweepWarps = 8;
+constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
+constexpr int kRowWarps = 4;
+constexpr int kHubThreads = 256;               // hub kernel: 8 warps per CTA
 constexpr int kMetaRing = 64;                  // (offset, w) pairs per warp, + 8 mirrored entries
 constexpr int kMetaSlots = kMetaRing + 8;
 constexpr int kHubStage = 32;                  // neighbours per ring stage
@@ -64,11 +65,10 @@ constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 constexpr int kWarpStash = 1024;               // |delta| of one fused group (G*d <= 1024 floats) per warp
-// dynamic shared memory: meta rings (row role) | hub ring + hub w ring, reused as the row role's stashes
-constexpr size_t kSweepSmemBytes = (size_t)kSweepWarps * kMetaSlots * sizeof(int2) +
-                                   (size_t)kHubRingFloats * sizeof(float) +
-                                   (size_t)kHubStages * kHubStage * sizeof(float);
-static_assert((size_t)kSweepWarps * kWarpStash <= (size_t)kHubRingFloats, "stashes alias the hub ring");
+// row kernel shared memory: per-warp meta rings | per-warp stashes
+constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kMetaSlots * sizeof(int2) + (size_t)kRowWarps * kWarpStash * sizeof(float);
+// hub kernel shared memory: copy ring | w ring
+constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float);
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -111,7 +111,7 @@ __device__ __forceinline__ float4 absdiff4(const float4& a, const float4& b) {
 // skipped).  Per batch (one 8-neighbour block of one row) the warp reads (offset, w) pairs
 // from its shared-memory ring, issues up to 8 independent 512-byte gathers (LDG.128 per lane)
 // and reduces them in the reference's order; latency is hidden by the other resident warps
-// (24 per SM), not by software pipelining, which keeps the kernel at <= 85 registers.
+// (20 per SM), not by software pipelining, which keeps the kernel free of register spills.
 // The batch body is instantiated for every length 1..8 (no predication, no padding).
 template <int M>
 __device__ __forceinline__ void reduce_batch(const int2* __restrict__ mp, const float* __restrict__ zb, float4& acc,
@@ -259,22 +259,40 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     auto consume = [&](int s, float& acc) {
         const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
         const float* wrow = wsm + (s % kHubStages) * kHubStage;
-        const float4* w4 = reinterpret_cast<const float4*>(wrow);
         const int cnt = min(kHubStage, k - s * kHubStage);
-        int o = 0;
-        for (; o + 8 <= cnt; o += 8) {
-            const float4 wa = w4[o >> 2], wb = w4[(o >> 2) + 1];
-            const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            float z[8];
+        if (cnt == kHubStage) {
+            // full stage: all 32 values and weights are fetched before the in-order chain starts
+            float z[kHubStage];
+            float4 w4[kHubStage / 4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = src[(o + i) * 32];
-            if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
-            else {
+            for (int i = 0; i < kHubStage; ++i) z[i] = src[i * 32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
+            for (int i = 0; i < kHubStage / 4; ++i) w4[i] = reinterpret_cast<const float4*>(wrow)[i];
+#pragma unroll
+            for (int b = 0; b < kHubStage / 8; ++b) {
+                const float ww[8] = {w4[2 * b].x, w4[2 * b].y, w4[2 * b].z, w4[2 * b].w,
+                                     w4[2 * b + 1].x, w4[2 * b + 1].y, w4[2 * b + 1].z, w4[2 * b + 1].w};
+                const float* zz = z + 8 * b;
+                if (blk) acc = blocked8(acc, ww, zz[0], zz[1], zz[2], zz[3], zz[4], zz[5], zz[6], zz[7]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], zz[i], acc);
+                }
             }
+        } else {
+            int o = 0;
+            for (; o + 8 <= cnt; o += 8) {
+                float ww[8], z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { ww[i] = wrow[o + i]; z[i] = src[(o + i) * 32]; }
+                if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
+                }
+            }
+            for (; o < cnt; ++o) acc = ffma(wrow[o], src[o * 32], acc);
         }
-        for (; o < cnt; ++o) acc = ffma(wrow[o], src[o * 32], acc);
     };
 
     static_assert(kHubStages - 1 == 2 * kHubMeta - 1 || (kHubStages - 1) % kHubMeta == kHubMeta - 1,
@@ -336,25 +354,27 @@ k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, 
     P0[(size_t)g * 32 + lane] = acc;
 }
 
-__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     int2* rings = reinterpret_cast<int2*>(smem);
-    float* ringf = reinterpret_cast<float*>(smem + (size_t)kSweepWarps * kMetaSlots * sizeof(int2));
-    float* wsm = ringf + kHubRingFloats;
+    float* stashes = reinterpret_cast<float*>(smem + (size_t)kRowWarps * kMetaSlots * sizeof(int2));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_hub_ctas = p.n_hub_rows * p.nslab32;
-    if ((int)blockIdx.x < n_hub_ctas) {
-        const int hr = blockIdx.x / p.nslab32;
-        hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm);
-        return;
-    }
-    const int64_t task = (int64_t)(blockIdx.x - n_hub_ctas) * kSweepWarps + warp;
+    const int64_t task = (int64_t)blockIdx.x * kRowWarps + warp;
     const int64_t si = task / p.nslab;
     if (si >= p.n_spans) return;
     const int meta = __ldg(p.span_meta + si);
     row_span_task(p, __ldg(p.span_row + si), meta & 0xff, (meta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
-                  rings + warp * kMetaSlots, ringf + warp * kWarpStash);
+                  rings + warp * kMetaSlots, stashes + warp * kWarpStash);
+}
+
+__global__ void __launch_bounds__(kHubThreads, 2) k_sweep_hubs(SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (p.st != nullptr && p.st->stop) return;
+    float* ringf = reinterpret_cast<float*>(smem);
+    float* wsm = ringf + kHubRingFloats;
+    const int hr = blockIdx.x / p.nslab32;
+    hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm);
 }
 
 }  // namespace clane
