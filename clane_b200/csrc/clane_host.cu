@@ -119,7 +119,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_span_edges); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);
@@ -185,7 +185,14 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     PLAN_CUDA(cudaMalloc(&plan->d_span_meta, std::max<size_t>(n_spans, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_span_edges, std::max<size_t>(n_spans, 1) * sizeof(int2)));
     if (n_spans) {
+        std::vector<int2> sedges((size_t)n_spans);
+        for (int32_t i = 0; i < n_spans; ++i) {
+            const int32_t a = h_rowptr[srow[i]], b = h_rowptr[srow[i] + (smeta[i] & 0xff)];
+            sedges[i] = make_int2(a, b - a);
+        }
+        PLAN_CUDA(cudaMemcpy(plan->d_span_edges, sedges.data(), n_spans * sizeof(int2), cudaMemcpyHostToDevice));
         PLAN_CUDA(cudaMemcpy(plan->d_span_row, srow.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
         PLAN_CUDA(cudaMemcpy(plan->d_span_meta, smeta.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
     }

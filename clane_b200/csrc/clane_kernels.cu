@@ -297,7 +297,8 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     }
     p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
     p.hub_rows = plan->d_hub_rows; p.n_hub_rows = plan->n_hub_rows; p.nslab32 = plan->nslab32;
-    p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.n_spans = plan->n_spans;
+    p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.span_edges = plan->d_span_edges;
+    p.n_spans = plan->n_spans;
     p.row_lo = plan->row_lo; p.row_hi = plan->row_hi;
     p.G = plan->G; p.nslab = plan->nslab;
     p.fuse = (plan->fuse && want_l1) ? 1 : 0;

@@ -18,6 +18,7 @@ struct clane_plan {
     int32_t nslab32 = 1;        // 32-column slabs per row (hub role)
     int32_t* d_span_row = nullptr;     // spans (runs of ordinary rows inside one group), by edge count descending
     int32_t* d_span_meta = nullptr;    // rows | direct << 8
+    int2* d_span_edges = nullptr;      // (first edge, edge count) of each span
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes

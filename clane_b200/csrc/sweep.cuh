@@ -45,6 +45,7 @@ struct SweepParams {
     int nslab32;                // 32-column slabs per row (hub role)
     const int32_t* span_row;    // first row of each span; spans sorted by edge count, descending
     const int32_t* span_meta;   // rows in the span | (1 << 8 if the span is a whole fused chunk)
+    const int2* span_edges;     // (first edge, edge count) of the span: the first window is fetched with rowptr
     int n_spans;
     int row_lo, row_hi;         // rows covered by the plan; groups are cut from row_lo
     int G;                      // rows per group (<= 32)
@@ -132,8 +133,10 @@ __device__ __forceinline__ void reduce_batch(const int2* __restrict__ mp, const 
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int nrows, bool direct, int slab,
-                                              int lane, int2* ring, float* stash) {
+                                              int lane, int2* ring, float* stash, int e_first, int e_total) {
     const int c = slab * 128 + lane * 4;
     const bool active = c < p.ld;
     const bool col_blocked = c < (p.d / 16) * 16;
@@ -143,8 +146,15 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
     // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
     if (lane < nrows) { rp_a = __ldg(p.rowptr + r0 + lane); rp_b = __ldg(p.rowptr + r0 + lane + 1); }
-    const int e_first = __shfl_sync(kFull, rp_a, 0);
-    const int e_total = __shfl_sync(kFull, rp_b, nrows - 1) - e_first;
+    {   // X rows (and, for the fused L1, the own Zcur rows) of the span are contiguous: pull them into L2 now so
+        // that the loads riding with each row's last batch are L2 hits instead of DRAM misses on the row's path
+        const int row_lines = (min(128, p.ld - slab * 128) * 4 + 127) >> 7;
+        for (int i = lane; i < nrows * row_lines; i += 32) {
+            const size_t off = (size_t)(r0 + i / row_lines) * p.ld + slab * 128 + (i % row_lines) * 32;
+            prefetch_l2(p.X + off);
+            if (direct) prefetch_l2(p.Zc + off);
+        }
+    }
     const int* __restrict__ offp = p.coloff + e_first;
     const float* __restrict__ wp = p.w + e_first;
     int pc = 0;
@@ -364,8 +374,9 @@ __global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
     const int64_t si = task / p.nslab;
     if (si >= p.n_spans) return;
     const int meta = __ldg(p.span_meta + si);
+    const int2 se = __ldg(p.span_edges + si);
     row_span_task(p, __ldg(p.span_row + si), meta & 0xff, (meta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
-                  rings + warp * kMetaSlots, stashes + warp * kWarpStash);
+                  rings + warp * kMetaSlots, stashes + warp * kWarpStash, se.x, se.y);
 }
 
 __global__ void __launch_bounds__(kHubThreads, 2) k_sweep_hubs(SweepParams p) {
