@@ -59,15 +59,15 @@ struct SweepParams {
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
 constexpr int kRowWarps = 4;
 constexpr int kHubThreads = 256;               // hub kernel: 8 warps per CTA
-constexpr int kMetaRing = 64;                  // (offset, w) pairs per warp, + 8 mirrored entries
+constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
 constexpr int kMetaSlots = kMetaRing + 8;
 constexpr int kHubStage = 32;                  // neighbours per ring stage
 constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
-constexpr int kWarpStash = 1024;               // |delta| of one fused group (G*d <= 1024 floats) per warp
-// row kernel shared memory: per-warp meta rings | per-warp stashes
-constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kMetaSlots * sizeof(int2) + (size_t)kRowWarps * kWarpStash * sizeof(float);
+// row kernel shared memory per warp: (offset, w) ring | 32 x 512-byte row-piece ring
+constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)32 * 32 * sizeof(float4);
+constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
 constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float);
 
@@ -105,25 +105,69 @@ __device__ __forceinline__ float4 absdiff4(const float4& a, const float4& b) {
     return make_float4(fabsf(fsub(a.x, b.x)), fabsf(fsub(a.y, b.y)), fabsf(fsub(a.z, b.z)), fabsf(fsub(a.w, b.w)));
 }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane
+// m owns cascade lane m: the row is d/32 consecutive cascade rows, taken in order.
+__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane) {
+    const int sub = lane >> 2, comp = lane & 3;
+    for (int seg = 0; seg < nseg; ++seg) {
+        const int src = seg * 8 + sub;
+        const float v0 = __shfl_sync(kFull, dl.x, src), v1 = __shfl_sync(kFull, dl.y, src);
+        const float v2 = __shfl_sync(kFull, dl.z, src), v3 = __shfl_sync(kFull, dl.w, src);
+        const float v = comp == 0 ? v0 : (comp == 1 ? v1 : (comp == 2 ? v2 : v3));
+        chunk_acc = fadd(chunk_acc, v);
+    }
+    return chunk_acc;
+}
+
 // ------------------------------------------------------------------------------------------
 // row role: one warp per (span, 128-column slab)
 // ------------------------------------------------------------------------------------------
 // A span is a run of consecutive rows of one group with a bounded edge count (hub rows are
-// skipped).  Per batch (one 8-neighbour block of one row) the warp reads (offset, w) pairs
-// from its shared-memory ring, issues up to 8 independent 512-byte gathers (LDG.128 per lane)
-// and reduces them in the reference's order; latency is hidden by the other resident warps
-// (20 per SM), not by software pipelining, which keeps the kernel free of register spills.
-// The batch body is instantiated for every length 1..8 (no predication, no padding).
+// skipped).  The warp walks the span's edge stream twice, with two cursors:
+//   issue   : per "batch" (one 8-neighbour block of one row) it reads the neighbours' row
+//             offsets from its (offset, w) ring and starts one 512-byte cp.async per neighbour
+//             (16 bytes per lane: lane L copies exactly the float4 of columns it will reduce,
+//             so no barrier is ever needed) into its private 32-slot ring of row pieces; the
+//             row's X piece (and own Zcur piece, fused L1) ride with the row's last batch;
+//   consume : waits for the OLDEST batch only (cp.async.wait_group), reduces it in the
+//             reference's order, and frees its slots.
+// Up to 32 row pieces (16 KB) per warp are in flight whatever the row lengths: the gathers of
+// the next rows overlap the reduction of the current one (decoupled access / execute).
+constexpr int kRing = 32;              // 512-byte row-piece slots per warp
+constexpr int kMaxPending = 8;         // batches in flight per warp
+
+struct Cursor { int ri, a, k, pos; };
+
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {   // oldest of `pending` groups complete
+    switch (pending) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        case 4: cp_async_wait<3>(); break;
+        case 5: cp_async_wait<4>(); break;
+        case 6: cp_async_wait<5>(); break;
+        case 7: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
+}
+
 template <int M>
-__device__ __forceinline__ void reduce_batch(const int2* __restrict__ mp, const float* __restrict__ zb, float4& acc,
-                                             bool col_blocked) {
+__device__ __forceinline__ void reduce_batch(const float4* __restrict__ ring, int head, const int2* __restrict__ mp,
+                                             int lane, float4& acc, bool col_blocked) {
     float4 z[M];
     float w[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        const int2 mv = mp[i];
-        w[i] = __int_as_float(mv.y);
-        z[i] = ldg4(zb + mv.x);          // mv.x = col * ld (element offset of the neighbour's row)
+        z[i] = ring[((head + i) & (kRing - 1)) * 32 + lane];
+        w[i] = __int_as_float(mp[i].y);
     }
     if (M == 8 && col_blocked) {
         blocked8x4(acc, w, z);
@@ -133,103 +177,119 @@ __device__ __forceinline__ void reduce_batch(const int2* __restrict__ mp, const 
     }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int nrows, bool direct, int slab,
-                                              int lane, int2* ring, float* stash, int e_first, int e_total) {
+                                              int lane, int2* meta, float4* ring, int e_first, int e_total) {
     const int c = slab * 128 + lane * 4;
     const bool active = c < p.ld;
     const bool col_blocked = c < (p.d / 16) * 16;
-    const float* zb = p.Zc + (active ? c : 0);
-    asm volatile("" : "+l"(zb));         // keep the lane's column base in registers (no rematerialisation)
+    const int cc = active ? c : 0;
+    const float* zb = p.Zc + cc;
+    const int nseg = p.d >> 5;
+    const int extra = direct ? 2 : 1;      // ring slots a row's last batch adds: X piece (+ own Zcur piece)
 
     // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
     if (lane < nrows) { rp_a = __ldg(p.rowptr + r0 + lane); rp_b = __ldg(p.rowptr + r0 + lane + 1); }
-    {   // X rows (and, for the fused L1, the own Zcur rows) of the span are contiguous: pull them into L2 now so
-        // that the loads riding with each row's last batch are L2 hits instead of DRAM misses on the row's path
-        const int row_lines = (min(128, p.ld - slab * 128) * 4 + 127) >> 7;
-        for (int i = lane; i < nrows * row_lines; i += 32) {
-            const size_t off = (size_t)(r0 + i / row_lines) * p.ld + slab * 128 + (i % row_lines) * 32;
-            prefetch_l2(p.X + off);
-            if (direct) prefetch_l2(p.Zc + off);
-        }
-    }
     const int* __restrict__ offp = p.coloff + e_first;
     const float* __restrict__ wp = p.w + e_first;
     int pc = 0;
     float pw = 0.0f;
     if (lane < e_total) { pc = __ldg(offp + lane); pw = __ldg(wp + lane); }
-    int win_q = 0, filled = 0;   // window held in registers / stream offset published to the ring
+    int win_q = 0, filled = 0;   // window held in registers / stream offset published to the meta ring
 
-    if (direct) {   // rows that are skipped (sinks) contribute +0 to the chunk partial
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = lane * 4; i < nrows * p.d; i += 128) *reinterpret_cast<float4*>(stash + i) = zero;
-    }
-    float4 xs = make_float4(0.f, 0.f, 0.f, 0.f), zo = xs;
+    auto advance = [&](Cursor& cu) -> bool {   // move to the next batch; false when the span is exhausted
+        while (cu.pos >= cu.k) {
+            if (++cu.ri >= nrows) return false;
+            cu.a = __shfl_sync(kFull, rp_a, cu.ri);
+            cu.k = __shfl_sync(kFull, rp_b, cu.ri) - cu.a;
+            cu.pos = cu.k > p.hub_threshold ? cu.k : 0;   // hub rows have their own kernel; sinks have k = 0
+        }
+        return true;
+    };
 
-    for (int ri = 0; ri < nrows; ++ri) {
-        const int a = __shfl_sync(kFull, rp_a, ri);
-        const int k = __shfl_sync(kFull, rp_b, ri) - a;
-        if (k == 0 || k > p.hub_threshold) continue;    // sinks are never updated; hub rows have their own role
-        const size_t row_off = (size_t)(r0 + ri) * p.ld + c;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int pos = 0; pos < k; pos += 8) {
-            const int u = a + pos - e_first;            // stream offset of the batch
-            const int m = min(8, k - pos);
-            while (filled < u + m) {                    // publish the fetched window, fetch the next
-                const int base = (win_q & 1) * 32;
-                __syncwarp();                           // every lane is done reading the slots it replaces
+    Cursor ic, cq;
+    ic.ri = cq.ri = -1; ic.a = cq.a = 0; ic.k = cq.k = 0; ic.pos = cq.pos = 0;
+    bool more = advance(ic);
+    advance(cq);
+    int head = 0, tail = 0, used = 0, pending = 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float chunk_acc = 0.0f;
+
+    for (;;) {
+        // ---- issue: as many batches as the ring and the group budget allow ----
+        while (more && pending < kMaxPending) {
+            const int m = min(8, ic.k - ic.pos);
+            const bool last = ic.pos + m >= ic.k;
+            const int need = m + (last ? extra : 0);
+            if (used + need > kRing) break;
+            const int u = ic.a + ic.pos - e_first;          // stream offset of the batch
+            while (filled < u + m) {                        // publish the fetched window, fetch the next
+                const int base = (win_q & 3) * 32;
                 const int2 v = make_int2(pc, __float_as_int(pw));
-                ring[base + lane] = v;
-                if (base == 0 && lane < 8) ring[kMetaRing + lane] = v;   // mirror: a batch never wraps
+                meta[base + lane] = v;
+                if (base == 0 && lane < 8) meta[128 + lane] = v;   // mirror: a batch never wraps
                 __syncwarp();
                 filled = (++win_q) * 32;
                 const int off = filled + lane;
                 if (off < e_total) { pc = __ldg(offp + off); pw = __ldg(wp + off); }
             }
-            if (pos + 8 >= k && active) {               // last batch: the row's X and own Zcur ride along
-                xs = ld_stream4(p.X + row_off);
-                if (direct) zo = ldg4(p.Zc + row_off);
+            if (active) {
+                const int2* mp = meta + (u & 127);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < m)
+                        cp_async16(reinterpret_cast<float*>(ring + ((tail + i) & (kRing - 1)) * 32 + lane), zb + mp[i].x);
+                if (last) {
+                    const size_t row_off = (size_t)(r0 + ic.ri) * p.ld + cc;
+                    cp_async16(reinterpret_cast<float*>(ring + ((tail + m) & (kRing - 1)) * 32 + lane), p.X + row_off);
+                    if (direct)
+                        cp_async16(reinterpret_cast<float*>(ring + ((tail + m + 1) & (kRing - 1)) * 32 + lane), p.Zc + row_off);
+                }
             }
-            const int2* mp = ring + (u & (kMetaRing - 1));
-            switch (m) {
-                case 8: reduce_batch<8>(mp, zb, acc, col_blocked); break;
-                case 7: reduce_batch<7>(mp, zb, acc, col_blocked); break;
-                case 6: reduce_batch<6>(mp, zb, acc, col_blocked); break;
-                case 5: reduce_batch<5>(mp, zb, acc, col_blocked); break;
-                case 4: reduce_batch<4>(mp, zb, acc, col_blocked); break;
-                case 3: reduce_batch<3>(mp, zb, acc, col_blocked); break;
-                case 2: reduce_batch<2>(mp, zb, acc, col_blocked); break;
-                default: reduce_batch<1>(mp, zb, acc, col_blocked); break;
+            cp_async_commit();
+            tail += need; used += need; ++pending;
+            ic.pos += m;
+            more = advance(ic);
+        }
+        if (pending == 0) break;
+        // ---- consume the oldest batch ----
+        cp_async_wait_pending(pending);
+        const int m = min(8, cq.k - cq.pos);
+        const bool last = cq.pos + m >= cq.k;
+        const int2* mp = meta + ((cq.a + cq.pos - e_first) & 127);
+        if (cq.pos == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        switch (m) {
+            case 8: reduce_batch<8>(ring, head, mp, lane, acc, col_blocked); break;
+            case 7: reduce_batch<7>(ring, head, mp, lane, acc, col_blocked); break;
+            case 6: reduce_batch<6>(ring, head, mp, lane, acc, col_blocked); break;
+            case 5: reduce_batch<5>(ring, head, mp, lane, acc, col_blocked); break;
+            case 4: reduce_batch<4>(ring, head, mp, lane, acc, col_blocked); break;
+            case 3: reduce_batch<3>(ring, head, mp, lane, acc, col_blocked); break;
+            case 2: reduce_batch<2>(ring, head, mp, lane, acc, col_blocked); break;
+            default: reduce_batch<1>(ring, head, mp, lane, acc, col_blocked); break;
+        }
+        if (last) {
+            float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
+                const float4 xs = ring[((head + m) & (kRing - 1)) * 32 + lane];
+                const float4 out = finish_row(xs, acc, p.gamma);
+                *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
+                if (direct) dl = absdiff4(out, ring[((head + m + 1) & (kRing - 1)) * 32 + lane]);
             }
+            if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
         }
-        if (active) {
-            const float4 out = finish_row(xs, acc, p.gamma);
-            *reinterpret_cast<float4*>(p.Zn + row_off) = out;
-            if (direct) *reinterpret_cast<float4*>(stash + ri * p.d + c) = absdiff4(out, zo);
-        }
+        const int need = m + (last ? extra : 0);
+        head += need; used -= need; --pending;
+        cq.pos += m;
+        advance(cq);
     }
-    if (direct) {
-        // the span is one whole level-0 chunk: nrows*d/32 cascade rows, summed in order per cascade lane
-        __syncwarp();
-        const int ncr = nrows * (p.d >> 5);
-        float sum = 0.0f;
-        for (int r = 0; r < ncr; ++r) sum = fadd(sum, stash[r * 32 + lane]);
-        p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = sum;
-    }
+    // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
+    if (direct) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
 }
 
 // ------------------------------------------------------------------------------------------
 // hub role
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One (hub row, 32-column slab): all 8 warps copy, warp 0 reduces.
 __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm) {
@@ -364,19 +424,20 @@ k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, 
     P0[(size_t)g * 32 + lane] = acc;
 }
 
-__global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, 3) k_sweep_rows(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
-    int2* rings = reinterpret_cast<int2*>(smem);
-    float* stashes = reinterpret_cast<float*>(smem + (size_t)kRowWarps * kMetaSlots * sizeof(int2));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
+    float4* ring = reinterpret_cast<float4*>(mine);
+    int2* meta = reinterpret_cast<int2*>(mine + (size_t)32 * 32 * sizeof(float4));
     const int64_t task = (int64_t)blockIdx.x * kRowWarps + warp;
     const int64_t si = task / p.nslab;
     if (si >= p.n_spans) return;
-    const int meta = __ldg(p.span_meta + si);
+    const int smeta = __ldg(p.span_meta + si);
     const int2 se = __ldg(p.span_edges + si);
-    row_span_task(p, __ldg(p.span_row + si), meta & 0xff, (meta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
-                  rings + warp * kMetaSlots, stashes + warp * kWarpStash, se.x, se.y);
+    row_span_task(p, __ldg(p.span_row + si), smeta & 0xff, (smeta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
+                  meta, ring, se.x, se.y);
 }
 
 __global__ void __launch_bounds__(kHubThreads, 2) k_sweep_hubs(SweepParams p) {

@@ -27,8 +27,8 @@ __global__ void k_gather(const float4* __restrict__ Z, const int* __restrict__ i
     out[(size_t)warp * 32 + lane] = acc;
 }
 
-int main() {
-    const int N = 169343, D4 = 32, E = 1166243;
+int main(int argc, char** argv) {
+    const int N = argc > 1 ? atoi(argv[1]) : 169343, D4 = 32, E = 1166243;
     std::mt19937 rng(1);
     std::vector<int> uni(E), pl(E);
     std::uniform_real_distribution<double> u01(0, 1);
@@ -43,7 +43,7 @@ int main() {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int dist = 0; dist < 2; ++dist) {
         cudaMemcpy(idx, dist ? pl.data() : uni.data(), (size_t)E * 4, cudaMemcpyHostToDevice);
-        for (int wpsm : {8, 16, 24, 32, 48, 64}) {
+        for (int wpsm : {16, 24, 32, 64}) {
             auto run = [&](auto kern, int U) {
                 const int blocks = 148 * wpsm / 8;   // 256-thread blocks
                 float best = 1e9;
@@ -58,7 +58,7 @@ int main() {
                 printf("dist=%s warps/SM=%2d U=%2d  %.1f us  %.2f TB/s gathered  %.2f Gedges/s\n", dist ? "powerlaw" : "uniform ", wpsm, U,
                        best * 1e3, (double)E * 512 / (best * 1e-3) / 1e12, E / (best * 1e-3) / 1e9);
             };
-            run(k_gather<4>, 4); run(k_gather<8>, 8); run(k_gather<16>, 16);
+            run(k_gather<8>, 8);
         }
     }
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
