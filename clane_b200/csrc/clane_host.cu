@@ -81,8 +81,14 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
         const size_t first_span = spans.size();
         Span cur{r0, 0, 0, 0};
         for (int32_t v = r0; v < r1; ++v) {
-            int32_t k = h_rowptr[v + 1] - h_rowptr[v];
-            if (k > hub_threshold) { has_hub = true; hub_rows.push_back(v); k = 0; }
+            const int32_t k = h_rowptr[v + 1] - h_rowptr[v];
+            if (k > hub_threshold) {      // hub rows are never inside a span: its edge stream stays contiguous
+                has_hub = true;
+                hub_rows.push_back(v);
+                if (cur.work > 0) spans.push_back(cur);
+                cur = Span{v + 1, 0, 0, 0};
+                continue;
+            }
             if (cur.work > 0 && cur.work + k > span_edges) {   // close the span before this row
                 spans.push_back(cur);
                 cur = Span{v, 0, 0, 0};

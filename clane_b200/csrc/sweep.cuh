@@ -54,6 +54,7 @@ struct SweepParams {
     float* P0;
     int hub_threshold;
     const clane_patience* st;
+    int dbg_skip;               // profiling aid: bit0 no gathers, bit1 no X/own loads, bit2 no stores, bit3 fixed offsets
 };
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
@@ -177,6 +178,30 @@ __device__ __forceinline__ void reduce_batch(const float4* __restrict__ ring, in
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Warm L2 with what a span needs first (row pointers, the head of its (offset, w) stream, its X rows
+// and -- fused L1 -- its own Zcur rows).  Called by the warp that sweeps a span `kPrefetchAhead`
+// places earlier in the schedule: those cold, streaming reads are otherwise three serial DRAM round
+// trips at the start of every span.
+constexpr int kPrefetchAhead = 2048;
+__device__ __forceinline__ void prefetch_span(const SweepParams& p, int64_t si, int slab, int lane) {
+    if (si >= p.n_spans) return;
+    const int r0 = __ldg(p.span_row + si);
+    const int nrows = __ldg(p.span_meta + si) & 0xff;
+    const int2 se = __ldg(p.span_edges + si);
+    if (lane == 0) { prefetch_l2(p.rowptr + r0); prefetch_l2(p.rowptr + r0 + nrows); }
+    if (lane < 4) {   // first 128 edges of the stream
+        if (lane * 32 < se.y) { prefetch_l2(p.coloff + se.x + lane * 32); prefetch_l2(p.w + se.x + lane * 32); }
+    }
+    const int row_lines = (min(128, p.ld - slab * 128) * 4 + 127) >> 7;
+    for (int i = lane; i < nrows * row_lines; i += 32) {
+        const size_t off = (size_t)(r0 + i / row_lines) * p.ld + slab * 128 + (i % row_lines) * 32;
+        prefetch_l2(p.X + off);
+        if (p.fuse) prefetch_l2(p.Zc + off);
+    }
+}
+
 __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int nrows, bool direct, int slab,
                                               int lane, int2* meta, float4* ring, int e_first, int e_total) {
     const int c = slab * 128 + lane * 4;
@@ -196,6 +221,9 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
     float pw = 0.0f;
     if (lane < e_total) { pc = __ldg(offp + lane); pw = __ldg(wp + lane); }
     int win_q = 0, filled = 0;   // window held in registers / stream offset published to the meta ring
+    // the rest of this span's (offset, w) stream: one L2 prefetch per 128-byte line now, so that the
+    // window loads further down are L2 hits instead of DRAM round trips on the warp's critical path
+    for (int i = 32 + lane * 32; i < e_total; i += 32 * 32) { prefetch_l2(offp + i); prefetch_l2(wp + i); }
 
     auto advance = [&](Cursor& cu) -> bool {   // move to the next batch; false when the span is exhausted
         while (cu.pos >= cu.k) {
@@ -237,9 +265,10 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
                 const int2* mp = meta + (u & 127);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (i < m)
-                        cp_async16(reinterpret_cast<float*>(ring + ((tail + i) & (kRing - 1)) * 32 + lane), zb + mp[i].x);
-                if (last) {
+                    if (i < m && !(p.dbg_skip & 1))
+                        cp_async16(reinterpret_cast<float*>(ring + ((tail + i) & (kRing - 1)) * 32 + lane),
+                                   zb + ((p.dbg_skip & 8) ? (size_t)((r0 + i) * p.ld) : (size_t)mp[i].x));
+                if (last && !(p.dbg_skip & 2)) {
                     const size_t row_off = (size_t)(r0 + ic.ri) * p.ld + cc;
                     cp_async16(reinterpret_cast<float*>(ring + ((tail + m) & (kRing - 1)) * 32 + lane), p.X + row_off);
                     if (direct)
@@ -273,7 +302,7 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
             if (active) {
                 const float4 xs = ring[((head + m) & (kRing - 1)) * 32 + lane];
                 const float4 out = finish_row(xs, acc, p.gamma);
-                *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
+                if (!(p.dbg_skip & 4)) *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
                 if (direct) dl = absdiff4(out, ring[((head + m + 1) & (kRing - 1)) * 32 + lane]);
             }
             if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
@@ -436,6 +465,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) k_sweep_rows(SweepParams p) {
     if (si >= p.n_spans) return;
     const int smeta = __ldg(p.span_meta + si);
     const int2 se = __ldg(p.span_edges + si);
+    prefetch_span(p, si + kPrefetchAhead, (int)(task - si * p.nslab), lane);
     row_span_task(p, __ldg(p.span_row + si), smeta & 0xff, (smeta >> 8) != 0 && p.fuse, (int)(task - si * p.nslab), lane,
                   meta, ring, se.x, se.y);
 }
