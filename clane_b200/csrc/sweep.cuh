@@ -67,7 +67,7 @@ constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 // row kernel shared memory per warp: (offset, w) ring | 32 x 512-byte row-piece ring
-constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)32 * 32 * sizeof(float4);
+constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)16 * 32 * sizeof(float4);
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
 constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float);
@@ -136,14 +136,14 @@ __device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl
 //   issue   : per "batch" (one 8-neighbour block of one row) it reads the neighbours' row
 //             offsets from its (offset, w) ring and starts one 512-byte cp.async per neighbour
 //             (16 bytes per lane: lane L copies exactly the float4 of columns it will reduce,
-//             so no barrier is ever needed) into its private 32-slot ring of row pieces; the
+//             so no barrier is ever needed) into its private 16-slot ring of row pieces; the
 //             row's X piece (and own Zcur piece, fused L1) ride with the row's last batch;
 //   consume : waits for the OLDEST batch only (cp.async.wait_group), reduces it in the
 //             reference's order, and frees its slots.
-// Up to 32 row pieces (16 KB) per warp are in flight whatever the row lengths: the gathers of
+// Up to 16 row pieces (8 KB) per warp are in flight whatever the row lengths: the gathers of
 // the next rows overlap the reduction of the current one (decoupled access / execute).
-constexpr int kRing = 32;              // 512-byte row-piece slots per warp
-constexpr int kMaxPending = 8;         // batches in flight per warp
+constexpr int kRing = 16;              // 512-byte row-piece slots per warp
+constexpr int kMaxPending = 6;         // batches in flight per warp
 
 struct Cursor { int ri, a, k, pos; };
 
@@ -453,13 +453,13 @@ k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, 
     P0[(size_t)g * 32 + lane] = acc;
 }
 
-__global__ void __launch_bounds__(kRowThreads, 3) k_sweep_rows(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     float4* ring = reinterpret_cast<float4*>(mine);
-    int2* meta = reinterpret_cast<int2*>(mine + (size_t)32 * 32 * sizeof(float4));
+    int2* meta = reinterpret_cast<int2*>(mine + (size_t)16 * 32 * sizeof(float4));
     const int64_t task = (int64_t)blockIdx.x * kRowWarps + warp;
     const int64_t si = task / p.nslab;
     if (si >= p.n_spans) return;
