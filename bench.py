@@ -242,11 +242,11 @@ def run_gpu(args):
     if world > 1:
         from clane_b200 import dist as cdist
         runner = cdist.ShardedSweeper(g, sim, GAMMA)
+        S = None
     else:
         runner = None
-
-    S = g._device_state()
-    g._build_P_device(sim)
+        S = g._device_state()
+        g._build_P_device(sim)
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
     gamma = ctypes.c_float(float(np.float32(GAMMA)))
@@ -260,19 +260,19 @@ def run_gpu(args):
         _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.rowptr.data_ptr(),
                                  S.col.data_ptr(), S.w.data_ptr(), gamma, S.amount.data_ptr() if with_l1 else 0, 0, 0, 0,
                                  sh))
-        launches_per_step[0] = S.plan.launches_per_sweep if with_l1 else 1
+        launches_per_step[0] = S.plan.launches_per_sweep if with_l1 else 1 + (1 if S.plan.n_hub_rows else 0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(steps, with_l1):
+    def timed_loop(steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record(stream)
         for i in range(steps):
-            one_step(i, with_l1)
+            one_step(i, True)
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -282,19 +282,38 @@ def run_gpu(args):
             ms = float(t.item())
         return ms
 
+    def kernel_loop(steps):
+        """The same steps again with the library's event brackets on: average duration of the dominant
+        kernel (k_sweep_rows) alone, measured on the stream it is launched on."""
+        plan = S.plan if runner is None else runner.plan
+        _lib.check(L.clane_plan_profile(plan.handle, 1))
+        acc = np.zeros(4)
+        buf = (ctypes.c_float * 4)()
+        for i in range(steps):
+            one_step(i, True)
+            _lib.check(L.clane_plan_profile_read(plan.handle, buf))
+            acc += np.array(buf[:])
+        _lib.check(L.clane_plan_profile(plan.handle, 0))
+        acc /= steps
+        if world > 1:
+            t = torch.tensor(acc, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            acc = t.cpu().numpy()
+        return acc
+
     for i in range(max(args.warmup, 3)):
         one_step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    total_ms = timed_loop(args.steps, True)                 # the metric: whole steps
-    kernel_ms = timed_loop(args.steps, False)               # the dominant kernel alone (roofline)
+    total_ms = timed_loop(args.steps)                                  # the metric: whole steps
+    kern = kernel_loop(min(args.steps, 200))                           # per-kernel durations (roofline)
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
     value = e / (ms_per_step * 1e-3)
     amount = float(S.amount.cpu()[0]) if runner is None else runner.last_amount()
 
     peak, peak_src = measured_peak()
-    kern_ms = kernel_ms / args.steps
+    kern_ms = float(kern[0])
     bytes_sweep = sweep_bytes(n, e, d)
     achieved = bytes_sweep / world / (kern_ms * 1e-3) / 1e9
     line = {
@@ -307,9 +326,14 @@ def run_gpu(args):
                                                                   "NCCL all-gather of Z per sweep",
                    "l2": f"no flush: working set {(3 * n * d * 4 + 8 * e) / 1e6:.0f} MB exceeds the 126 MB L2"
                          if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",
-                   "step": "sweep kernel(s) + exact L1 cascade + finish; P frozen"},
+                   "step": "row + hub sweep kernels, exact L1 change (fused partials / cascade), device patience; P frozen",
+                   "plan": {"group_rows": (S.plan if runner is None else runner.plan).group_rows,
+                            "spans": (S.plan if runner is None else runner.plan).n_spans,
+                            "hub_rows": (S.plan if runner is None else runner.plan).n_hub_rows,
+                            "fused_l1": (S.plan if runner is None else runner.plan).fused_l1}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(name), "kernel": "k_sweep", "kernel_ms": kern_ms,
+                     "traffic": ncu_traffic(name), "kernel": "k_sweep_rows", "kernel_ms": kern_ms,
+                     "sweep_ms_serialized": float(kern[1]), "l1_tail_ms": float(kern[2]), "hub_kernel_ms": float(kern[3]),
                      "algorithmic_bytes_per_launch": bytes_sweep / world, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "whole_step_gbs": bytes_sweep / world / (ms_per_step * 1e-3) / 1e9},
@@ -321,7 +345,7 @@ def run_gpu(args):
     if rank == 0 and world == 1:
         line["e2e"] = e2e_session(L, g, X, n, e, d, args.steps)
     elif rank == 0:
-        line["e2e"] = runner.e2e(args.steps) if hasattr(runner, "e2e") else None
+        line["e2e"] = None   # the host-buffer session API is single-GPU; see DESIGN.md
 
     if not args.no_converge and world == 1:
         g.set_Z(g.X)

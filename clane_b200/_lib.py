@@ -51,6 +51,8 @@ SIGNATURES = {
     "clane_l1_diff": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_l1_partial": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
     "clane_l1_finish": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
+    "clane_plan_profile": (C.c_int, [c_vp, C.c_int]),
+    "clane_plan_profile_read": (C.c_int, [c_vp, c_f32p]),
     "clane_patience_reset": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp]),
     "clane_session_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, c_vp, c_vp, C.c_int32]),
     "clane_session_destroy": (C.c_int, [c_vp]),

@@ -315,18 +315,28 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     // The hub rows (few, long in-order chains) run on the plan's side stream next to the row kernel.
     const int64_t hub_ctas = (int64_t)p.n_hub_rows * plan->nslab32;
     const int64_t row_ctas = ((int64_t)p.n_spans * plan->nslab + kRowWarps - 1) / kRowWarps;
+    const bool prof = plan->profile;
+    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[0], st));
     if (hub_ctas > 0) {
         CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
         CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], plan->side));
         k_sweep_hubs<<<(unsigned)hub_ctas, kHubThreads, kHubSmemBytes, plan->side>>>(p);
         CLANE_LAUNCH_CHECK();
+        if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], plan->side));
         CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
     }
+    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[1], st));
     if (row_ctas > 0) {
         k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, kRowSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
+    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[2], st));
     if (hub_ctas > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+    struct ProfTail {   // records the end-of-sweep event on every exit path below
+        clane_plan* pl; cudaStream_t s;
+        ~ProfTail() { if (pl->profile) cudaEventRecord(pl->ev_prof[3], s); }
+    } prof_tail{plan, st};
     if (!want_l1) return CLANE_OK;
     const int64_t n_elems = (int64_t)plan->n * plan->d;
     ElemAbsDiff el{d_Znext, d_Zcur, plan->d, plan->ld};
@@ -367,6 +377,25 @@ int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, floa
     ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
     return cascade_launch_finish(el, (int64_t)plan->n * plan->d, d_p1, plan->d_p2, d_out, d_state, d_amounts_log,
                                  log_cap, nullptr, (cudaStream_t)s);
+}
+
+int clane_plan_profile(clane_plan* plan, int enable) {
+    if (!plan) return CLANE_EINVAL;
+    if (enable && !plan->ev_prof[0])
+        for (int i = 0; i < 6; ++i) CLANE_CUDA(cudaEventCreate(&plan->ev_prof[i]));
+    plan->profile = enable != 0;
+    return CLANE_OK;
+}
+
+int clane_plan_profile_read(clane_plan* plan, float* h_ms) {
+    if (!plan || !h_ms || !plan->ev_prof[0]) return CLANE_EINVAL;
+    CLANE_CUDA(cudaEventSynchronize(plan->ev_prof[3]));
+    CLANE_CUDA(cudaEventElapsedTime(&h_ms[0], plan->ev_prof[1], plan->ev_prof[2]));   // row kernel
+    CLANE_CUDA(cudaEventElapsedTime(&h_ms[1], plan->ev_prof[0], plan->ev_prof[3]));   // whole sweep
+    CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[2], plan->ev_prof[3]));   // join + L1 tail
+    h_ms[3] = 0.0f;
+    if (plan->n_hub_rows > 0) CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // hub kernel
+    return CLANE_OK;
 }
 
 int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweeps, clane_stream_t s) {

@@ -25,6 +25,8 @@ struct clane_plan {
     const int32_t* coloff_src = nullptr;
     cudaStream_t side = nullptr;       // hub kernel runs here, forked from / joined to the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool profile = false;              // record timing events around the kernels of each sweep
+    cudaEvent_t ev_prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;

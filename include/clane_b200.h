@@ -167,6 +167,13 @@ int clane_l1_partial(clane_plan* plan, const float* d_Za, const float* d_Zb, int
 int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_p1, float* d_out,
                     clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
 
+/* Measurement aid: when enabled, clane_sweep brackets its kernels with CUDA events on the
+ * streams they are launched on; clane_plan_profile_read waits for the last sweep and returns
+ * h_ms[0] = row kernel (k_sweep_rows), h_ms[1] = whole sweep, h_ms[2] = hub join + exact L1
+ * tail (fix-up, level-1, finish), h_ms[3] = hub kernel (side stream; 0 if there is none). */
+int clane_plan_profile(clane_plan* plan, int enable);
+int clane_plan_profile_read(clane_plan* plan, float* h_ms);
+
 /* Reset the device patience state for a new propagate() call (embedder.py:78-79). */
 int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweeps, clane_stream_t s);
 
