@@ -247,7 +247,8 @@ def run_gpu(args):
         runner = None
         S = g._device_state()
         g._build_P_device(sim)
-    stream = torch.cuda.current_stream()
+    stream = S.stream if S is not None else torch.cuda.current_stream()
+    torch.cuda.synchronize()
     sh = stream.cuda_stream
     gamma = ctypes.c_float(float(np.float32(GAMMA)))
     launches_per_step = [0]

@@ -127,6 +127,7 @@ int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_span_edges); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
+    for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int i = 0; i < 6; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);

@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "cascade.cuh"
 #include "common.cuh"
@@ -280,21 +281,13 @@ int clane_build_p_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ro
     return clane_row_softmax(d_w, d_norms2, plan->row_lo, plan->row_hi, d_rowptr, d_w, s);
 }
 
-int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext, const int32_t* d_rowptr,
-                const int32_t* d_col, const float* d_w, float gamma, float* d_amount, clane_patience* d_state,
-                float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
-    if (!plan || !plan->has_schedule || !d_X || !d_Zcur || !d_Znext || !d_rowptr) return CLANE_EINVAL;
-    if (plan->e > 0 && (!d_col || !d_w)) return CLANE_EINVAL;
-    cudaStream_t st = (cudaStream_t)s;
+static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext,
+                         const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma, float* d_amount,
+                         clane_patience* d_state, float* d_amounts_log, int32_t log_cap, cudaStream_t st) {
     const bool want_l1 = d_amount != nullptr || d_state != nullptr;
     SweepParams p;
     p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
     p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
-    if (plan->e > 0 && plan->coloff_src != d_col) {   // first sweep with this column array
-        k_col_offsets<<<(unsigned)((plan->e + 255) / 256), 256, 0, st>>>(d_col, plan->e, plan->ld, plan->d_coloff);
-        CLANE_LAUNCH_CHECK();
-        plan->coloff_src = d_col;
-    }
     p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
     p.hub_rows = plan->d_hub_rows; p.n_hub_rows = plan->n_hub_rows; p.nslab32 = plan->nslab32;
     p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.span_edges = plan->d_span_edges;
@@ -355,6 +348,57 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
                                      nullptr, st);
     }
     return cascade_launch(el, n_elems, plan->d_p1, plan->d_p2, d_amount, d_state, d_amounts_log, log_cap, st);
+}
+
+int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext, const int32_t* d_rowptr,
+                const int32_t* d_col, const float* d_w, float gamma, float* d_amount, clane_patience* d_state,
+                float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_X || !d_Zcur || !d_Znext || !d_rowptr) return CLANE_EINVAL;
+    if (plan->e > 0 && (!d_col || !d_w)) return CLANE_EINVAL;
+    cudaStream_t st = (cudaStream_t)s;
+    if (plan->e > 0 && plan->coloff_src != d_col) {   // first sweep with this column array
+        k_col_offsets<<<(unsigned)((plan->e + 255) / 256), 256, 0, st>>>(d_col, plan->e, plan->ld, plan->d_coloff);
+        CLANE_LAUNCH_CHECK();
+        plan->coloff_src = d_col;
+    }
+    static const bool env_graphs = getenv("CLANE_NO_GRAPHS") == nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (!plan->use_graphs || !env_graphs || plan->profile || cap != cudaStreamCaptureStatusNone || st == nullptr)
+        return sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state, d_amounts_log,
+                             log_cap, st);
+    // One sweep = up to five kernels on two streams.  Replay it as a CUDA graph: a propagate() call
+    // alternates between two argument sets (Zcur/Znext swapped), so each is captured once.
+    const void* key[10] = {d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, d_amount, d_state, d_amounts_log, st};
+    clane_plan::SweepGraph* slot = nullptr;
+    for (auto& g : plan->graphs)
+        if (g.exec && g.gamma == gamma && g.log_cap == log_cap && memcmp(g.key, key, sizeof(key)) == 0) slot = &g;
+    if (!slot) {
+        slot = plan->graphs[0].last_use <= plan->graphs[1].last_use ? &plan->graphs[0] : &plan->graphs[1];
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CLANE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state,
+                               d_amounts_log, log_cap, st);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != CLANE_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc != CLANE_OK) return rc;
+            plan->use_graphs = false;   // capture unsupported here: direct launches from now on
+            return sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state,
+                                 d_amounts_log, log_cap, st);
+        }
+        ce = cudaGraphInstantiate(&slot->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { slot->exec = nullptr; return (int)ce; }
+        memcpy(slot->key, key, sizeof(key));
+        slot->gamma = gamma;
+        slot->log_cap = log_cap;
+    }
+    slot->last_use = ++plan->graph_clock;
+    CLANE_CUDA(cudaGraphLaunch(slot->exec, st));
+    return CLANE_OK;
 }
 
 int clane_l1_diff(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_out, clane_stream_t s) {

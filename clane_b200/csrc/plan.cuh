@@ -25,6 +25,17 @@ struct clane_plan {
     const int32_t* coloff_src = nullptr;
     cudaStream_t side = nullptr;       // hub kernel runs here, forked from / joined to the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between
+    // two argument sets, so two entries suffice; anything else falls back to direct launches.
+    struct SweepGraph {
+        const void* key[10] = {nullptr};
+        float gamma = 0.0f;
+        int log_cap = 0;
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long last_use = 0;
+    } graphs[2];
+    unsigned long long graph_clock = 0;
+    bool use_graphs = true;
     bool profile = false;              // record timing events around the kernels of each sweep
     cudaEvent_t ev_prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float* d_P0 = nullptr;      // [n_groups][32]   (fused only)

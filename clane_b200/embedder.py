@@ -77,7 +77,7 @@ class Embedder(object):
             self.propagate()
             _lib.check(L.clane_l1_diff(S.plan.handle, S.Z[S.cur].data_ptr(), prev.data_ptr(), S.amount.data_ptr(),
                                        _lib.stream_handle()), "clane_l1_diff")
-            amount_updated_Z_current = float(S.amount.cpu()[0])
+            amount_updated_Z_current = float(S.amount.cpu()[0])   # synchronises the current stream
             if self.minimum_amount_updated_Z > amount_updated_Z_current:
                 self.tolerences['global'].reset()
                 self.minimum_amount_updated_Z = amount_updated_Z_current
@@ -96,7 +96,10 @@ class Embedder(object):
         g._build_P_device(self.similarity_measure)
         tol = self.tolerences['propagation']
         tol.reset()
-        stream = _lib.stream_handle()
+        # the sweeps run on the graph's own stream (capturable, so whole sweeps replay as CUDA graphs)
+        caller = torch.cuda.current_stream()
+        S.stream.wait_stream(caller)
+        stream = S.stream.cuda_stream
         _lib.check(L.clane_patience_reset(S.state.data_ptr(), int(tol.initial_value), int(max_sweeps), stream),
                    "clane_patience_reset")
         gamma = ctypes.c_float(float(np.float32(self.gamma)))
@@ -111,14 +114,16 @@ class Embedder(object):
                                          S.rowptr.data_ptr(), S.col.data_ptr(), S.w.data_ptr(), gamma,
                                          0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream), "clane_sweep")
                 enqueued += 1
-            S.state_host.copy_(S.state, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(S.stream):
+                S.state_host.copy_(S.state, non_blocking=True)
+            S.stream.synchronize()
             st = _lib.Patience.from_buffer_copy(S.state_host.numpy().tobytes())
             if history_Z is not None:
                 history_Z.append(dst[:S.n, :S.d].cpu())
             if st.stop:
                 break
         done = int(st.sweeps)
+        caller.wait_stream(S.stream)
         S.cur = (start + done) & 1
         amounts = S.log[:min(done, S.log_cap)].cpu().numpy()
         self.sweeps_per_call.append(done)

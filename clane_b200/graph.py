@@ -223,6 +223,7 @@ class Graph(Dataset):
             S.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
             S.log_cap = 1 << 16
             S.log = torch.zeros(S.log_cap, dtype=torch.float32, device=dev)
+            S.stream = torch.cuda.Stream(device=dev)   # sweeps run here (a capturable stream: CUDA-graph replay)
             _lib.check(L.clane_edge_rows(S.rowptr.data_ptr(), n, e, S.erow.data_ptr(), _lib.stream_handle()),
                        "clane_edge_rows")
             self._dev = S
