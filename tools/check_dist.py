@@ -1,0 +1,37 @@
+"""torchrun check (N >= 2 GPUs): the row-partitioned sweeps equal the single-GPU ones bit for bit."""
+import os, sys
+from pathlib import Path
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from clane_b200 import similarity, synth, dist as cdist
+from clane_b200.embedder import Embedder
+from clane_b200.graph import Graph
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+ok = True
+for shape, scale in (("arxiv", 0.3), ("products", 0.01), ("pubmed", 1.0)):
+    n, src, dst, X = synth.make_graph(shape, seed=0, scale=scale)
+    g = Graph.from_arrays(n, src, dst, X)
+    sim = similarity.CosineSimilarity()
+    sw = cdist.ShardedSweeper(g, sim, 0.76)
+    amounts = []
+    for _ in range(4):
+        sw.sweep(True)
+        amounts.append(sw.last_amount())
+    Zs = sw.Z_host().numpy()
+    g1 = Graph.from_arrays(n, src, dst, X)
+    e = Embedder(g1, sim, device=torch.device("cuda", lr), gamma=0.76, tolerence=10)
+    e.verbose = False
+    e.propagate(max_sweeps=4)
+    same = np.array_equal(Zs, g1.Z.numpy()) and np.array_equal(np.float32(amounts), e.amounts_per_call[0])
+    t = torch.tensor([int(same)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"{shape} x{scale}: n={n} e={g._nnz} world={world} sharded == single-GPU: {bool(t.item())}", flush=True)
+    ok &= bool(t.item())
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
