@@ -153,7 +153,7 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     clane_plan* plan = new (std::nothrow) clane_plan();
     if (!plan) return (int)cudaErrorMemoryAllocation;
     plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
-    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 128;
+    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 1024;
     plan->span_edges = 128;
     // tuning aids (benchmark sweeps only)
     if (const char* v = getenv("CLANE_HUB_THRESHOLD")) plan->hub_threshold = std::max(atoi(v), 8);

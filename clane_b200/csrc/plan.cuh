@@ -7,7 +7,7 @@ struct clane_plan {
     int64_t e = 0;
     int32_t row_lo = 0, row_hi = 0;
     int64_t edge_lo = 0, edge_hi = 0;   // rowptr[row_lo], rowptr[row_hi]
-    int32_t hub_threshold = 128;
+    int32_t hub_threshold = 1024;
     bool has_schedule = false;
     int32_t G = 8;              // rows per group
     int32_t nslab = 1;

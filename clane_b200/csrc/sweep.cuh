@@ -59,7 +59,7 @@ struct SweepParams {
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
 constexpr int kRowWarps = 4;
-constexpr int kHubThreads = 256;               // hub kernel: 8 warps per CTA
+constexpr int kHubThreads = 288;               // hub kernel: 9 warps per CTA (chain, 4 pre-reduce, 4 copy)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
 constexpr int kMetaSlots = kMetaRing + 8;
 constexpr int kHubStage = 32;                  // neighbours per ring stage
@@ -70,7 +70,8 @@ constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)16 * 32 * sizeof(float4);
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
-constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float);
+constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float) +
+                                 (size_t)2 * 4 * 64 * sizeof(float);   // copy ring | w ring | X/Y of two stages
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -320,104 +321,134 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
 // hub role
 // ------------------------------------------------------------------------------------------
 
-// One (hub row, 32-column slab): all 8 warps copy, warp 0 reduces.
-__device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm) {
+// One (hub row, 32-column slab) per CTA of 9 warps, three roles, lock-stepped per 32-neighbour stage:
+//   warps 5-8  copy: warp 5+b streams block b (8 neighbours x 128 B) of every stage into the ring with two
+//              cp.async per stage; (col*ld, w) are prefetched 8 stages ahead in statically indexed registers;
+//   warps 1-4  pre-reduce: warp 1+b computes, for block b of the stage that has just landed, the two
+//              sub-trees of the 8-neighbour pattern that do not involve the running sum,
+//              X = fma(w5,z5, w7*z7) and Y = fma(w0,z0, w2*z2) + fma(w1,z1, w3*z3), per column;
+//   warp 0     chain: a = fma(w6,z6,a); a = fma(w4,z4,a); a += X; a += Y for the blocks of the previous
+//              stage -- 4 dependent operations per 8 neighbours, the minimum the reference's order allows.
+// Columns in the sequential regime (>= 16*floor(d/16)) are reduced by warp 0 alone, straight from the ring.
+constexpr int kHubWarps = 9;
+
+__device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm, float* xy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
     const int nst = (k + kHubStage - 1) / kHubStage;
-    // copy view: this lane moves 16 bytes (4 columns) of neighbour `nb` of every stage
-    const int nb = warp * 4 + (lane >> 3);
+    const int ccol = slab32 * 32 + lane;                 // reduce view: one column per lane
+    const bool blk = ccol < (p.d / 16) * 16;             // k > hub_threshold >= 8
+    const bool all_blk = slab32 * 32 + 31 < (p.d / 16) * 16;
+    // copy view (warps 5-8): this lane moves 16 bytes of neighbours nb0 and nb0 + 4 of every stage
+    const int cw = warp - 5;
+    const int nb0 = cw * 8 + (lane >> 3);
     const int pcol = slab32 * 32 + (lane & 7) * 4;
     const bool pact = pcol < p.ld;
-    // reduce view (warp 0): one column per lane
-    const int ccol = slab32 * 32 + lane;
-    const bool blk = ccol < (p.d / 16) * 16;           // k > hub_threshold >= 8
 
-    // (offset, w) of stage s live in cq[s % kHubMeta] / wq[s % kHubMeta]; a slot is refilled for stage
-    // s + kHubMeta right after stage s is issued.  The stage loop is unrolled kHubMeta times so the
-    // slot index is static: nothing reads a prefetched register before it is needed (a rotating
-    // register queue would wait on the newest load every iteration).
-    int cq[kHubMeta];
+    int cq0[kHubMeta], cq1[kHubMeta];
     float wq[kHubMeta];
 #pragma unroll
-    for (int i = 0; i < kHubMeta; ++i) {
-        const int idx = i * kHubStage + nb, widx = i * kHubStage + lane;
-        cq[i] = idx < k ? __ldg(p.coloff + a + idx) : 0;
-        wq[i] = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
+    for (int i = 0; i < kHubMeta; ++i) { cq0[i] = cq1[i] = 0; wq[i] = 0.0f; }
+    if (warp >= 5) {
+#pragma unroll
+        for (int i = 0; i < kHubMeta; ++i) {
+            const int i0 = i * kHubStage + nb0, i1 = i0 + 4, wi = i * kHubStage + lane;
+            cq0[i] = i0 < k ? __ldg(p.coloff + a + i0) : 0;
+            cq1[i] = i1 < k ? __ldg(p.coloff + a + i1) : 0;
+            wq[i] = (warp == 5 && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
+        }
     }
-    auto issue = [&](int si, int& cslot, float& wslot) {   // si: stage to issue; its meta sits in (cslot, wslot)
+    auto issue = [&](int si, int& c0, int& c1, float& wslot) {   // copy warps only
         const int slot = si % kHubStages;
-        if (si * kHubStage + nb < k && pact)
-            cp_async16(ringf + (size_t)slot * kHubStage * 32 + nb * 32 + (lane & 7) * 4, p.Zc + (size_t)cslot + pcol);
-        if (warp == 0) wsm[slot * kHubStage + lane] = wslot;
+        float* dst = ringf + (size_t)slot * kHubStage * 32 + (lane & 7) * 4;
+        if (pact) {
+            if (si * kHubStage + nb0 < k) cp_async16(dst + nb0 * 32, p.Zc + (size_t)c0 + pcol);
+            if (si * kHubStage + nb0 + 4 < k) cp_async16(dst + (nb0 + 4) * 32, p.Zc + (size_t)c1 + pcol);
+        }
+        if (warp == 5) wsm[slot * kHubStage + lane] = wslot;
         cp_async_commit();
-        const int idx = (si + kHubMeta) * kHubStage + nb, widx = (si + kHubMeta) * kHubStage + lane;
-        cslot = idx < k ? __ldg(p.coloff + a + idx) : 0;
-        wslot = (warp == 0 && widx < k) ? __ldg(p.w + a + widx) : 0.0f;
+        const int i0 = (si + kHubMeta) * kHubStage + nb0, i1 = i0 + 4, wi = (si + kHubMeta) * kHubStage + lane;
+        c0 = i0 < k ? __ldg(p.coloff + a + i0) : 0;
+        c1 = i1 < k ? __ldg(p.coloff + a + i1) : 0;
+        wslot = (warp == 5 && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
     };
-    auto consume = [&](int s, float& acc) {
+    // pre-reduce block b of stage s (a full block) -> xy[s & 1][b][0..1][lane]
+    auto prereduce = [&](int s, int b) {
+        const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + b * 8 * 32 + lane;
+        const float4* w4 = reinterpret_cast<const float4*>(wsm + (s % kHubStages) * kHubStage + b * 8);
+        const float4 wa = w4[0], wb = w4[1];
+        const float z0 = src[0], z1 = src[32], z2 = src[64], z3 = src[96], z5 = src[160], z7 = src[224];
+        const float x = ffma(wb.y, z5, fmul(wb.w, z7));
+        const float y = fadd(ffma(wa.x, z0, fmul(wa.z, z2)), ffma(wa.y, z1, fmul(wa.w, z3)));
+        float* dst = xy + ((s & 1) * 4 + b) * 64 + lane;
+        dst[0] = x;
+        dst[32] = y;
+    };
+    // chain over stage s (its X/Y were written during the previous interval)
+    auto chain = [&](int s, float& acc) {
         const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
         const float* wrow = wsm + (s % kHubStages) * kHubStage;
+        const float* xys = xy + (s & 1) * 4 * 64 + lane;
         const int cnt = min(kHubStage, k - s * kHubStage);
-        if (cnt == kHubStage) {
-            // full stage: all 32 values and weights are fetched before the in-order chain starts
-            float z[kHubStage];
-            float4 w4[kHubStage / 4];
+        const int nfull = cnt >> 3;
+        if (blk) {
+            float z6[4], z4[4], w6[4], w4v[4], xv[4], yv[4];
 #pragma unroll
-            for (int i = 0; i < kHubStage; ++i) z[i] = src[i * 32];
-#pragma unroll
-            for (int i = 0; i < kHubStage / 4; ++i) w4[i] = reinterpret_cast<const float4*>(wrow)[i];
-#pragma unroll
-            for (int b = 0; b < kHubStage / 8; ++b) {
-                const float ww[8] = {w4[2 * b].x, w4[2 * b].y, w4[2 * b].z, w4[2 * b].w,
-                                     w4[2 * b + 1].x, w4[2 * b + 1].y, w4[2 * b + 1].z, w4[2 * b + 1].w};
-                const float* zz = z + 8 * b;
-                if (blk) acc = blocked8(acc, ww, zz[0], zz[1], zz[2], zz[3], zz[4], zz[5], zz[6], zz[7]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], zz[i], acc);
+            for (int b = 0; b < 4; ++b)
+                if (b < nfull) {
+                    z6[b] = src[(b * 8 + 6) * 32]; z4[b] = src[(b * 8 + 4) * 32];
+                    w6[b] = wrow[b * 8 + 6]; w4v[b] = wrow[b * 8 + 4];
+                    xv[b] = xys[b * 64]; yv[b] = xys[b * 64 + 32];
                 }
-            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (b < nfull) {
+                    acc = ffma(w6[b], z6[b], acc);
+                    acc = ffma(w4v[b], z4[b], acc);
+                    acc = fadd(acc, xv[b]);
+                    acc = fadd(acc, yv[b]);
+                }
         } else {
-            int o = 0;
-            for (; o + 8 <= cnt; o += 8) {
-                float ww[8], z[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { ww[i] = wrow[o + i]; z[i] = src[(o + i) * 32]; }
-                if (blk) acc = blocked8(acc, ww, z[0], z[1], z[2], z[3], z[4], z[5], z[6], z[7]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc = ffma(ww[i], z[i], acc);
-                }
-            }
-            for (; o < cnt; ++o) acc = ffma(wrow[o], src[o * 32], acc);
+            for (int o = 0; o < nfull * 8; ++o) acc = ffma(wrow[o], src[o * 32], acc);
         }
+        for (int o = nfull * 8; o < cnt; ++o) acc = ffma(wrow[o], src[o * 32], acc);   // k mod 8 leftovers
     };
 
-    static_assert(kHubStages - 1 == 2 * kHubMeta - 1 || (kHubStages - 1) % kHubMeta == kHubMeta - 1,
-                  "prologue must end on a slot boundary");
-    // prologue: stages 0 .. kHubStages-2 in flight (kHubStages - 1 = 15 = 8 + 7 issues)
+    // prologue: stages 0 .. kAhead-1 in flight (slot = stage % 8).  The chain lags the copies by one more
+    // stage than a plain ring would, so only kHubStages - 2 stages may be in flight: interval s overwrites the
+    // ring slot of stage s - 2, which the chain finished in interval s - 1.
+    constexpr int kAhead = kHubStages - 2;
+    if (warp >= 5) {
 #pragma unroll
-    for (int s = 0; s < kHubStages - 1; ++s) {
-        if (s < nst) issue(s, cq[s % kHubMeta], wq[s % kHubMeta]);
-        else cp_async_commit();
+        for (int s = 0; s < kAhead; ++s) {
+            if (s < nst) issue(s, cq0[s % kHubMeta], cq1[s % kHubMeta], wq[s % kHubMeta]);
+            else cp_async_commit();
+        }
     }
     float acc = 0.0f;
-    for (int sb = 0; sb < nst; sb += kHubMeta) {
+    // interval s (after barrier s): copy warps issue stage s+14; pre-reduce warps work on stage s; the chain
+    // warp consumes stage s-1.  One more interval drains the chain.
+    for (int sb = 0; sb <= nst; sb += kHubMeta) {
 #pragma unroll
         for (int j = 0; j < kHubMeta; ++j) {
             const int s = sb + j;
-            if (s < nst) {                                  // CTA-uniform
-                cp_async_wait<kHubStages - 2>();
-                __syncthreads();                           // stage s landed for everyone; stage s-1 reduced
-                const int si = s + kHubStages - 1;         // (sb + j + 15) % 8 == (j + 7) % 8: static slot
-                if (si < nst) issue(si, cq[(j + kHubStages - 1) % kHubMeta], wq[(j + kHubStages - 1) % kHubMeta]);
-                else cp_async_commit();
-                if (warp == 0) consume(s, acc);
+            if (s <= nst) {                                   // CTA-uniform
+                if (warp >= 5) cp_async_wait<kAhead - 1>();
+                __syncthreads();                             // stage s landed; X/Y of stage s-1 written; stage s-2 consumed
+                if (warp >= 5) {
+                    const int si = s + kAhead;
+                    if (si < nst) issue(si, cq0[(j + kAhead) % kHubMeta], cq1[(j + kAhead) % kHubMeta], wq[(j + kAhead) % kHubMeta]);
+                    else cp_async_commit();
+                } else if (warp >= 1) {
+                    if (s < nst && (warp - 1) * 8 + 8 <= min(kHubStage, k - s * kHubStage)) prereduce(s, warp - 1);
+                } else if (s >= 1) {
+                    chain(s - 1, acc);
+                }
             }
         }
     }
     cp_async_wait<0>();
+    (void)all_blk;
     if (warp == 0 && ccol < p.ld) {
         const size_t off = (size_t)row * p.ld + ccol;
         p.Zn[off] = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
@@ -470,13 +501,14 @@ __global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
                   meta, ring, se.x, se.y);
 }
 
-__global__ void __launch_bounds__(kHubThreads, 2) k_sweep_hubs(SweepParams p) {
+__global__ void __launch_bounds__(kHubThreads, 1) k_sweep_hubs(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     float* ringf = reinterpret_cast<float*>(smem);
     float* wsm = ringf + kHubRingFloats;
+    float* xy = wsm + kHubStages * kHubStage;
     const int hr = blockIdx.x / p.nslab32;
-    hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm);
+    hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm, xy);
 }
 
 }  // namespace clane

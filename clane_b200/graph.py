@@ -25,7 +25,7 @@ from torch.utils.data import Dataset
 
 from . import _lib
 
-HUB_THRESHOLD = 0      # 0 = library default (rows of degree > 128 take the hub path)
+HUB_THRESHOLD = 0      # 0 = library default (rows of degree > 1024 take the hub path)
 
 
 class Vertex(object):

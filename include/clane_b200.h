@@ -82,7 +82,7 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
  *   - the ordinary rows of a group are cut into spans of bounded edge count, sorted by edge
  *     count descending and handed to warps eight at a time; groups of sinks only are dropped
  *     (embedder.py:88-89: such rows are never updated).
- * hub_threshold <= 0 selects the default (128).
+ * hub_threshold <= 0 selects the default (1024).
  * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
 typedef struct clane_plan clane_plan;
 /* The schedule alone, on the host (what clane_plan_create uploads); every output has capacity

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_ring(const float* __restrict__ Z, const
                 for (int i = 0; i < 32; ++i) acc += src[i * 32];
             }
         }
-    } else if (MODE == 2) {
+    } else if (MODE >= 2) {
         // like MODE 0 but the row ids are prefetched 8 stages ahead into statically indexed registers
         int cq[8];
 #pragma unroll
@@ -52,15 +52,13 @@ __global__ void __launch_bounds__(256) k_ring(const float* __restrict__ Z, const
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int s = sb + j;
-                cp_async_wait<STAGES - 2>();
-                __syncthreads();
+                if (MODE != 5) { cp_async_wait<STAGES - 2>(); __syncthreads(); }
                 const int si = s + STAGES - 1;
-                constexpr int dummy = 0; (void)dummy;
                 const int slot = (j + STAGES - 1) % 8;
-                if (si < nst) cp_async16(ring + (si % STAGES) * 1024 + nb * 32 + pc, Z + (size_t)cq[slot] * ld + pc);
+                if (si < nst && MODE != 4) cp_async16(ring + (si % STAGES) * 1024 + nb * 32 + pc, Z + (size_t)cq[slot] * ld + pc);
                 cp_async_commit();
                 cq[slot] = (si + 8) * 32 + nb < k ? __ldg(my + (si + 8) * 32 + nb) : 0;
-                if (warp == 0) {
+                if (warp == 0 && MODE != 3) {
                     const float* src = ring + (s % STAGES) * 1024 + lane;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc += src[i * 32];
@@ -109,9 +107,11 @@ int main() {
             }
             printf("ctas=%3d %-18s stages=%2d  %.1f us total, %.0f ns per 32-neighbour stage\n", ctas, name, stages, best * 1e3, best * 1e6 / (K / 32));
         };
-        run(k_ring<4, 0>, 4, "cp.async"); run(k_ring<8, 0>, 8, "cp.async"); run(k_ring<16, 0>, 16, "cp.async");
-        run(k_ring<4, 1>, 4, "ldg+sts depth2");
-        run(k_ring<8, 2>, 8, "cp.async+prefetch"); run(k_ring<16, 2>, 16, "cp.async+prefetch");
+
+        run(k_ring<16, 2>, 16, "full");
+        run(k_ring<16, 3>, 16, "no consumer");
+        run(k_ring<16, 4>, 16, "no copies");
+        run(k_ring<16, 5>, 16, "no wait/sync");
         cudaFree(idx);
     }
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
