@@ -10,7 +10,8 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libclane_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ["CLANE_LIB"]) if _os.environ.get("CLANE_LIB") else _PKG / "libclane_b200.so"
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)

@@ -29,6 +29,14 @@
 #pragma once
 #include "common.cuh"
 
+// build-time tuning knobs of the row kernel: ring slots per warp, resident CTAs per SM
+#ifndef CLANE_RING
+#define CLANE_RING 8
+#endif
+#ifndef CLANE_ROW_OCC
+#define CLANE_ROW_OCC 6
+#endif
+
 namespace clane {
 
 struct SweepParams {
@@ -59,7 +67,7 @@ struct SweepParams {
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
 constexpr int kRowWarps = 4;
-constexpr int kHubThreads = 288;               // hub kernel: 9 warps per CTA (chain, 4 pre-reduce, 4 copy)
+constexpr int kHubThreads = 416;               // hub kernel: 13 warps per CTA (chain, 4 pre-reduce, 8 copy)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
 constexpr int kMetaSlots = kMetaRing + 8;
 constexpr int kHubStage = 32;                  // neighbours per ring stage
@@ -67,11 +75,11 @@ constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
 constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 // row kernel shared memory per warp: (offset, w) ring | 32 x 512-byte row-piece ring
-constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)16 * 32 * sizeof(float4);
+constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)CLANE_RING * 32 * sizeof(float4);
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
 constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float) +
-                                 (size_t)2 * 4 * 64 * sizeof(float);   // copy ring | w ring | X/Y of two stages
+                                 (size_t)2 * 4 * 32 * sizeof(float4);  // copy ring | w ring | {z6,z4,X,Y} of two stages
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -137,13 +145,13 @@ __device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl
 //   issue   : per "batch" (one 8-neighbour block of one row) it reads the neighbours' row
 //             offsets from its (offset, w) ring and starts one 512-byte cp.async per neighbour
 //             (16 bytes per lane: lane L copies exactly the float4 of columns it will reduce,
-//             so no barrier is ever needed) into its private 16-slot ring of row pieces; the
+//             so no barrier is ever needed) into its private ring of row pieces; the
 //             row's X piece (and own Zcur piece, fused L1) ride with the row's last batch;
 //   consume : waits for the OLDEST batch only (cp.async.wait_group), reduces it in the
 //             reference's order, and frees its slots.
-// Up to 16 row pieces (8 KB) per warp are in flight whatever the row lengths: the gathers of
+// Up to CLANE_RING row pieces (512 B each) per warp are in flight whatever the row lengths: the gathers of
 // the next rows overlap the reduction of the current one (decoupled access / execute).
-constexpr int kRing = 16;              // 512-byte row-piece slots per warp
+constexpr int kRing = CLANE_RING;      // 512-byte row-piece slots per warp
 constexpr int kMaxPending = 6;         // batches in flight per warp
 
 struct Cursor { int ri, a, k, pos; };
@@ -321,92 +329,83 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
 // hub role
 // ------------------------------------------------------------------------------------------
 
-// One (hub row, 32-column slab) per CTA of 9 warps, three roles, lock-stepped per 32-neighbour stage:
-//   warps 5-8  copy: warp 5+b streams block b (8 neighbours x 128 B) of every stage into the ring with two
+// One (hub row, 32-column slab) per CTA of 13 warps, three roles, lock-stepped per 32-neighbour stage:
+//   warps 5-12 copy: warp 5+c streams neighbours 4c..4c+3 of every stage (4 x 128 B) into the ring with one
 //              cp.async per stage; (col*ld, w) are prefetched 8 stages ahead in statically indexed registers;
 //   warps 1-4  pre-reduce: warp 1+b computes, for block b of the stage that has just landed, the two
 //              sub-trees of the 8-neighbour pattern that do not involve the running sum,
-//              X = fma(w5,z5, w7*z7) and Y = fma(w0,z0, w2*z2) + fma(w1,z1, w3*z3), per column;
+//              X = fma(w5,z5, w7*z7) and Y = fma(w0,z0, w2*z2) + fma(w1,z1, w3*z3), and parks
+//              {z6, z4, X, Y} per column as one float4;
 //   warp 0     chain: a = fma(w6,z6,a); a = fma(w4,z4,a); a += X; a += Y for the blocks of the previous
-//              stage -- 4 dependent operations per 8 neighbours, the minimum the reference's order allows.
+//              stage -- 4 dependent operations per 8 neighbours, the minimum the reference's order allows,
+//              fed by two 128-bit shared-memory loads per block.
 // Columns in the sequential regime (>= 16*floor(d/16)) are reduced by warp 0 alone, straight from the ring.
-constexpr int kHubWarps = 9;
-
-__device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm, float* xy) {
+__device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* ringf, float* wsm, float4* xy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
     const int nst = (k + kHubStage - 1) / kHubStage;
     const int ccol = slab32 * 32 + lane;                 // reduce view: one column per lane
     const bool blk = ccol < (p.d / 16) * 16;             // k > hub_threshold >= 8
-    const bool all_blk = slab32 * 32 + 31 < (p.d / 16) * 16;
-    // copy view (warps 5-8): this lane moves 16 bytes of neighbours nb0 and nb0 + 4 of every stage
-    const int cw = warp - 5;
-    const int nb0 = cw * 8 + (lane >> 3);
+    // copy view (warps 5-12): this lane moves 16 bytes of neighbour nb of every stage
+    const int nb = (warp - 5) * 4 + (lane >> 3);
     const int pcol = slab32 * 32 + (lane & 7) * 4;
     const bool pact = pcol < p.ld;
 
-    int cq0[kHubMeta], cq1[kHubMeta];
+    int cq[kHubMeta];
     float wq[kHubMeta];
 #pragma unroll
-    for (int i = 0; i < kHubMeta; ++i) { cq0[i] = cq1[i] = 0; wq[i] = 0.0f; }
+    for (int i = 0; i < kHubMeta; ++i) { cq[i] = 0; wq[i] = 0.0f; }
     if (warp >= 5) {
 #pragma unroll
         for (int i = 0; i < kHubMeta; ++i) {
-            const int i0 = i * kHubStage + nb0, i1 = i0 + 4, wi = i * kHubStage + lane;
-            cq0[i] = i0 < k ? __ldg(p.coloff + a + i0) : 0;
-            cq1[i] = i1 < k ? __ldg(p.coloff + a + i1) : 0;
+            const int i0 = i * kHubStage + nb, wi = i * kHubStage + lane;
+            cq[i] = i0 < k ? __ldg(p.coloff + a + i0) : 0;
             wq[i] = (warp == 5 && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
         }
     }
-    auto issue = [&](int si, int& c0, int& c1, float& wslot) {   // copy warps only
+    const float* zsrc = p.Zc + pcol;
+    float* rdst = ringf + nb * 32 + (lane & 7) * 4;
+    auto issue = [&](int si, int& c0, float& wslot) {   // copy warps only
         const int slot = si % kHubStages;
-        float* dst = ringf + (size_t)slot * kHubStage * 32 + (lane & 7) * 4;
-        if (pact) {
-            if (si * kHubStage + nb0 < k) cp_async16(dst + nb0 * 32, p.Zc + (size_t)c0 + pcol);
-            if (si * kHubStage + nb0 + 4 < k) cp_async16(dst + (nb0 + 4) * 32, p.Zc + (size_t)c1 + pcol);
-        }
+        if (pact && si * kHubStage + nb < k) cp_async16(rdst + slot * (kHubStage * 32), zsrc + c0);
         if (warp == 5) wsm[slot * kHubStage + lane] = wslot;
         cp_async_commit();
-        const int i0 = (si + kHubMeta) * kHubStage + nb0, i1 = i0 + 4, wi = (si + kHubMeta) * kHubStage + lane;
+        const int i0 = (si + kHubMeta) * kHubStage + nb, wi = (si + kHubMeta) * kHubStage + lane;
         c0 = i0 < k ? __ldg(p.coloff + a + i0) : 0;
-        c1 = i1 < k ? __ldg(p.coloff + a + i1) : 0;
-        wslot = (warp == 5 && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
+        if (warp == 5) wslot = wi < k ? __ldg(p.w + a + wi) : 0.0f;
     };
-    // pre-reduce block b of stage s (a full block) -> xy[s & 1][b][0..1][lane]
+    // pre-reduce block b of stage s (a full block) -> xy[s & 1][b][lane] = {z6, z4, X, Y}
     auto prereduce = [&](int s, int b) {
         const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + b * 8 * 32 + lane;
         const float4* w4 = reinterpret_cast<const float4*>(wsm + (s % kHubStages) * kHubStage + b * 8);
         const float4 wa = w4[0], wb = w4[1];
-        const float z0 = src[0], z1 = src[32], z2 = src[64], z3 = src[96], z5 = src[160], z7 = src[224];
+        const float z0 = src[0], z1 = src[32], z2 = src[64], z3 = src[96], z4 = src[128], z5 = src[160],
+                    z6 = src[192], z7 = src[224];
         const float x = ffma(wb.y, z5, fmul(wb.w, z7));
         const float y = fadd(ffma(wa.x, z0, fmul(wa.z, z2)), ffma(wa.y, z1, fmul(wa.w, z3)));
-        float* dst = xy + ((s & 1) * 4 + b) * 64 + lane;
-        dst[0] = x;
-        dst[32] = y;
+        xy[((s & 1) * 4 + b) * 32 + lane] = make_float4(z6, z4, x, y);
     };
-    // chain over stage s (its X/Y were written during the previous interval)
+    // chain over stage s (its {z6, z4, X, Y} were written during the previous interval)
     auto chain = [&](int s, float& acc) {
-        const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
         const float* wrow = wsm + (s % kHubStages) * kHubStage;
-        const float* xys = xy + (s & 1) * 4 * 64 + lane;
         const int cnt = min(kHubStage, k - s * kHubStage);
         const int nfull = cnt >> 3;
+        const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
         if (blk) {
-            float z6[4], z4[4], w6[4], w4v[4], xv[4], yv[4];
+            float4 v[4], wv[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b)
                 if (b < nfull) {
-                    z6[b] = src[(b * 8 + 6) * 32]; z4[b] = src[(b * 8 + 4) * 32];
-                    w6[b] = wrow[b * 8 + 6]; w4v[b] = wrow[b * 8 + 4];
-                    xv[b] = xys[b * 64]; yv[b] = xys[b * 64 + 32];
+                    v[b] = xy[((s & 1) * 4 + b) * 32 + lane];
+                    wv[b] = *reinterpret_cast<const float4*>(wrow + b * 8 + 4);   // {w4, w5, w6, w7}
                 }
 #pragma unroll
             for (int b = 0; b < 4; ++b)
                 if (b < nfull) {
-                    acc = ffma(w6[b], z6[b], acc);
-                    acc = ffma(w4v[b], z4[b], acc);
-                    acc = fadd(acc, xv[b]);
-                    acc = fadd(acc, yv[b]);
+                    acc = ffma(wv[b].z, v[b].x, acc);
+                    acc = ffma(wv[b].x, v[b].y, acc);
+                    acc = fadd(acc, v[b].z);
+                    acc = fadd(acc, v[b].w);
                 }
         } else {
             for (int o = 0; o < nfull * 8; ++o) acc = ffma(wrow[o], src[o * 32], acc);
@@ -421,7 +420,7 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     if (warp >= 5) {
 #pragma unroll
         for (int s = 0; s < kAhead; ++s) {
-            if (s < nst) issue(s, cq0[s % kHubMeta], cq1[s % kHubMeta], wq[s % kHubMeta]);
+            if (s < nst) issue(s, cq[s % kHubMeta], wq[s % kHubMeta]);
             else cp_async_commit();
         }
     }
@@ -434,10 +433,10 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
             const int s = sb + j;
             if (s <= nst) {                                   // CTA-uniform
                 if (warp >= 5) cp_async_wait<kAhead - 1>();
-                __syncthreads();                             // stage s landed; X/Y of stage s-1 written; stage s-2 consumed
+                __syncthreads();                             // stage s landed; {z6,z4,X,Y} of stage s-1 written
                 if (warp >= 5) {
                     const int si = s + kAhead;
-                    if (si < nst) issue(si, cq0[(j + kAhead) % kHubMeta], cq1[(j + kAhead) % kHubMeta], wq[(j + kAhead) % kHubMeta]);
+                    if (si < nst) issue(si, cq[(j + kAhead) % kHubMeta], wq[(j + kAhead) % kHubMeta]);
                     else cp_async_commit();
                 } else if (warp >= 1) {
                     if (s < nst && (warp - 1) * 8 + 8 <= min(kHubStage, k - s * kHubStage)) prereduce(s, warp - 1);
@@ -448,7 +447,6 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
         }
     }
     cp_async_wait<0>();
-    (void)all_blk;
     if (warp == 0 && ccol < p.ld) {
         const size_t off = (size_t)row * p.ld + ccol;
         p.Zn[off] = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
@@ -484,13 +482,13 @@ k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, 
     P0[(size_t)g * 32 + lane] = acc;
 }
 
-__global__ void __launch_bounds__(kRowThreads, 5) k_sweep_rows(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     float4* ring = reinterpret_cast<float4*>(mine);
-    int2* meta = reinterpret_cast<int2*>(mine + (size_t)16 * 32 * sizeof(float4));
+    int2* meta = reinterpret_cast<int2*>(mine + (size_t)CLANE_RING * 32 * sizeof(float4));
     const int64_t task = (int64_t)blockIdx.x * kRowWarps + warp;
     const int64_t si = task / p.nslab;
     if (si >= p.n_spans) return;
@@ -506,7 +504,7 @@ __global__ void __launch_bounds__(kHubThreads, 1) k_sweep_hubs(SweepParams p) {
     if (p.st != nullptr && p.st->stop) return;
     float* ringf = reinterpret_cast<float*>(smem);
     float* wsm = ringf + kHubRingFloats;
-    float* xy = wsm + kHubStages * kHubStage;
+    float4* xy = reinterpret_cast<float4*>(wsm + kHubStages * kHubStage);
     const int hr = blockIdx.x / p.nslab32;
     hub_slab_task(p, __ldg(p.hub_rows + hr), blockIdx.x - hr * p.nslab32, ringf, wsm, xy);
 }

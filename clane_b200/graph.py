@@ -211,7 +211,7 @@ class Graph(Dataset):
             S.rowptr = torch.from_numpy(self._rowptr).to(dev)
             S.col = torch.from_numpy(self._col if e else np.zeros(1, np.int32)).to(dev)
             S.erow = torch.zeros(max(e, 1), dtype=torch.int32, device=dev)
-            S.plan = _lib.Plan(n, e, d, self._rowptr, 0, n, HUB_THRESHOLD)
+            S.plan = _lib.Plan(n, e, d, self._rowptr, 0, n, HUB_THRESHOLD)   # module attribute: tests lower it
             S.X = torch.zeros([max(n, 1), ld], dtype=torch.float32, device=dev)
             S.X[:n, :d] = self.X.to(dev)
             S.Z = [torch.zeros_like(S.X), torch.zeros_like(S.X)]

@@ -257,9 +257,11 @@ def test_baseline_shapes_against_oracle(shape, scale):
 
 @pytest.mark.parametrize("n,d,hub_deg,tol", [(3000, 128, 900, 2), (3000, 64, 400, 2), (5000, 32, 300, 2), (3000, 100, 700, 2),
                                              (700, 500, 600, 1), (300, 1433, 290, 1), (140003, 128, 9000, 1)])
-def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol):
+def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol, monkeypatch):
     """Power-law graphs with hub rows (shared-memory ring path), every d regime: fused L1
     (d = 32/64/128, level step 16 and 32), padded / multi-slab rows (100, 500, 1433)."""
+    import clane_b200.graph as graph_module
+    monkeypatch.setattr(graph_module, "HUB_THRESHOLD", 128)     # default is 1024: force the hub kernel on these sizes
     rng = np.random.default_rng(n + d)
     e = n * 6
     src, dst = synth.make_edges(n, e, "powerlaw", rng)
@@ -279,6 +281,29 @@ def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol):
     rowptr, col = O.csr_from_edges(src, dst, n)
     Zo, amounts, w = O.propagate(X, X, rowptr, col, 0.76, tol, max_sweeps=4)
     assert np.array_equal(S.w[:S.e].cpu().numpy(), w)
+    assert np.array_equal(emb.amounts_per_call[0], amounts)
+    assert np.array_equal(g.Z.numpy(), Zo)
+
+
+def test_default_hub_threshold_long_rows_in_row_kernel():
+    """Rows of a few hundred neighbours stay in the row kernel at the default threshold (1024); one longer row
+    takes the hub kernel.  Both against the oracle."""
+    rng = np.random.default_rng(77)
+    n, d = 6000, 128
+    src, dst = synth.make_edges(n, n * 5, "powerlaw", rng)
+    extra = [(5, 1500), (6, 1030), (900, 1000), (901, 700), (902, 300), (4001, 129)]
+    src = np.concatenate([src] + [np.full(k, r) for r, k in extra])
+    dst = np.concatenate([dst] + [rng.permutation(n)[:k] for _, k in extra])
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    g = Graph.from_arrays(n, src, dst, X)
+    emb = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=2)
+    emb.verbose = False
+    emb.propagate(max_sweeps=3)
+    S = g._device_state()
+    assert S.plan.n_hub_rows == 2 and S.plan.fused_l1
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    Zo, amounts, w = O.propagate(X, X, rowptr, col, 0.76, 2, max_sweeps=3)
     assert np.array_equal(emb.amounts_per_call[0], amounts)
     assert np.array_equal(g.Z.numpy(), Zo)
 
