@@ -173,7 +173,11 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     if ((int64_t)n * plan->ld > (int64_t)INT32_MAX) { clane_plan_destroy(plan); return CLANE_ERANGE; }   // int32 row offsets
     plan->has_schedule = true;
     PLAN_CUDA(cudaMalloc(&plan->d_coloff, std::max<size_t>((size_t)e, 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking));
+    {   // the hub kernel is the sweep's critical path: its CTAs are dispatched ahead of the row kernel's
+        int lo = 0, hi = 0;
+        PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
+    }
     PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
     PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
     plan->row_lo = row_lo; plan->row_hi = row_hi;

@@ -31,7 +31,7 @@
 
 // build-time tuning knobs of the row kernel: ring slots per warp, resident CTAs per SM
 #ifndef CLANE_RING
-#define CLANE_RING 8
+#define CLANE_RING 16
 #endif
 #ifndef CLANE_ROW_OCC
 #define CLANE_ROW_OCC 6
@@ -78,8 +78,12 @@ constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)CLANE_RING * 32 * sizeof(float4);
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
-constexpr size_t kHubSmemBytes = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float) +
-                                 (size_t)2 * 4 * 32 * sizeof(float4);  // copy ring | w ring | {z6,z4,X,Y} of two stages
+constexpr size_t kHubSmemUsed = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float) +
+                                (size_t)2 * 4 * 32 * sizeof(float4);   // copy ring | w ring | {z6,z4,X,Y} of two stages
+// A hub CTA is a long serial chain: it asks for (nearly) all of the SM's shared memory so that no row CTA
+// shares -- and slows -- its SM while it runs.
+constexpr size_t kHubSmemBytes = 210 * 1024;
+static_assert(kHubSmemUsed <= kHubSmemBytes, "hub rings fit");
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -152,6 +156,7 @@ __device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl
 // Up to CLANE_RING row pieces (512 B each) per warp are in flight whatever the row lengths: the gathers of
 // the next rows overlap the reduction of the current one (decoupled access / execute).
 constexpr int kRing = CLANE_RING;      // 512-byte row-piece slots per warp
+static_assert(kRing >= 16 && (kRing & (kRing - 1)) == 0, "a batch needs up to 10 slots; slot indices are masked");
 constexpr int kMaxPending = 6;         // batches in flight per warp
 
 struct Cursor { int ri, a, k, pos; };
