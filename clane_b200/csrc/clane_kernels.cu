@@ -302,8 +302,6 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
         static const char* dbg = getenv("CLANE_DEBUG_ROLE");
         if (dbg && dbg[0] == 'r') p.n_hub_rows = 0;
         if (dbg && dbg[0] == 'h') p.n_spans = 0;
-        static const char* skip = getenv("CLANE_DEBUG_SKIP");
-        p.dbg_skip = skip ? atoi(skip) : 0;
     }
     // The hub rows (few, long in-order chains) run on the plan's side stream next to the row kernel.
     const int64_t hub_ctas = (int64_t)p.n_hub_rows * plan->nslab32;

@@ -62,7 +62,6 @@ struct SweepParams {
     float* P0;
     int hub_threshold;
     const clane_patience* st;
-    int dbg_skip;               // profiling aid: bit0 no gathers, bit1 no X/own loads, bit2 no stores, bit3 fixed offsets
 };
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5 CTAs per SM at <= 102 registers
@@ -171,6 +170,18 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {   // oldest
     }
 }
 
+__device__ __forceinline__ void cp_async16_sa(unsigned smem_addr, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+
+// start the M gathers of one batch: slot (tail + i) of the warp's ring <- 16 bytes of neighbour i's row
+template <int M>
+__device__ __forceinline__ void issue_batch(unsigned ring_sa, int tail, const int2* __restrict__ mp,
+                                            const float* __restrict__ zb) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) cp_async16_sa(ring_sa + (((tail + i) & (kRing - 1)) << 9), zb + mp[i].x);
+}
+
 template <int M>
 __device__ __forceinline__ void reduce_batch(const float4* __restrict__ ring, int head, const int2* __restrict__ mp,
                                              int lane, float4& acc, bool col_blocked) {
@@ -222,6 +233,7 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
     const float* zb = p.Zc + cc;
     const int nseg = p.d >> 5;
     const int extra = direct ? 2 : 1;      // ring slots a row's last batch adds: X piece (+ own Zcur piece)
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;   // this lane's 16 bytes of slot 0
 
     // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
@@ -274,16 +286,20 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
             }
             if (active) {
                 const int2* mp = meta + (u & 127);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < m && !(p.dbg_skip & 1))
-                        cp_async16(reinterpret_cast<float*>(ring + ((tail + i) & (kRing - 1)) * 32 + lane),
-                                   zb + ((p.dbg_skip & 8) ? (size_t)((r0 + i) * p.ld) : (size_t)mp[i].x));
-                if (last && !(p.dbg_skip & 2)) {
+                switch (m) {
+                    case 8: issue_batch<8>(ring_sa, tail, mp, zb); break;
+                    case 7: issue_batch<7>(ring_sa, tail, mp, zb); break;
+                    case 6: issue_batch<6>(ring_sa, tail, mp, zb); break;
+                    case 5: issue_batch<5>(ring_sa, tail, mp, zb); break;
+                    case 4: issue_batch<4>(ring_sa, tail, mp, zb); break;
+                    case 3: issue_batch<3>(ring_sa, tail, mp, zb); break;
+                    case 2: issue_batch<2>(ring_sa, tail, mp, zb); break;
+                    default: issue_batch<1>(ring_sa, tail, mp, zb); break;
+                }
+                if (last) {
                     const size_t row_off = (size_t)(r0 + ic.ri) * p.ld + cc;
-                    cp_async16(reinterpret_cast<float*>(ring + ((tail + m) & (kRing - 1)) * 32 + lane), p.X + row_off);
-                    if (direct)
-                        cp_async16(reinterpret_cast<float*>(ring + ((tail + m + 1) & (kRing - 1)) * 32 + lane), p.Zc + row_off);
+                    cp_async16_sa(ring_sa + (((tail + m) & (kRing - 1)) << 9), p.X + row_off);
+                    if (direct) cp_async16_sa(ring_sa + (((tail + m + 1) & (kRing - 1)) << 9), p.Zc + row_off);
                 }
             }
             cp_async_commit();
@@ -313,7 +329,7 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
             if (active) {
                 const float4 xs = ring[((head + m) & (kRing - 1)) * 32 + lane];
                 const float4 out = finish_row(xs, acc, p.gamma);
-                if (!(p.dbg_skip & 4)) *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
+                *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
                 if (direct) dl = absdiff4(out, ring[((head + m + 1) & (kRing - 1)) * 32 + lane]);
             }
             if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
