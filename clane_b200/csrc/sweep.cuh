@@ -69,16 +69,16 @@ constexpr int kRowWarps = 4;
 constexpr int kHubThreads = 416;               // hub kernel: 13 warps per CTA (chain, 4 pre-reduce, 8 copy)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
 constexpr int kMetaSlots = kMetaRing + 8;
-constexpr int kHubStage = 32;                  // neighbours per ring stage
-constexpr int kHubStages = 16;                 // 16 x 32 x 128 B = 64 KB
-constexpr int kHubMeta = 8;                    // col / w are fetched this many stages ahead of the copies
+constexpr int kHubStage = 64;                  // neighbours per ring stage
+constexpr int kHubStages = 8;                  // 8 x 64 x 128 B = 64 KB
+constexpr int kHubMeta = 4;                    // col / w are fetched this many stages ahead of the copies
 constexpr int kHubRingFloats = kHubStages * kHubStage * 32;
 // row kernel shared memory per warp: (offset, w) ring | 32 x 512-byte row-piece ring
 constexpr size_t kRowWarpSmem = (size_t)kMetaSlots * sizeof(int2) + (size_t)CLANE_RING * 32 * sizeof(float4);
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub kernel shared memory: copy ring | w ring
 constexpr size_t kHubSmemUsed = (size_t)kHubRingFloats * sizeof(float) + (size_t)kHubStages * kHubStage * sizeof(float) +
-                                (size_t)2 * 4 * 32 * sizeof(float4);   // copy ring | w ring | {z6,z4,X,Y} of two stages
+                                (size_t)2 * 8 * 32 * sizeof(float4);   // copy ring | w ring | {z6,z4,X,Y} of two stages
 constexpr size_t kHubSmemBytes = kHubSmemUsed;   // (asking for the whole SM to keep row CTAs away delays the hub CTAs' start: measured worse)
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
@@ -364,33 +364,38 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     const int nst = (k + kHubStage - 1) / kHubStage;
     const int ccol = slab32 * 32 + lane;                 // reduce view: one column per lane
     const bool blk = ccol < (p.d / 16) * 16;             // k > hub_threshold >= 8
-    // copy view (warps 5-12): this lane moves 16 bytes of neighbour nb of every stage
+    // copy view (warps 5-12): this lane moves 16 bytes of neighbours nb and nb + 32 of every stage
     const int nb = (warp - 5) * 4 + (lane >> 3);
     const int pcol = slab32 * 32 + (lane & 7) * 4;
     const bool pact = pcol < p.ld;
 
-    int cq[kHubMeta];
-    float wq[kHubMeta];
+    int cq[kHubMeta], cq2[kHubMeta];
+    float wq[kHubMeta];    // warps 5 and 6 carry the stage's 64 weights (32 each)
 #pragma unroll
-    for (int i = 0; i < kHubMeta; ++i) { cq[i] = 0; wq[i] = 0.0f; }
+    for (int i = 0; i < kHubMeta; ++i) { cq[i] = cq2[i] = 0; wq[i] = 0.0f; }
+    const int wbase = (warp == 6) ? 32 : 0;
+    const bool wcarrier = warp == 5 || warp == 6;
     if (warp >= 5) {
 #pragma unroll
         for (int i = 0; i < kHubMeta; ++i) {
-            const int i0 = i * kHubStage + nb, wi = i * kHubStage + lane;
+            const int i0 = i * kHubStage + nb, wi = i * kHubStage + wbase + lane;
             cq[i] = i0 < k ? __ldg(p.coloff + a + i0) : 0;
-            wq[i] = (warp == 5 && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
+            cq2[i] = i0 + 32 < k ? __ldg(p.coloff + a + i0 + 32) : 0;
+            wq[i] = (wcarrier && wi < k) ? __ldg(p.w + a + wi) : 0.0f;
         }
     }
     const float* zsrc = p.Zc + pcol;
     float* rdst = ringf + nb * 32 + (lane & 7) * 4;
-    auto issue = [&](int si, int& c0, float& wslot) {   // copy warps only
+    auto issue = [&](int si, int& c0, int& c1, float& wslot) {   // copy warps only
         const int slot = si % kHubStages;
         if (pact && si * kHubStage + nb < k) cp_async16(rdst + slot * (kHubStage * 32), zsrc + c0);
-        if (warp == 5) wsm[slot * kHubStage + lane] = wslot;
+        if (pact && si * kHubStage + nb + 32 < k) cp_async16(rdst + slot * (kHubStage * 32) + 32 * 32, zsrc + c1);
+        if (wcarrier) wsm[slot * kHubStage + wbase + lane] = wslot;
         cp_async_commit();
-        const int i0 = (si + kHubMeta) * kHubStage + nb, wi = (si + kHubMeta) * kHubStage + lane;
+        const int i0 = (si + kHubMeta) * kHubStage + nb, wi = (si + kHubMeta) * kHubStage + wbase + lane;
         c0 = i0 < k ? __ldg(p.coloff + a + i0) : 0;
-        if (warp == 5) wslot = wi < k ? __ldg(p.w + a + wi) : 0.0f;
+        c1 = i0 + 32 < k ? __ldg(p.coloff + a + i0 + 32) : 0;
+        if (wcarrier) wslot = wi < k ? __ldg(p.w + a + wi) : 0.0f;
     };
     // pre-reduce block b of stage s (a full block) -> xy[s & 1][b][lane] = {z6, z4, X, Y}
     auto prereduce = [&](int s, int b) {
@@ -401,7 +406,7 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
                     z6 = src[192], z7 = src[224];
         const float x = ffma(wb.y, z5, fmul(wb.w, z7));
         const float y = fadd(ffma(wa.x, z0, fmul(wa.z, z2)), ffma(wa.y, z1, fmul(wa.w, z3)));
-        xy[((s & 1) * 4 + b) * 32 + lane] = make_float4(z6, z4, x, y);
+        xy[((s & 1) * 8 + b) * 32 + lane] = make_float4(z6, z4, x, y);
     };
     // chain over stage s (its {z6, z4, X, Y} were written during the previous interval)
     auto chain = [&](int s, float& acc) {
@@ -410,15 +415,15 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
         const int nfull = cnt >> 3;
         const float* src = ringf + (size_t)(s % kHubStages) * kHubStage * 32 + lane;
         if (blk) {
-            float4 v[4], wv[4];
+            float4 v[8], wv[8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 8; ++b)
                 if (b < nfull) {
-                    v[b] = xy[((s & 1) * 4 + b) * 32 + lane];
+                    v[b] = xy[((s & 1) * 8 + b) * 32 + lane];
                     wv[b] = *reinterpret_cast<const float4*>(wrow + b * 8 + 4);   // {w4, w5, w6, w7}
                 }
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 8; ++b)
                 if (b < nfull) {
                     acc = ffma(wv[b].z, v[b].x, acc);
                     acc = ffma(wv[b].x, v[b].y, acc);
@@ -438,7 +443,7 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
     if (warp >= 5) {
 #pragma unroll
         for (int s = 0; s < kAhead; ++s) {
-            if (s < nst) issue(s, cq[s % kHubMeta], wq[s % kHubMeta]);
+            if (s < nst) issue(s, cq[s % kHubMeta], cq2[s % kHubMeta], wq[s % kHubMeta]);
             else cp_async_commit();
         }
     }
@@ -454,10 +459,12 @@ __device__ void hub_slab_task(const SweepParams& p, int row, int slab32, float* 
                 __syncthreads();                             // stage s landed; {z6,z4,X,Y} of stage s-1 written
                 if (warp >= 5) {
                     const int si = s + kAhead;
-                    if (si < nst) issue(si, cq[(j + kAhead) % kHubMeta], wq[(j + kAhead) % kHubMeta]);
+                    if (si < nst) issue(si, cq[(j + kAhead) % kHubMeta], cq2[(j + kAhead) % kHubMeta], wq[(j + kAhead) % kHubMeta]);
                     else cp_async_commit();
-                } else if (warp >= 1) {
-                    if (s < nst && (warp - 1) * 8 + 8 <= min(kHubStage, k - s * kHubStage)) prereduce(s, warp - 1);
+                } else if (warp >= 1) {     // two blocks per pre-reduce warp
+                    const int cnt = min(kHubStage, k - s * kHubStage);
+                    if (s < nst && (warp - 1) * 8 + 8 <= cnt) prereduce(s, warp - 1);
+                    if (s < nst && (warp + 3) * 8 + 8 <= cnt) prereduce(s, warp + 3);
                 } else if (s >= 1) {
                     chain(s - 1, acc);
                 }
