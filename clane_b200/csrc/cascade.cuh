@@ -164,15 +164,24 @@ k_cascade_finish(Elem elem, CascadeShape sh, const float* __restrict__ ws, float
         const int64_t first = k * step;
         const int cnt = (k < sh.n2_full) ? step : (int)(sh.n1_full - first);
         float acc = 0.0f;
-        int i = 0;
-        for (; i + 8 <= cnt; i += 8) {
-            float v[8];
+        if (step <= 32) {
+            float v[32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = P1[((size_t)(first + i + u) * NQ + q) * 32 + lane];
+            for (int u = 0; u < 32; ++u) v[u] = (u < cnt) ? P1[((size_t)(first + u) * NQ + q) * 32 + lane] : 0.0f;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+            for (int u = 0; u < 32; ++u)
+                if (u < cnt) acc = fadd(acc, v[u]);
+        } else {
+            int i = 0;
+            for (; i + 8 <= cnt; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = P1[((size_t)(first + i + u) * NQ + q) * 32 + lane];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+            }
+            for (; i < cnt; ++i) acc = fadd(acc, P1[((size_t)(first + i) * NQ + q) * 32 + lane]);
         }
-        for (; i < cnt; ++i) acc = fadd(acc, P1[((size_t)(first + i) * NQ + q) * 32 + lane]);
         P2[((size_t)k * NQ + q) * 32 + lane] = acc;
     }
     __syncthreads();
@@ -284,15 +293,24 @@ k_level1_from_p0(CascadeShape sh, const float* __restrict__ P0, float* __restric
     const int cnt = node < sh.n1_full ? step : (int)sh.c_rem;
     const float* src = P0 + (size_t)node * step * 32 + lane;
     float acc = 0.0f;
-    int i = 0;
-    for (; i + 8 <= cnt; i += 8) {
-        float v[8];
+    if (step <= 32) {   // fused mode: chunks of <= 1024 elements, so <= 32 chunks per node: one round trip
+        float v[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(i + u) * 32);
+        for (int u = 0; u < 32; ++u) v[u] = (u < cnt) ? __ldg(src + (size_t)u * 32) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+        for (int u = 0; u < 32; ++u)
+            if (u < cnt) acc = fadd(acc, v[u]);
+    } else {
+        int i = 0;
+        for (; i + 8 <= cnt; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(i + u) * 32);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+        }
+        for (; i < cnt; ++i) acc = fadd(acc, __ldg(src + (size_t)i * 32));
     }
-    for (; i < cnt; ++i) acc = fadd(acc, __ldg(src + (size_t)i * 32));
     p1[(size_t)node * 32 + lane] = acc;
     if (node == sh.n1_nodes - 1 && sh.rem_rows > 0 && sh.r_rem > 0)   // leftover rows = the last, partial group
         p1[(size_t)(sh.n1_nodes + 1) * 32 + lane] = __ldg(P0 + (size_t)(sh.n1_full * step + sh.c_rem) * 32 + lane);

@@ -492,18 +492,17 @@ k_fix_chunks(const float* __restrict__ Zn, const float* __restrict__ Zc, int d, 
     const int r0 = g * G, nrows = min(G, n - r0);
     const int ncr = nrows * (d >> 5);                   // cascade rows of the chunk (ld == d here)
     const size_t base = (size_t)r0 * d + lane;
-    float acc = 0.0f;
-    for (int r = 0; r < ncr; r += 8) {
-        float v[8];
+    // a chunk is at most 32 cascade rows (G*d <= 1024): fetch them all, then add in order -- one round trip
+    float v[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const size_t t = base + (size_t)(r + u) * 32;
-            v[u] = (r + u < ncr) ? fabsf(fsub(__ldcg(Zn + t), __ldg(Zc + t))) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (r + u < ncr) acc = fadd(acc, v[u]);
+    for (int r = 0; r < 32; ++r) {
+        const size_t t = base + (size_t)r * 32;
+        v[r] = (r < ncr) ? fabsf(fsub(__ldcg(Zn + t), __ldg(Zc + t))) : 0.0f;
     }
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if (r < ncr) acc = fadd(acc, v[r]);
     P0[(size_t)g * 32 + lane] = acc;
 }
 
