@@ -123,17 +123,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane
-// m owns cascade lane m: the row is d/32 consecutive cascade rows, taken in order.
-__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane) {
-    const int sub = lane >> 2, comp = lane & 3;
-    for (int seg = 0; seg < nseg; ++seg) {
-        const int src = seg * 8 + sub;
-        const float v0 = __shfl_sync(kFull, dl.x, src), v1 = __shfl_sync(kFull, dl.y, src);
-        const float v2 = __shfl_sync(kFull, dl.z, src), v3 = __shfl_sync(kFull, dl.w, src);
-        const float v = comp == 0 ? v0 : (comp == 1 ? v1 : (comp == 2 ? v2 : v3));
-        chunk_acc = fadd(chunk_acc, v);
-    }
+// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane m owns
+// cascade lane m: the row is d/32 consecutive cascade rows, taken in order.  The float4-per-lane layout is
+// transposed through 512 bytes of the warp's shared memory (one 128-bit store, d/32 32-bit loads).
+__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane, float* scratch) {
+    __syncwarp();                                              // the previous row's reads are done
+    reinterpret_cast<float4*>(scratch)[lane] = dl;
+    __syncwarp();
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg)
+        if (seg < nseg) chunk_acc = fadd(chunk_acc, scratch[seg * 32 + lane]);
     return chunk_acc;
 }
 
@@ -332,7 +331,8 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
                 *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
                 if (direct) dl = absdiff4(out, ring[((head + m + 1) & (kRing - 1)) * 32 + lane]);
             }
-            if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane);
+            // transpose scratch: the X slot of this batch (already read; not re-targeted before the next issue)
+            if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane, reinterpret_cast<float*>(ring + ((head + m) & (kRing - 1)) * 32));
         }
         const int need = m + (last ? extra : 0);
         head += need; used -= need; --pending;
