@@ -68,7 +68,7 @@ constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA, 5
 constexpr int kRowWarps = 4;
 constexpr int kHubThreads = 416;               // hub kernel: 13 warps per CTA (chain, 4 pre-reduce, 8 copy)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
-constexpr int kMetaSlots = kMetaRing + 8;
+constexpr int kMetaSlots = kMetaRing + 8 + 4;   // + 8-entry batch descriptor queue (8 ints = 4 int2)
 constexpr int kHubStage = 64;                  // neighbours per ring stage
 constexpr int kHubStages = 8;                  // 8 x 64 x 128 B = 64 KB
 constexpr int kHubMeta = 4;                    // col / w are fetched this many stages ahead of the copies
@@ -233,6 +233,7 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
     const int nseg = p.d >> 5;
     const int extra = direct ? 2 : 1;      // ring slots a row's last batch adds: X piece (+ own Zcur piece)
     const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;   // this lane's 16 bytes of slot 0
+    int* dq = reinterpret_cast<int*>(meta + kMetaRing + 8);
 
     // row pointers of the span: lane i holds [start, end) of row r0 + i
     int rp_a = 0, rp_b = 0;
@@ -257,11 +258,13 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
         return true;
     };
 
-    Cursor ic, cq;
-    ic.ri = cq.ri = -1; ic.a = cq.a = 0; ic.k = cq.k = 0; ic.pos = cq.pos = 0;
+    // The consume side does not walk the rows again: every issued batch leaves a descriptor
+    //   m | last << 4 | row-in-span << 8 | meta offset << 16
+    // in an 8-entry queue of the warp's shared memory (all lanes store the same word, each reads its own).
+    Cursor ic;
+    ic.ri = -1; ic.a = 0; ic.k = 0; ic.pos = 0;
     bool more = advance(ic);
-    advance(cq);
-    int head = 0, tail = 0, used = 0, pending = 0;
+    int head = 0, tail = 0, used = 0, pending = 0, qh = 0, qt = 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float chunk_acc = 0.0f;
 
@@ -283,6 +286,8 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
                 const int off = filled + lane;
                 if (off < e_total) { pc = __ldg(offp + off); pw = __ldg(wp + off); }
             }
+            dq[qt & 7] = m | (last ? 16 : 0) | (ic.ri << 8) | ((u & 127) << 16);
+            ++qt;
             if (active) {
                 const int2* mp = meta + (u & 127);
                 switch (m) {
@@ -309,10 +314,11 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
         if (pending == 0) break;
         // ---- consume the oldest batch ----
         cp_async_wait_pending(pending);
-        const int m = min(8, cq.k - cq.pos);
-        const bool last = cq.pos + m >= cq.k;
-        const int2* mp = meta + ((cq.a + cq.pos - e_first) & 127);
-        if (cq.pos == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int desc = dq[qh & 7];
+        ++qh;
+        const int m = desc & 15;
+        const bool last = (desc & 16) != 0;
+        const int2* mp = meta + (desc >> 16);
         switch (m) {
             case 8: reduce_batch<8>(ring, head, mp, lane, acc, col_blocked); break;
             case 7: reduce_batch<7>(ring, head, mp, lane, acc, col_blocked); break;
@@ -323,21 +329,21 @@ __device__ __forceinline__ void row_span_task(const SweepParams& p, int r0, int 
             case 2: reduce_batch<2>(ring, head, mp, lane, acc, col_blocked); break;
             default: reduce_batch<1>(ring, head, mp, lane, acc, col_blocked); break;
         }
+        int need = m;
         if (last) {
             float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active) {
                 const float4 xs = ring[((head + m) & (kRing - 1)) * 32 + lane];
                 const float4 out = finish_row(xs, acc, p.gamma);
-                *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + cq.ri) * p.ld + c) = out;
+                *reinterpret_cast<float4*>(p.Zn + (size_t)(r0 + ((desc >> 8) & 0xff)) * p.ld + c) = out;
                 if (direct) dl = absdiff4(out, ring[((head + m + 1) & (kRing - 1)) * 32 + lane]);
             }
             // transpose scratch: the X slot of this batch (already read; not re-targeted before the next issue)
             if (direct) chunk_acc = chunk_add_row(chunk_acc, dl, nseg, lane, reinterpret_cast<float*>(ring + ((head + m) & (kRing - 1)) * 32));
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            need += extra;
         }
-        const int need = m + (last ? extra : 0);
         head += need; used -= need; --pending;
-        cq.pos += m;
-        advance(cq);
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
     if (direct) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
