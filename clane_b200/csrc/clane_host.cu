@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "plan.cuh"
+#include "program.cuh"
 
 extern "C" {
 
@@ -125,13 +126,11 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_span_row); cudaFree(plan->d_span_meta); cudaFree(plan->d_span_edges); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_tasks); cudaFree(plan->d_descs); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_hub_blk0); cudaFree(plan->d_hubS); cudaFree(plan->d_hubW); cudaFree(plan->d_hubT);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
     for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int i = 0; i < 6; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
-    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
-    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
-    if (plan->side) cudaStreamDestroy(plan->side);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -143,8 +142,115 @@ int clane_plan_destroy(clane_plan* plan) {
         if (e__ != cudaSuccess) { clane_plan_destroy(plan); return (int)e__; } \
     } while (0)
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// the sweep's program: every control decision of k_sweep_rows, made once per graph (sweep.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Batch { int m, last, row, u; };
+
+// Descriptors of a task's batches.  The kernel keeps one batch of loads in flight ahead of the one it reduces;
+// the only other decision is when the next 32-edge (offset, w) window must be published to the warp's ring
+// (128 entries: the reducer, one batch behind, never sees its entries overwritten).
+void emit_descriptors(const std::vector<Batch>& bs, std::vector<int32_t>& out) {
+    using namespace clane;
+    int filled = 0;
+    for (const Batch& b : bs) {
+        int pub = 0;
+        if (filled < b.u + b.m) { pub = 1; filled += 32; }
+        out.push_back(b.m | (b.last ? kDescLast : 0) | (pub ? kDescPub : 0) | (b.row << kDescRowShift) |
+                      ((b.u & (kMetaRing - 1)) << kDescMetaShift));
+    }
+}
+
+// hub segments (16 full blocks each, longest rows first), then the spans by edge count, descending
+int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const int32_t* smeta, int32_t n_spans,
+                  const int32_t* hrows, int32_t n_hrows, std::vector<clane::SweepTask>& tasks,
+                  std::vector<int32_t>& descs, std::vector<int32_t>& blk0, int64_t* hub_blocks) {
+    using namespace clane;
+    std::vector<Batch> bs;
+    try {
+        blk0.assign((size_t)std::max(n_hrows, 1), 0);
+        int64_t blocks = 0;
+        for (int32_t h = 0; h < n_hrows; ++h) {
+            const int32_t v = hrows[h], a = h_rowptr[v], nblk = (h_rowptr[v + 1] - a) / 8;
+            if (blocks + nblk > INT32_MAX) return CLANE_ERANGE;
+            blk0[h] = (int32_t)blocks;
+            for (int32_t b0 = 0; b0 < nblk; b0 += kSegEdges / 8) {
+                const int32_t nbk = std::min<int32_t>(kSegEdges / 8, nblk - b0);
+                bs.clear();
+                for (int32_t j = 0; j < nbk; ++j) bs.push_back(Batch{8, 0, 0, 8 * j});
+                SweepTask t{(int32_t)descs.size(), nbk, a + b0 * 8, nbk * 8, b0, kTaskSegment, (int32_t)blocks, nblk};
+                emit_descriptors(bs, descs);
+                tasks.push_back(t);
+            }
+            blocks += (nblk + 1) & ~1;   // every row's scratch starts 16-byte aligned in hubW
+        }
+        *hub_blocks = blocks;
+        for (int32_t i = 0; i < n_spans; ++i) {
+            const int32_t r0 = srow[i], nrows = smeta[i] & 0xff, direct = (smeta[i] >> 8) && fuse;
+            const int32_t e0 = h_rowptr[r0];
+            bs.clear();
+            for (int32_t r = 0; r < nrows; ++r) {
+                const int32_t a = h_rowptr[r0 + r], k = h_rowptr[r0 + r + 1] - a;
+                for (int32_t pos = 0; pos < k; pos += 8) {
+                    const int32_t m = std::min(8, k - pos);
+                    bs.push_back(Batch{m, pos + m >= k, r, a + pos - e0});
+                }
+            }
+            SweepTask t{(int32_t)descs.size(), (int32_t)bs.size(), e0, h_rowptr[r0 + nrows] - e0, r0,
+                        nrows | (direct ? kTaskDirect : 0), 0, 0};
+            emit_descriptors(bs, descs);
+            tasks.push_back(t);
+            if (descs.size() > (size_t)INT32_MAX) return CLANE_ERANGE;
+        }
+    } catch (const std::bad_alloc&) {
+        return (int)cudaErrorMemoryAllocation;
+    }
+    return CLANE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clane_sweep_program(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
+                        int32_t hub_threshold, int32_t span_edges, int32_t* h_tasks, int64_t task_cap,
+                        int32_t* h_descs, int64_t desc_cap, int64_t* n_tasks, int64_t* n_descs) {
+    if (!h_rowptr || !n_tasks || !n_descs || n < 0 || row_lo < 0 || row_hi > n || row_lo > row_hi) return CLANE_EINVAL;
+    const size_t cap = (size_t)(row_hi - row_lo) + 1;
+    try {
+        std::vector<int32_t> srow(cap), smeta(cap), fix(cap), hrows(cap), blk0, descs;
+        std::vector<clane::SweepTask> tasks;
+        int32_t n_spans = 0, n_fix = 0, n_hrows = 0, G = 0, fuse = 0;
+        int rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, hub_threshold, span_edges, srow.data(), smeta.data(),
+                                      &n_spans, fix.data(), &n_fix, hrows.data(), &n_hrows, &G, &fuse);
+        if (rc != CLANE_OK) return rc;
+        int64_t hub_blocks = 0;
+        rc = build_program(h_rowptr, fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, descs, blk0,
+                           &hub_blocks);
+        if (rc != CLANE_OK) return rc;
+        *n_tasks = (int64_t)tasks.size();
+        *n_descs = (int64_t)descs.size();
+        if (h_tasks) {
+            if (task_cap < (int64_t)tasks.size()) return CLANE_EWORKSPACE;
+            memcpy(h_tasks, tasks.data(), tasks.size() * sizeof(clane::SweepTask));
+        }
+        if (h_descs) {
+            if (desc_cap < (int64_t)descs.size()) return CLANE_EWORKSPACE;
+            memcpy(h_descs, descs.data(), descs.size() * sizeof(int32_t));
+        }
+    } catch (const std::bad_alloc&) {
+        return (int)cudaErrorMemoryAllocation;
+    }
+    return CLANE_OK;
+}
+
 int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr, int32_t row_lo,
                       int32_t row_hi, int32_t hub_threshold) {
+    using namespace clane;
     if (!out || n < 0 || e < 0 || d < 1) return CLANE_EINVAL;
     if (h_rowptr && (row_lo < 0 || row_hi > n || row_lo > row_hi)) return CLANE_EINVAL;
     if (h_rowptr && h_rowptr[n] != e) return CLANE_EINVAL;
@@ -153,12 +259,18 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     clane_plan* plan = new (std::nothrow) clane_plan();
     if (!plan) return (int)cudaErrorMemoryAllocation;
     plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
-    plan->hub_threshold = hub_threshold > 0 ? std::max(hub_threshold, 8) : 1024;
+    // hub rows bound the critical path of a sweep: a row of k neighbours is an in-order chain of k/8 batches
+    // on one warp (~30 ns per neighbour), so rows longer than ~E/4096 neighbours go to the segment + chain path
+    const int64_t auto_thr = std::min<int64_t>(16384, std::max<int64_t>(256, (e / 4096 + 7) / 8 * 8));
+    plan->hub_threshold = hub_threshold > 0 ? std::min(std::max(hub_threshold, 8), 1 << 20) : (int32_t)auto_thr;
     plan->span_edges = 128;
     // tuning aids (benchmark sweeps only)
     if (const char* v = getenv("CLANE_HUB_THRESHOLD")) plan->hub_threshold = std::max(atoi(v), 8);
     if (const char* v = getenv("CLANE_SPAN_EDGES")) plan->span_edges = std::max(atoi(v), 8);
     plan->nslab = (plan->ld + 127) / 128;
+    plan->limit = (d / 16) * 16;
+    plan->ntail4 = (plan->ld - plan->limit) / 4;
+    plan->nslab32b = (plan->limit + 31) / 32;
 
     // cascade scratch: L1 over n*d (one quantity) and the norms over e*d (two quantities)
     const int64_t n_l1 = (int64_t)n * d, n_nrm = e * (int64_t)d;
@@ -173,13 +285,6 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     if ((int64_t)n * plan->ld > (int64_t)INT32_MAX) { clane_plan_destroy(plan); return CLANE_ERANGE; }   // int32 row offsets
     plan->has_schedule = true;
     PLAN_CUDA(cudaMalloc(&plan->d_coloff, std::max<size_t>((size_t)e, 1) * sizeof(int32_t)));
-    {   // the hub kernel is the sweep's critical path: its CTAs are dispatched ahead of the row kernel's
-        int lo = 0, hi = 0;
-        PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
-    }
-    PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
-    PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
     plan->row_lo = row_lo; plan->row_hi = row_hi;
     plan->edge_lo = h_rowptr[row_lo]; plan->edge_hi = h_rowptr[row_hi];
     const size_t cap = (size_t)(row_hi - row_lo) + 1;
@@ -192,24 +297,30 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->n_spans = n_spans;
     plan->n_fix_groups = n_fix;
     plan->n_hub_rows = n_hrows;
-    plan->nslab32 = (plan->ld + 31) / 32;
-    PLAN_CUDA(cudaMalloc(&plan->d_span_row, std::max<size_t>(n_spans, 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaMalloc(&plan->d_span_meta, std::max<size_t>(n_spans, 1) * sizeof(int32_t)));
+
+    std::vector<SweepTask> tasks;
+    std::vector<int32_t> descs, blk0;
+    rc = build_program(h_rowptr, plan->fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, descs, blk0,
+                       &plan->hub_blocks);
+    if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
+    plan->n_tasks = (int32_t)tasks.size();
+    plan->n_descs = (int64_t)descs.size();
+    PLAN_CUDA(cudaMalloc(&plan->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(SweepTask)));
+    PLAN_CUDA(cudaMalloc(&plan->d_descs, std::max<size_t>(descs.size(), 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaMalloc(&plan->d_span_edges, std::max<size_t>(n_spans, 1) * sizeof(int2)));
-    if (n_spans) {
-        std::vector<int2> sedges((size_t)n_spans);
-        for (int32_t i = 0; i < n_spans; ++i) {
-            const int32_t a = h_rowptr[srow[i]], b = h_rowptr[srow[i] + (smeta[i] & 0xff)];
-            sedges[i] = make_int2(a, b - a);
-        }
-        PLAN_CUDA(cudaMemcpy(plan->d_span_edges, sedges.data(), n_spans * sizeof(int2), cudaMemcpyHostToDevice));
-        PLAN_CUDA(cudaMemcpy(plan->d_span_row, srow.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
-        PLAN_CUDA(cudaMemcpy(plan->d_span_meta, smeta.data(), n_spans * sizeof(int32_t), cudaMemcpyHostToDevice));
-    }
+    PLAN_CUDA(cudaMalloc(&plan->d_hub_blk0, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
+    if (!tasks.empty()) PLAN_CUDA(cudaMemcpy(plan->d_tasks, tasks.data(), tasks.size() * sizeof(SweepTask), cudaMemcpyHostToDevice));
+    if (!descs.empty()) PLAN_CUDA(cudaMemcpy(plan->d_descs, descs.data(), descs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_fix) PLAN_CUDA(cudaMemcpy(plan->d_fix_groups, fix.data(), n_fix * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (n_hrows) PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (n_hrows) {
+        PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PLAN_CUDA(cudaMemcpy(plan->d_hub_blk0, blk0.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
+        const size_t nb = (size_t)plan->hub_blocks;
+        PLAN_CUDA(cudaMalloc(&plan->d_hubS, std::max<size_t>(nb * plan->nslab32b * 32, 1) * 16));
+        PLAN_CUDA(cudaMalloc(&plan->d_hubW, nb * 8));
+        if (plan->ntail4 > 0) PLAN_CUDA(cudaMalloc(&plan->d_hubT, nb * 8 * plan->ntail4 * 16));
+    }
     if (plan->fuse) {
         const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);
         PLAN_CUDA(cudaMalloc(&plan->d_P0, p0));
@@ -227,7 +338,7 @@ int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_span
     if (n_hub_rows) *n_hub_rows = plan->n_hub_rows;
     if (n_fix_groups) *n_fix_groups = plan->n_fix_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    // row sweep, [hub sweep], [chunk fix-up], level-1, finish
+    // row sweep, [hub chain], [chunk fix-up], level-1, finish
     if (launches_per_sweep)
         *launches_per_sweep = 3 + (plan->n_hub_rows > 0 ? 1 : 0) + ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
     return CLANE_OK;

@@ -163,10 +163,10 @@ k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2
     }
 }
 
-// col[e] * ld: the element offset the sweep gathers from (one multiply per edge, once per graph)
+// col[e] * ld / 4: the float4 index the sweep gathers from (one multiply per edge, once per graph)
 __global__ void k_col_offsets(const int32_t* __restrict__ col, int64_t e, int ld, int32_t* __restrict__ off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < e) off[i] = col[i] * ld;
+    if (i < e) off[i] = col[i] * (ld >> 2);
 }
 
 __global__ void k_cosine_finalize(const float* __restrict__ dots, const float* __restrict__ norms2, int64_t e,
@@ -289,41 +289,33 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
     p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
     p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
-    p.hub_rows = plan->d_hub_rows; p.n_hub_rows = plan->n_hub_rows; p.nslab32 = plan->nslab32;
-    p.span_row = plan->d_span_row; p.span_meta = plan->d_span_meta; p.span_edges = plan->d_span_edges;
-    p.n_spans = plan->n_spans;
-    p.row_lo = plan->row_lo; p.row_hi = plan->row_hi;
+    p.tasks = static_cast<const SweepTask*>(plan->d_tasks); p.descs = plan->d_descs; p.n_tasks = plan->n_tasks;
+    p.row_lo = plan->row_lo;
     p.G = plan->G; p.nslab = plan->nslab;
     p.fuse = (plan->fuse && want_l1) ? 1 : 0;
     p.P0 = plan->d_P0;
-    p.hub_threshold = plan->hub_threshold;
+    p.hub_rows = plan->d_hub_rows; p.hub_blk0 = plan->d_hub_blk0; p.n_hub_rows = plan->n_hub_rows;
+    p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
+    p.hubS = static_cast<float4*>(plan->d_hubS); p.hubW = static_cast<float2*>(plan->d_hubW);
+    p.hubT = static_cast<float4*>(plan->d_hubT);
     p.st = d_state;
-    {   // profiling aid only (results are incomplete): CLANE_DEBUG_ROLE=row | hub isolates one role
-        static const char* dbg = getenv("CLANE_DEBUG_ROLE");
-        if (dbg && dbg[0] == 'r') p.n_hub_rows = 0;
-        if (dbg && dbg[0] == 'h') p.n_spans = 0;
-    }
-    // The hub rows (few, long in-order chains) run on the plan's side stream next to the row kernel.
-    const int64_t hub_ctas = (int64_t)p.n_hub_rows * plan->nslab32;
-    const int64_t row_ctas = ((int64_t)p.n_spans * plan->nslab + kRowWarps - 1) / kRowWarps;
+    // Hub rows: their segments are the first tasks of the row kernel; the chains follow on the same stream.
+    const int64_t chain_ctas = (int64_t)p.n_hub_rows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
+    const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
     const bool prof = plan->profile;
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[0], st));
-    if (hub_ctas > 0) {
-        CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
-        CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-        if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], plan->side));
-        k_sweep_hubs<<<(unsigned)hub_ctas, kHubThreads, kHubSmemBytes, plan->side>>>(p);
-        CLANE_LAUNCH_CHECK();
-        if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], plan->side));
-        CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
-    }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[1], st));
     if (row_ctas > 0) {
-        k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, kRowSmemBytes, st>>>(p);
+        k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, 0, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[2], st));
-    if (hub_ctas > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], st));
+    if (chain_ctas > 0) {
+        k_hub_chain<<<(unsigned)chain_ctas, 32, kChainSmemBytes, st>>>(p);
+        CLANE_LAUNCH_CHECK();
+    }
+    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], st));
     struct ProfTail {   // records the end-of-sweep event on every exit path below
         clane_plan* pl; cudaStream_t s;
         ~ProfTail() { if (pl->profile) cudaEventRecord(pl->ev_prof[3], s); }
@@ -434,9 +426,8 @@ int clane_plan_profile_read(clane_plan* plan, float* h_ms) {
     CLANE_CUDA(cudaEventSynchronize(plan->ev_prof[3]));
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[0], plan->ev_prof[1], plan->ev_prof[2]));   // row kernel
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[1], plan->ev_prof[0], plan->ev_prof[3]));   // whole sweep
-    CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[2], plan->ev_prof[3]));   // join + L1 tail
-    h_ms[3] = 0.0f;
-    if (plan->n_hub_rows > 0) CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // hub kernel
+    CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[5], plan->ev_prof[3]));   // exact L1 tail
+    CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // hub chain kernel
     return CLANE_OK;
 }
 
@@ -451,8 +442,7 @@ int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweep
 int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
-    CLANE_CUDA(cudaFuncSetAttribute(k_sweep_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHubSmemBytes));
-    CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

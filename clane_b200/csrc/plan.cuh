@@ -15,16 +15,21 @@ struct clane_plan {
     int32_t n_groups = 0;       // groups covering [row_lo, row_hi)
     int32_t span_edges = 128;   // edge budget of a span
     int32_t n_spans = 0, n_fix_groups = 0, n_hub_rows = 0;
-    int32_t nslab32 = 1;        // 32-column slabs per row (hub role)
-    int32_t* d_span_row = nullptr;     // spans (runs of ordinary rows inside one group), by edge count descending
-    int32_t* d_span_meta = nullptr;    // rows | direct << 8
-    int2* d_span_edges = nullptr;      // (first edge, edge count) of each span
+    // the sweep's program (sweep.cuh): tasks sorted by work descending (hub segments first), batch descriptors
+    void* d_tasks = nullptr;           // SweepTask[n_tasks]
+    int32_t* d_descs = nullptr;
+    int32_t n_tasks = 0;
+    int64_t n_descs = 0;
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
+    int32_t* d_hub_blk0 = nullptr;     // first scratch block of each hub row
+    int64_t hub_blocks = 0;            // 8-neighbour blocks of all hub rows
+    int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it
+    void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
+    void* d_hubW = nullptr;            // float2[hub_blocks]      {w4, w6}
+    void* d_hubT = nullptr;            // float4[hub_blocks * 8][ntail4]  raw z, sequential-regime columns
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
-    cudaStream_t side = nullptr;       // hub kernel runs here, forked from / joined to the caller's stream
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between
     // two argument sets, so two entries suffice; anything else falls back to direct launches.
     struct SweepGraph {

@@ -77,12 +77,17 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
  *   - rows are cut into groups of `group_rows` consecutive rows (one level-0 chunk of the
  *     ATen cascade sum when d is 32, 64 or 128 and the plan covers all rows -- then the L1
  *     change is fused into the sweep; otherwise 8 rows and the L1 change is a second pass);
- *   - rows of degree > hub_threshold are "hub rows": one CTA per 32-column slab of the row,
- *     the neighbour rows streamed through a shared-memory ring, longest first;
+ *   - rows of degree > hub_threshold are "hub rows": cut into segments of 128 neighbours that any
+ *     warp gathers and pre-reduces ({z6, z4, X, Y} per 8-neighbour block -- the part of the
+ *     reference's summation order that does not involve the running sum); one warp per (hub
+ *     row, 32 columns) then runs the short in-order chain over that contiguous stream;
  *   - the ordinary rows of a group are cut into spans of bounded edge count, sorted by edge
- *     count descending and handed to warps eight at a time; groups of sinks only are dropped
- *     (embedder.py:88-89: such rows are never updated).
- * hub_threshold <= 0 selects the default (1024).
+ *     count descending, one warp per (span, 128-column slab); groups of sinks only are dropped
+ *     (embedder.py:88-89: such rows are never updated);
+ *   - the control flow of the sweep kernel (batch sizes, row ends, window refills) is
+ *     precomputed into 32-bit batch descriptors: see clane_sweep_program.
+ * hub_threshold <= 0 selects the default: E/4096 rounded up to a multiple of 8, clamped to
+ * [256, 16384] (a row is an in-order chain on one warp; this bounds it to a few percent of a sweep).
  * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
 typedef struct clane_plan clane_plan;
 /* The schedule alone, on the host (what clane_plan_create uploads); every output has capacity
@@ -98,6 +103,18 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
                          int32_t hub_threshold, int32_t span_edges, int32_t* h_span_row, int32_t* h_span_meta,
                          int32_t* n_spans, int32_t* h_fix_groups, int32_t* n_fix_groups, int32_t* h_hub_rows,
                          int32_t* n_hub_rows, int32_t* group_rows, int32_t* fused_l1);
+/* The sweep kernel's program for that schedule, on the host (what clane_plan_create uploads).
+ *   h_tasks : 8 int32 per task {first descriptor, batches, first edge, edges, first row (span) or
+ *             first 8-block within the hub row (segment), rows | direct << 8 | segment << 9,
+ *             first scratch block of the hub row (segment), 8-blocks of the hub row (segment)};
+ *             hub segments first (rows by degree, descending), then spans by edge count descending
+ *   h_descs : one int32 per batch (<= 8 neighbours of one row):  m | last << 4 | publish the
+ *             next 32-edge (offset, w) window first << 5 | row in span << 6 | (edge offset in
+ *             the task's stream mod 128) << 19.
+ * Either buffer may be NULL (sizes only); CLANE_EWORKSPACE if a capacity is too small. */
+int clane_sweep_program(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
+                        int32_t hub_threshold, int32_t span_edges, int32_t* h_tasks, int64_t task_cap,
+                        int32_t* h_descs, int64_t desc_cap, int64_t* n_tasks, int64_t* n_descs);
 int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
                       int32_t row_lo, int32_t row_hi, int32_t hub_threshold);
 int clane_plan_destroy(clane_plan* plan);
@@ -169,8 +186,8 @@ int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, floa
 
 /* Measurement aid: when enabled, clane_sweep brackets its kernels with CUDA events on the
  * streams they are launched on; clane_plan_profile_read waits for the last sweep and returns
- * h_ms[0] = row kernel (k_sweep_rows), h_ms[1] = whole sweep, h_ms[2] = hub join + exact L1
- * tail (fix-up, level-1, finish), h_ms[3] = hub kernel (side stream; 0 if there is none). */
+ * h_ms[0] = row kernel (k_sweep_rows), h_ms[1] = whole sweep, h_ms[2] = exact L1 tail (fix-up,
+ * level-1, finish), h_ms[3] = hub chain kernel (k_hub_chain; ~0 if there are no hub rows). */
 int clane_plan_profile(clane_plan* plan, int enable);
 int clane_plan_profile_read(clane_plan* plan, float* h_ms);
 

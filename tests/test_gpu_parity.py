@@ -286,12 +286,12 @@ def test_hub_rows_and_fused_l1_against_oracle(n, d, hub_deg, tol, monkeypatch):
 
 
 def test_default_hub_threshold_long_rows_in_row_kernel():
-    """Rows of a few hundred neighbours stay in the row kernel at the default threshold (1024); one longer row
-    takes the hub kernel.  Both against the oracle."""
+    """Rows up to the default threshold (256 neighbours on a small graph) stay whole in the row kernel; longer
+    rows take the segment + chain path.  Both against the oracle."""
     rng = np.random.default_rng(77)
     n, d = 6000, 128
     src, dst = synth.make_edges(n, n * 5, "powerlaw", rng)
-    extra = [(5, 1500), (6, 1030), (900, 1000), (901, 700), (902, 300), (4001, 129)]
+    extra = [(5, 1500), (6, 1030), (900, 250), (901, 200), (902, 255), (4001, 129)]
     src = np.concatenate([src] + [np.full(k, r) for r, k in extra])
     dst = np.concatenate([dst] + [rng.permutation(n)[:k] for _, k in extra])
     X = rng.standard_normal((n, d), dtype=np.float32)

@@ -293,3 +293,144 @@ def test_cli_missing_config_and_unknown_method(tmp_path, data_root):
                                     "--config_file", str(cfg)])
     with pytest.raises(AttributeError, match="Given similarity method Nope not found."):
         embedding(args)
+
+
+# ---------------------------------------------------------------------------------------------
+# the sweep kernel's program: a host emulation of k_sweep_rows' control flow (sweep.cuh run_task)
+# ---------------------------------------------------------------------------------------------
+def sweep_program(rowptr, n, d, lo, hi, hub, span_edges=128):
+    L = _lib.lib()
+    nt, nd = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, 0, 0, 0, 0, ctypes.byref(nt),
+                                     ctypes.byref(nd)))
+    tasks = np.zeros((max(nt.value, 1), 8), np.int32)
+    descs = np.zeros(max(nd.value, 1), np.int32)
+    _lib.check(L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, tasks.ctypes.data, nt.value,
+                                     descs.ctypes.data, nd.value, ctypes.byref(nt), ctypes.byref(nd)))
+    assert L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, tasks.ctypes.data, nt.value - 1,
+                                 0, 0, ctypes.byref(nt), ctypes.byref(nd)) == (-3 if nt.value else 0)
+    return tasks[:nt.value], descs[:nd.value]
+
+
+def emulate_task(task, descs):
+    """Walk one task exactly as a warp of k_sweep_rows does (run_span / run_segment in sweep.cuh), with edge ids
+    instead of data.  Returns (segment, direct, [(row or scratch block, [edge ids in reduction order])])."""
+    desc_first, nb, e_first, e_total, r0, flags, blk_base, nblk_row = (int(x) for x in task)
+    segment, direct, nrows = bool(flags & 512), bool(flags & 256), flags & 0xff
+    dp = descs[desc_first:desc_first + nb]
+    if segment:        # whole (offset, w) stream in the ring, batches of 8 in order
+        assert e_total <= 128 and e_total == 8 * nb and r0 + nb <= nblk_row
+        return True, False, [(blk_base + r0 + b, list(range(e_first + 8 * b, e_first + 8 * b + 8))) for b in range(nb)]
+    meta = [None] * (128 + 8)             # (offset, w) ring with 8 mirrored entries -> stream offset held
+    state = {"dwin": [int(dp[l]) if l < nb else 0 for l in range(32)],
+             "dnext": [int(dp[32 + l]) if 32 + l < nb else 0 for l in range(32)],
+             "window": list(range(32)), "win_q": 0}
+
+    def next_desc(ib):
+        if ib % 32 == 0 and ib > 0:
+            state["dwin"] = state["dnext"]
+            state["dnext"] = [int(dp[ib + 32 + l]) if ib + 32 + l < nb else 0 for l in range(32)]
+        idesc = state["dwin"][ib & 31]
+        assert idesc == int(dp[ib])
+        if idesc & 32:
+            base = (state["win_q"] & 3) * 32
+            for lane in range(32):
+                meta[base + lane] = state["window"][lane] if state["window"][lane] < e_total else None
+                if base == 0 and lane < 8:
+                    meta[128 + lane] = meta[base + lane]
+            state["win_q"] += 1
+            state["window"] = [state["win_q"] * 32 + lane for lane in range(32)]
+        return idesc
+
+    def issue(idesc):       # what the loads of this batch fetch
+        m, mi = idesc & 15, (idesc >> 19) & 127
+        assert 1 <= m <= 8
+        u = meta[mi]
+        assert u is not None and u % 128 == mi
+        for i in range(m):
+            assert meta[mi + i] == u + i, "(offset, w) ring does not hold the batch's edges"
+        row = r0 + ((idesc >> 6) & 31) if idesc & 16 else None
+        return [e_first + u + i for i in range(m)], row
+
+    def consume(idesc, loaded):
+        m, mi = idesc & 15, (idesc >> 19) & 127
+        edges, row = loaded
+        for i in range(m):     # the weights are read one batch later: the ring must still hold them
+            assert e_first + meta[mi + i] == edges[i]
+        cur.extend(edges)
+        if idesc & 16:
+            assert row is not None and row < r0 + nrows
+            out.append((row, list(cur)))
+            cur.clear()
+
+    out, cur = [], []
+    ida = next_desc(0)
+    A = issue(ida)
+    cb = 0
+    while True:
+        if cb + 1 < nb:
+            idb = next_desc(cb + 1)
+            B = issue(idb)
+        consume(ida, A)
+        cb += 1
+        if cb >= nb:
+            break
+        if cb + 1 < nb:
+            ida = next_desc(cb + 1)
+            A = issue(ida)
+        consume(idb, B)
+        cb += 1
+        if cb >= nb:
+            break
+    assert not cur
+    return False, direct, out
+
+
+@pytest.mark.parametrize("d,lo,hi,hub", [(128, 0, 2003, 128), (100, 0, 2003, 64), (128, 500, 1700, 128), (7, 0, 2003, 1 << 20)])
+def test_sweep_program_covers_every_edge_in_order(d, lo, hi, hub):
+    rng = np.random.default_rng(5)
+    n = 2003
+    deg = np.minimum((rng.pareto(1.0, n) * 3).astype(np.int64), n - 1)
+    deg[:6] = [0, 1, 33, 257, 1500, 2002]
+    deg[64:80] = 0
+    deg[96:104] = [0, 0, 0, 300, 0, 0, 0, 0]
+    deg[200:208] = [100, 100, 20, 5, 90, 90, 0, 120]
+    deg[300:308] = [7, 8, 9, 15, 16, 17, 1, 2]
+    src = np.repeat(np.arange(n), deg)
+    dst = np.concatenate([rng.permutation(n)[:k] for k in deg])
+    g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
+    rowptr = g._rowptr
+    k = np.diff(rowptr)
+    tasks, descs = sweep_program(rowptr, n, d, lo, hi, hub)
+    sr, sm, fx, hr, G, fused = group_schedule(rowptr, n, d, lo, hi, hub, 128)
+    seen_rows, seen_blocks, n_seg = {}, {}, 0
+    work = []
+    for t in tasks:
+        segment, direct, out = emulate_task(t, descs)
+        work.append((not segment, -int(t[3])))
+        if segment:
+            n_seg += 1
+            for blk, edges in out:
+                assert blk not in seen_blocks
+                seen_blocks[blk] = edges
+        else:
+            assert direct == (fused and any(int(r) == int(t[4]) and (m >> 8) for r, m in zip(sr, sm)))
+            for row, edges in out:
+                assert row not in seen_rows
+                seen_rows[row] = edges
+    spans_only = [w_ for w_ in work if w_[0]]
+    assert work[len(work) - len(spans_only):] == spans_only == sorted(spans_only)   # segments first, spans by edge count
+    for v in range(lo, hi):
+        if 0 < k[v] <= hub:
+            assert seen_rows[v] == list(range(rowptr[v], rowptr[v + 1]))
+        else:
+            assert v not in seen_rows
+    # hub rows: their full 8-blocks, rows in degree-descending order, every row's scratch starting at an even block
+    blk, nblocks = 0, 0
+    for v in hr:
+        for b in range(k[v] // 8):
+            assert seen_blocks[blk + b] == list(range(rowptr[v] + 8 * b, rowptr[v] + 8 * b + 8))
+        nblocks += k[v] // 8
+        blk += (k[v] // 8 + 1) & ~1
+    assert nblocks == len(seen_blocks)
+    assert n_seg == sum(-(-(k[v] // 8) // 16) for v in hr)
