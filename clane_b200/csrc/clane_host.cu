@@ -128,6 +128,10 @@ int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_tasks); cudaFree(plan->d_descs); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_hub_blk0); cudaFree(plan->d_hubS); cudaFree(plan->d_hubW); cudaFree(plan->d_hubT);
+    cudaFree(plan->d_hub_cnt); cudaFree(plan->d_hub_done);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+    if (plan->side) cudaStreamDestroy(plan->side);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
     for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int i = 0; i < 6; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
@@ -152,14 +156,16 @@ namespace {
 struct Batch { int m, last, row, u; };
 
 // Descriptors of a task's batches.  The kernel keeps one batch of loads in flight ahead of the one it reduces;
-// the only other decision is when the next 32-edge (offset, w) window must be published to the warp's ring
-// (128 entries: the reducer, one batch behind, never sees its entries overwritten).
-void emit_descriptors(const std::vector<Batch>& bs, std::vector<int32_t>& out) {
+// the only other decision is when the next 32-edge (offset, w) window is published to the warp's 4-window
+// ring: windows 0 and 1 when the task opens, window q at the first batch that touches window q - 1 (it
+// replaces window q - 4; the reducer, one batch behind, is in window q - 2 or later).
+void emit_descriptors(const std::vector<Batch>& bs, int e_total, std::vector<int32_t>& out) {
     using namespace clane;
-    int filled = 0;
+    int published = 2;
     for (const Batch& b : bs) {
         int pub = 0;
-        if (filled < b.u + b.m) { pub = 1; filled += 32; }
+        const int touched = (b.u + b.m - 1) / 32;
+        if (touched + 1 >= published && published * 32 < e_total) { pub = 1; ++published; }
         out.push_back(b.m | (b.last ? kDescLast : 0) | (pub ? kDescPub : 0) | (b.row << kDescRowShift) |
                       ((b.u & (kMetaRing - 1)) << kDescMetaShift));
     }
@@ -176,14 +182,14 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
         int64_t blocks = 0;
         for (int32_t h = 0; h < n_hrows; ++h) {
             const int32_t v = hrows[h], a = h_rowptr[v], nblk = (h_rowptr[v + 1] - a) / 8;
-            if (blocks + nblk > INT32_MAX) return CLANE_ERANGE;
+            if (blocks + nblk > INT32_MAX || h >= (1 << 21)) return CLANE_ERANGE;
             blk0[h] = (int32_t)blocks;
             for (int32_t b0 = 0; b0 < nblk; b0 += kSegEdges / 8) {
                 const int32_t nbk = std::min<int32_t>(kSegEdges / 8, nblk - b0);
                 bs.clear();
                 for (int32_t j = 0; j < nbk; ++j) bs.push_back(Batch{8, 0, 0, 8 * j});
-                SweepTask t{(int32_t)descs.size(), nbk, a + b0 * 8, nbk * 8, b0, kTaskSegment, (int32_t)blocks, nblk};
-                emit_descriptors(bs, descs);
+                SweepTask t{(int32_t)descs.size(), nbk, a + b0 * 8, nbk * 8, b0, kTaskSegment | (h << kTaskHubShift), (int32_t)blocks, nblk};
+                emit_descriptors(bs, nbk * 8, descs);
                 tasks.push_back(t);
             }
             blocks += (nblk + 1) & ~1;   // every row's scratch starts 16-byte aligned in hubW
@@ -202,7 +208,7 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
             }
             SweepTask t{(int32_t)descs.size(), (int32_t)bs.size(), e0, h_rowptr[r0 + nrows] - e0, r0,
                         nrows | (direct ? kTaskDirect : 0), 0, 0};
-            emit_descriptors(bs, descs);
+            emit_descriptors(bs, t.e_total, descs);
             tasks.push_back(t);
             if (descs.size() > (size_t)INT32_MAX) return CLANE_ERANGE;
         }
@@ -320,6 +326,18 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
         PLAN_CUDA(cudaMalloc(&plan->d_hubS, std::max<size_t>(nb * plan->nslab32b * 32, 1) * 16));
         PLAN_CUDA(cudaMalloc(&plan->d_hubW, nb * 8));
         if (plan->ntail4 > 0) PLAN_CUDA(cudaMalloc(&plan->d_hubT, nb * 8 * plan->ntail4 * 16));
+        const size_t chain_ctas = (size_t)n_hrows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
+        PLAN_CUDA(cudaMalloc(&plan->d_hub_cnt, n_hrows * sizeof(int32_t)));
+        PLAN_CUDA(cudaMalloc(&plan->d_hub_done, chain_ctas * sizeof(int32_t)));
+        PLAN_CUDA(cudaMemset(plan->d_hub_cnt, 0, n_hrows * sizeof(int32_t)));
+        PLAN_CUDA(cudaMemset(plan->d_hub_done, 0, chain_ctas * sizeof(int32_t)));
+        {   // the early chain pass runs beside the row kernel on its own stream, dispatched ahead of it
+            int lo = 0, hi = 0;
+            PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
+            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+        }
     }
     if (plan->fuse) {
         const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);

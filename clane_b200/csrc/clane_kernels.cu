@@ -298,21 +298,31 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
     p.hubS = static_cast<float4*>(plan->d_hubS); p.hubW = static_cast<float2*>(plan->d_hubW);
     p.hubT = static_cast<float4*>(plan->d_hubT);
+    p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
     p.st = d_state;
     // Hub rows: their segments are the first tasks of the row kernel; the chains follow on the same stream.
     const int64_t chain_ctas = (int64_t)p.n_hub_rows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
     const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
     const bool prof = plan->profile;
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[0], st));
+    static const bool overlap = getenv("CLANE_NO_CHAIN_OVERLAP") == nullptr;
+    if (chain_ctas > 0 && overlap) {   // early chain pass: beside the row kernel, waiting on its segment warps
+        CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
+        CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        k_hub_chain<true><<<(unsigned)chain_ctas, 32, kChainSmemBytes, plan->side>>>(p);
+        CLANE_LAUNCH_CHECK();
+        CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
+    }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[1], st));
     if (row_ctas > 0) {
         k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, 0, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[2], st));
+    if (chain_ctas > 0 && overlap) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], st));
-    if (chain_ctas > 0) {
-        k_hub_chain<<<(unsigned)chain_ctas, 32, kChainSmemBytes, st>>>(p);
+    if (chain_ctas > 0) {              // late pass: whatever the early one left, and the reset of its flags
+        k_hub_chain<false><<<(unsigned)chain_ctas, 32, kChainSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], st));
@@ -442,7 +452,8 @@ int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweep
 int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
-    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

@@ -28,6 +28,10 @@ struct clane_plan {
     void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
     void* d_hubW = nullptr;            // float2[hub_blocks]      {w4, w6}
     void* d_hubT = nullptr;            // float4[hub_blocks * 8][ntail4]  raw z, sequential-regime columns
+    int32_t* d_hub_cnt = nullptr;      // per hub row: segment warps done this sweep
+    int32_t* d_hub_done = nullptr;     // per chain CTA: produced by the early (overlapped) chain pass
+    cudaStream_t side = nullptr;       // the early chain pass runs here, forked from / joined to the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
     // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between

@@ -4,7 +4,7 @@
 
 // resident CTAs per SM the row kernel is compiled for (register budget: 65536 / (128 * occ) per thread)
 #ifndef CLANE_ROW_OCC
-#define CLANE_ROW_OCC 4
+#define CLANE_ROW_OCC 5
 #endif
 
 namespace clane {
@@ -16,7 +16,7 @@ struct SweepTask {
     int32_t e_first;      // first edge of the task's contiguous edge stream
     int32_t e_total;      // edges in the stream
     int32_t r0;           // span: first row.  segment: its first 8-block within the hub row
-    int32_t flags;        // rows in span (bits 0-7) | direct << 8 | segment << 9
+    int32_t flags;        // rows in span (bits 0-7) | direct << 8 | segment << 9 | hub row index << 10 (segment)
     int32_t blk_base;     // segment: first block of the hub row in the hub scratch
     int32_t nblk_row;     // segment: 8-blocks of the hub row
 };
@@ -24,6 +24,7 @@ static_assert(sizeof(SweepTask) == 32, "two int4 per task");
 
 constexpr int kTaskDirect = 1 << 8;
 constexpr int kTaskSegment = 1 << 9;
+constexpr int kTaskHubShift = 10;
 
 // batch descriptor fields
 constexpr int kDescLast = 1 << 4;

@@ -64,6 +64,8 @@ struct SweepParams {
     float4* hubS;               // per hub row [32-column slab][block][32] {z6, z4, X, Y}
     float2* hubW;               // [block] {w4, w6}
     float4* hubT;               // [block * 8 + i][ntail4] raw z of the sequential-regime columns
+    int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
+    int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
     const clane_patience* st;
 };
 
@@ -74,10 +76,11 @@ constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512;
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 
 // hub chain kernel: one warp per CTA
-constexpr int kChainGroup = 16;                // blocks per cp.async group
-constexpr int kChainGroups = 8;                // groups in flight (8 x 16 x 512 B = 64 KB)
+constexpr int kChainGroup = 16;                // blocks per TMA bulk copy (8 KB)
+constexpr int kChainGroups = 8;                // copies in flight (8 x 8 KB = 64 KB)
 constexpr size_t kChainSmemBytes = (size_t)kChainGroups * kChainGroup * 32 * sizeof(float4) +
-                                   (size_t)kChainGroups * kChainGroup * sizeof(float2);
+                                   (size_t)kChainGroups * kChainGroup * sizeof(float2) + kChainGroups * 8;   // + mbarriers
+constexpr unsigned long long kChainSpinNs = 2000000ull;   // early chain pass: give up after 2 ms
 constexpr int kTailGroup = 32;                 // neighbours per group of the sequential-regime chain
 constexpr int kTailGroups = 16;
 constexpr size_t kTailSmemBytes = (size_t)kTailGroups * kTailGroup * (4 * sizeof(float4) + sizeof(float));
@@ -139,6 +142,27 @@ __device__ __forceinline__ void cp_async4_sa(unsigned smem_addr, const void* gsr
 }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// mbarrier + TMA bulk copy (global -> shared, completion counted in bytes on the mbarrier)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred done;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
+        "@!done bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane m owns
@@ -154,17 +178,62 @@ __device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl
     return chunk_acc;
 }
 
-// neighbour row piece of this lane: 16 bytes at float4 index `off16` of the lane's column base
-__device__ __forceinline__ float4 gather4(const float4* __restrict__ zb, int off16) {
-    return __ldg(zb + (unsigned)off16);
+// L2 residency: Zcur (87 MB at arxiv shape) is gathered ~7 times per sweep and fits the 126 MB L2 only if the
+// streams that are touched once (X, Znext) do not displace it: Zcur loads carry an evict_last policy, X loads
+// and Znext stores an evict_first one.
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 
-// start the M gathers of one batch: 128-bit loads straight into registers (lane L loads exactly the float4
-// of columns it will reduce)
+// neighbour row piece of this lane: 16 bytes at float4 index `off16` of the lane's column base
+__device__ __forceinline__ float4 gather4(const float4* __restrict__ zb, int off16, unsigned long long keep) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(zb + (unsigned)off16), "l"(keep));
+    return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, const float4& v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+// Predicated loads in straight-line code.  Inside the pipelined loop every global load is one of these: loads
+// issued under divergent control flow (a switch on the batch length, an if on "last") make ptxas wait for the
+// outstanding loads at the next control-flow join -- which is the loop's back edge, exactly where the next
+// batch's loads must stay in flight.
+__device__ __forceinline__ void ldg4_if(float4& v, const float4* p, bool pred, unsigned long long pol) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred), "l"(pol));
+}
+__device__ __forceinline__ void ldg4_stream_if(float4& v, const float* p, bool pred, unsigned long long pol) {   // X
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred), "l"(pol));
+}
+__device__ __forceinline__ void ldg_i32_if(int& v, const int* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
+                 : "+r"(v) : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldg_f32_if(float& v, const float* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+                 : "+f"(v) : "l"(p), "r"((int)pred));
+}
+
+// the gathers of one batch: 128-bit loads straight into registers (lane L loads exactly the float4 of columns it
+// will reduce)
 template <int M>
-__device__ __forceinline__ void load_batch(float4 (&buf)[8], const int2* __restrict__ mp, const float4* __restrict__ zb) {
+__device__ __forceinline__ void load_batch(float4 (&buf)[8], const int2* __restrict__ mp, const float4* __restrict__ zb,
+                                           unsigned long long keep) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) buf[i] = gather4(zb, mp[i].x);
+    for (int i = 0; i < M; ++i) buf[i] = gather4(zb, mp[i].x, keep);
 }
 
 template <int M>
@@ -212,143 +281,124 @@ __device__ __forceinline__ void prefetch_task(const SweepParams& p, int ti, int 
 // ------------------------------------------------------------------------------------------
 // Per-warp state of the two streams a task reads: batch descriptors (a 32-entry window in registers, read
 // with a shuffle) and (offset, w) pairs (32-edge windows published to a 128-entry shared-memory ring).
+// Everything is an int offset from a kernel parameter (constant bank), not a pointer: registers are what
+// bounds the number of resident warps, and the resident warps are the memory-level parallelism.
 struct Streams {
-    const int32_t* dp;      // descriptors of the task
-    const int* offp;        // col * ld / 4 of the task's edges
-    const float* wp;
+    int desc_first, e_first;
     int nb, e_total;
     int dwin, dnext;        // descriptor windows: current, prefetched
-    int pc;                 // (offset, w) window held in registers, not yet published
+    int pc;                 // the next (offset, w) window to publish, held in registers
     float pw;
     int win_q;              // (offset, w) windows published so far
 };
 
+__device__ __forceinline__ void publish_window(int q, int pc, float pw, int lane, int2* meta) {
+    const int base = (q & 3) * 32;
+    const int2 v = make_int2(pc, __float_as_int(pw));
+    meta[base + lane] = v;
+    if (base == 0 && lane < 8) meta[kMetaRing + lane] = v;   // mirror: a batch never wraps
+}
+
+// Open a task's streams: descriptor windows 0 and 1 in registers; (offset, w) windows 0 and 1 published
+// (one coalesced round trip for all of it), window 2 on its way.
+__device__ __forceinline__ void open_streams(const SweepParams& p, Streams& s, int lane, int2* meta) {
+    const int32_t* dp = p.descs + s.desc_first;
+    const int* offp = p.coloff + s.e_first;
+    const float* wp = p.w + s.e_first;
+    s.dwin = lane < s.nb ? __ldg(dp + lane) : 0;
+    int c0 = 0, c1 = 0;
+    float w0 = 0.0f, w1 = 0.0f;
+    if (lane < s.e_total) { c0 = __ldg(offp + lane); w0 = __ldg(wp + lane); }
+    if (32 + lane < s.e_total) { c1 = __ldg(offp + 32 + lane); w1 = __ldg(wp + 32 + lane); }
+    s.dnext = 32 + lane < s.nb ? __ldg(dp + 32 + lane) : 0;
+    s.pc = 0; s.pw = 0.0f;
+    if (64 + lane < s.e_total) { s.pc = __ldg(offp + 64 + lane); s.pw = __ldg(wp + 64 + lane); }
+    // the rest of the streams: one L2 prefetch per 128-byte line now, so that the window loads further
+    // down are L2 hits
+    for (int i = 96 + lane * 32; i < s.e_total; i += 32 * 32) { prefetch_l2(offp + i); prefetch_l2(wp + i); }
+    for (int i = 64 + lane * 32; i < s.nb; i += 32 * 32) prefetch_l2(dp + i);
+    publish_window(0, c0, w0, lane, meta);
+    publish_window(1, c1, w1, lane, meta);
+    __syncwarp();
+    s.win_q = 2;
+}
+
 // descriptor of batch ib; afterwards the (offset, w) ring holds the batch's edges
-__device__ __forceinline__ int next_desc(Streams& s, int ib, int lane, int2* meta) {
-    if ((ib & 31) == 0 && ib > 0) {
-        s.dwin = s.dnext;
-        s.dnext = ib + 32 + lane < s.nb ? __ldg(s.dp + ib + 32 + lane) : 0;
-    }
+__device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int ib, int lane, int2* meta) {
+    const bool roll = (ib & 31) == 0 && ib > 0;
+    if (roll) { s.dwin = s.dnext; s.dnext = 0; }
+    ldg_i32_if(s.dnext, p.descs + s.desc_first + ib + 32 + lane, roll && ib + 32 + lane < s.nb);
     const int id = __shfl_sync(kFull, s.dwin, ib & 31);
-    if (id & kDescPub) {                               // publish the fetched window, fetch the next
-        const int base = (s.win_q & 3) * 32;
-        const int2 v = make_int2(s.pc, __float_as_int(s.pw));
-        meta[base + lane] = v;
-        if (base == 0 && lane < 8) meta[kMetaRing + lane] = v;   // mirror: a batch never wraps
+    const bool pub = (id & kDescPub) != 0;
+    if (pub) {
+        // This batch is the first to touch window win_q - 1: publish window win_q (fetched a whole window ago;
+        // it replaces window win_q - 4, which the previous batch has left) and fetch the next into the same
+        // registers.
+        publish_window(s.win_q, s.pc, s.pw, lane, meta);
         __syncwarp();
-        const int off = (++s.win_q) * 32 + lane;
-        if (off < s.e_total) { s.pc = __ldg(s.offp + off); s.pw = __ldg(s.wp + off); }
+        ++s.win_q;
     }
+    const int off = s.win_q * 32 + lane;
+    const bool fetch = pub && off < s.e_total;
+    ldg_i32_if(s.pc, p.coloff + s.e_first + off, fetch);
+    ldg_f32_if(s.pw, p.w + s.e_first + off, fetch);
     return id;
 }
 
-struct RowCtx {
-    const float4* zb;       // Zcur + this lane's columns
-    const float* xb;        // X + this lane's columns
-    float* znb;             // Znext + this lane's columns
-    int ld;
-    int r0;
-    float gamma;
-    bool active, col_blocked, direct;
-    int nseg, lane;
-    float* scratch;         // 512 bytes of the warp's shared memory (fused L1 transpose)
-};
-
-// loads of one batch into a register buffer (+ the row's X and own Zcur pieces if it is the row's last)
-__device__ __forceinline__ void issue_loads(const RowCtx& c, int id, const int2* meta, float4 (&buf)[8], float4& xs,
-                                            float4& own) {
-    const int2* mp = meta + ((id >> kDescMetaShift) & 127);
-    switch (id & 15) {
-        case 8: load_batch<8>(buf, mp, c.zb); break;
-        case 7: load_batch<7>(buf, mp, c.zb); break;
-        case 6: load_batch<6>(buf, mp, c.zb); break;
-        case 5: load_batch<5>(buf, mp, c.zb); break;
-        case 4: load_batch<4>(buf, mp, c.zb); break;
-        case 3: load_batch<3>(buf, mp, c.zb); break;
-        case 2: load_batch<2>(buf, mp, c.zb); break;
-        default: load_batch<1>(buf, mp, c.zb); break;
-    }
-    if (id & kDescLast) {
-        const size_t row_off = (size_t)(c.r0 + ((id >> kDescRowShift) & 31)) * c.ld;
-        xs = ld_stream4(c.xb + row_off);
-        if (c.direct) own = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(c.zb) + row_off));
-    }
-}
-
-__device__ __forceinline__ void consume_batch(const RowCtx& c, int id, const int2* meta, const float4 (&buf)[8],
-                                              const float4& xs, const float4& own, float4& acc, float& chunk_acc) {
-    const int2* mp = meta + ((id >> kDescMetaShift) & 127);
-    switch (id & 15) {
-        case 8: reduce_batch<8>(buf, mp, acc, c.col_blocked); break;
-        case 7: reduce_batch<7>(buf, mp, acc, c.col_blocked); break;
-        case 6: reduce_batch<6>(buf, mp, acc, c.col_blocked); break;
-        case 5: reduce_batch<5>(buf, mp, acc, c.col_blocked); break;
-        case 4: reduce_batch<4>(buf, mp, acc, c.col_blocked); break;
-        case 3: reduce_batch<3>(buf, mp, acc, c.col_blocked); break;
-        case 2: reduce_batch<2>(buf, mp, acc, c.col_blocked); break;
-        default: reduce_batch<1>(buf, mp, acc, c.col_blocked); break;
-    }
-    if (id & kDescLast) {
-        const float4 out = finish_row(xs, acc, c.gamma);
-        const size_t row_off = (size_t)(c.r0 + ((id >> kDescRowShift) & 31)) * c.ld;
-        if (c.active) *reinterpret_cast<float4*>(c.znb + row_off) = out;
-        if (c.direct) {
-            const float4 dl = c.active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
-            chunk_acc = chunk_add_row(chunk_acc, dl, c.nseg, c.lane, c.scratch);
-        }
-        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-// span task: double-buffered batches -- the loads of batch b + 1 are in flight while batch b is reduced
+// span task: one batch per round -- descriptor, <= 10 loads straight into registers, reduction.  A warp has one
+// batch of loads in flight; the memory-level parallelism comes from the resident warps per SM (measured with
+// tools/l1pf_probe.cu: deeper per-warp pipelines or L1 / L2 prefetching do not beat more warps).
+template <bool kDirect>
 __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, const int4 t1, int slab, int lane,
                                          int2* meta, float* scratch) {
     const int c0 = slab * 128 + lane * 4;
-    RowCtx c;
-    c.active = c0 < p.ld;
-    c.col_blocked = c0 < p.limit;
-    const int cc = c.active ? c0 : 0;          // idle lanes shadow lane 0 (same sectors: no extra traffic)
-    c.zb = reinterpret_cast<const float4*>(p.Zc + cc);
-    c.xb = p.X + cc;
-    c.znb = p.Zn + cc;
-    c.ld = p.ld;
-    c.r0 = t1.x;
-    c.gamma = p.gamma;
-    c.direct = (t1.y & kTaskDirect) != 0;
-    c.nseg = p.d >> 5;
-    c.lane = lane;
-    c.scratch = scratch;
-
+    const bool active = c0 < p.ld;
+    const bool col_blocked = c0 < p.limit;
+    const int cc = active ? c0 : 0;            // idle lanes shadow lane 0 (same sectors: no extra traffic)
+    const int r0 = t1.x;
     Streams s;
-    s.dp = p.descs + t0.x; s.nb = t0.y; s.offp = p.coloff + t0.z; s.wp = p.w + t0.z; s.e_total = t0.w;
-    // first windows: 32 descriptors, 32 (offset, w) pairs -- one coalesced round trip
-    s.dwin = lane < s.nb ? __ldg(s.dp + lane) : 0;
-    s.pc = 0; s.pw = 0.0f;
-    if (lane < s.e_total) { s.pc = __ldg(s.offp + lane); s.pw = __ldg(s.wp + lane); }
-    s.dnext = 32 + lane < s.nb ? __ldg(s.dp + 32 + lane) : 0;
-    s.win_q = 0;
-    // the rest of the streams: one L2 prefetch per 128-byte line now, so that the window loads further
-    // down are L2 hits instead of DRAM round trips on the warp's critical path
-    for (int i = 32 + lane * 32; i < s.e_total; i += 32 * 32) { prefetch_l2(s.offp + i); prefetch_l2(s.wp + i); }
-    for (int i = 64 + lane * 32; i < s.nb; i += 32 * 32) prefetch_l2(s.dp + i);
+    s.desc_first = t0.x; s.nb = t0.y; s.e_first = t0.z; s.e_total = t0.w;
+    open_streams(p, s, lane, meta);
 
-    float4 A[8], B[8], xa, xb, oa, ob;
-    xa = xb = oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned long long keep = policy_evict_last(), once = policy_evict_first();
+    float4 A[8], xs, own;
+    xs = own = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float chunk_acc = 0.0f;
     const int nb = s.nb;
-    int ida = next_desc(s, 0, lane, meta), idb = 0;
-    issue_loads(c, ida, meta, A, xa, oa);
-    for (int cb = 0;;) {
-        if (cb + 1 < nb) { idb = next_desc(s, cb + 1, lane, meta); issue_loads(c, idb, meta, B, xb, ob); }
-        consume_batch(c, ida, meta, A, xa, oa, acc, chunk_acc);
-        if (++cb >= nb) break;
-        if (cb + 1 < nb) { ida = next_desc(s, cb + 1, lane, meta); issue_loads(c, ida, meta, A, xa, oa); }
-        consume_batch(c, idb, meta, B, xb, ob, acc, chunk_acc);
-        if (++cb >= nb) break;
+    for (int cb = 0; cb < nb; ++cb) {
+        const int id = next_desc(p, s, cb, lane, meta);
+        const int2* mp = meta + ((id >> kDescMetaShift) & 127);
+        const bool last = (id & kDescLast) != 0;
+        const int row_off = (r0 + ((id >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
+        // ---- the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch
+        //      here would make ptxas wait for them at the join, before the gathers are even issued) ----
+        ldg4_stream_if(xs, p.X + row_off, last, once);
+        if (kDirect) ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last, keep);
+        // ---- m gathers, then the reduction in the reference's order ----
+        const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
+        switch (id & 15) {
+            case 8: load_batch<8>(A, mp, zb, keep); reduce_batch<8>(A, mp, acc, col_blocked); break;
+            case 7: load_batch<7>(A, mp, zb, keep); reduce_batch<7>(A, mp, acc, col_blocked); break;
+            case 6: load_batch<6>(A, mp, zb, keep); reduce_batch<6>(A, mp, acc, col_blocked); break;
+            case 5: load_batch<5>(A, mp, zb, keep); reduce_batch<5>(A, mp, acc, col_blocked); break;
+            case 4: load_batch<4>(A, mp, zb, keep); reduce_batch<4>(A, mp, acc, col_blocked); break;
+            case 3: load_batch<3>(A, mp, zb, keep); reduce_batch<3>(A, mp, acc, col_blocked); break;
+            case 2: load_batch<2>(A, mp, zb, keep); reduce_batch<2>(A, mp, acc, col_blocked); break;
+            default: load_batch<1>(A, mp, zb, keep); reduce_batch<1>(A, mp, acc, col_blocked); break;
+        }
+        if (last) {
+            const float4 out = finish_row(xs, acc, p.gamma);
+            if (active) st4_hint(p.Zn + row_off, out, once);
+            if (kDirect) {
+                const float4 dl = active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
+                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
-    if (c.direct && p.fuse) p.P0[(size_t)((c.r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
+    if (kDirect && p.fuse) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
 }
 
 // hub segment task: up to 16 full 8-blocks of one hub row; park {z6, z4, X, Y} per (block, column), or the
@@ -368,38 +418,46 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     const int* __restrict__ offp = p.coloff + t0.z;
     const float* __restrict__ wp = p.w + t0.z;
     // a segment is at most 128 edges: the whole (offset, w) stream fits the ring
-    for (int i = lane; i < t0.w; i += 32) meta[i] = make_int2(__ldg(offp + i), __float_as_int(__ldg(wp + i)));
+    const int slab_bytes = min(128, p.ld - slab * 128) * 4;
+    for (int i = lane; i < t0.w; i += 32) {
+        const int off16 = __ldg(offp + i);
+        meta[i] = make_int2(off16, __float_as_int(__ldg(wp + i)));
+        if (i >= 16) {   // the first two blocks are loaded right away
+            const char* a = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(p.Zc + slab * 128) + (unsigned)off16);
+            prefetch_l2(a);
+            if (slab_bytes > 128) prefetch_l2(a + 128);
+            if (slab_bytes > 256) prefetch_l2(a + 256);
+            if (slab_bytes > 384) prefetch_l2(a + 384);
+        }
+    }
     __syncwarp();
-    float4 A[8], B[8];
-    load_batch<8>(A, meta, zb);
-    auto park = [&](const float4 (&z)[8], int b) {
-        const int2* mp = meta + b * 8;
+    const unsigned long long keep = policy_evict_last();
+    float4 A[8];
+    for (int cb = 0; cb < nb; ++cb) {
+        load_batch<8>(A, meta + cb * 8, zb, keep);
+        const int2* mp = meta + cb * 8;
         float w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = __int_as_float(mp[i].y);
         if (active) {
             if (col_blocked) {
-                float4* o = sdst + (size_t)b * 32;
-                o[0] = park8(w, z[0].x, z[1].x, z[2].x, z[3].x, z[4].x, z[5].x, z[6].x, z[7].x);
-                o[1] = park8(w, z[0].y, z[1].y, z[2].y, z[3].y, z[4].y, z[5].y, z[6].y, z[7].y);
-                o[2] = park8(w, z[0].z, z[1].z, z[2].z, z[3].z, z[4].z, z[5].z, z[6].z, z[7].z);
-                o[3] = park8(w, z[0].w, z[1].w, z[2].w, z[3].w, z[4].w, z[5].w, z[6].w, z[7].w);
+                float4* o = sdst + (size_t)cb * 32;
+                st4_hint(reinterpret_cast<float*>(o + 0), park8(w, A[0].x, A[1].x, A[2].x, A[3].x, A[4].x, A[5].x, A[6].x, A[7].x), keep);
+                st4_hint(reinterpret_cast<float*>(o + 1), park8(w, A[0].y, A[1].y, A[2].y, A[3].y, A[4].y, A[5].y, A[6].y, A[7].y), keep);
+                st4_hint(reinterpret_cast<float*>(o + 2), park8(w, A[0].z, A[1].z, A[2].z, A[3].z, A[4].z, A[5].z, A[6].z, A[7].z), keep);
+                st4_hint(reinterpret_cast<float*>(o + 3), park8(w, A[0].w, A[1].w, A[2].w, A[3].w, A[4].w, A[5].w, A[6].w, A[7].w), keep);
             } else {
-                float4* o = tdst + (size_t)b * 8 * p.ntail4;
+                float4* o = tdst + (size_t)cb * 8 * p.ntail4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i * p.ntail4] = z[i];
+                for (int i = 0; i < 8; ++i) o[i * p.ntail4] = A[i];
             }
         }
-        if (slab == 0 && lane == 0) wdst[b] = make_float2(w[4], w[6]);
-    };
-    for (int cb = 0;;) {
-        if (cb + 1 < nb) load_batch<8>(B, meta + (cb + 1) * 8, zb);
-        park(A, cb);
-        if (++cb >= nb) break;
-        if (cb + 1 < nb) load_batch<8>(A, meta + (cb + 1) * 8, zb);
-        park(B, cb);
-        if (++cb >= nb) break;
+        if (slab == 0 && lane == 0) wdst[cb] = make_float2(w[4], w[6]);
     }
+    // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
 }
 
 __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(SweepParams p) {
@@ -417,22 +475,51 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
     prefetch_task(p, ti + kPrefetchAhead, slab, lane);
     if (t1.y & kTaskSegment) run_segment(p, t0, t1, slab, lane, meta);
-    else run_span(p, t0, t1, slab, lane, meta, scratch);
+    else if (t1.y & kTaskDirect) run_span<true>(p, t0, t1, slab, lane, meta, scratch);
+    else run_span<false>(p, t0, t1, slab, lane, meta, scratch);
 }
 
 // ------------------------------------------------------------------------------------------
 // hub chain: one warp per (hub row, 32 columns below `limit`), plus one warp per hub row for the
 // sequential-regime columns.  Runs after k_sweep_rows (same stream).
 // ------------------------------------------------------------------------------------------
+// kEarly: launched on a side stream BEFORE k_sweep_rows and running beside it; every CTA waits (bounded) for
+//         its row's segment warps, then chains.  The hub rows' segments are the first tasks of the row kernel,
+//         so the chains finish long before the ordinary rows do and cost the sweep nothing.
+// !kEarly: launched after both; chains whatever the early pass did not (it timed out: kernels serialised by a
+//         profiler, or the device too busy to co-schedule), and resets the flags for the next sweep.
+template <bool kEarly>
 __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x;
     const int per = p.nslab32b + (p.ntail4 > 0 ? 1 : 0);
     const int hr = blockIdx.x / per, s = blockIdx.x - hr * per;
+    const bool stopped = p.st != nullptr && p.st->stop;
+    if (kEarly && stopped) return;
     const int row = __ldg(p.hub_rows + hr);
     const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
     const int nblk = k >> 3;
+    if (kEarly) {
+        const int expect = ((nblk + kSegEdges / 8 - 1) / (kSegEdges / 8)) * p.nslab;
+        const volatile int* cnt = p.hub_cnt + hr;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        bool ready = false;
+        for (;;) {
+            if (*cnt >= expect) { ready = true; break; }
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > kChainSpinNs) break;
+        }
+        if (!ready) return;                            // the late pass does it
+        __threadfence();                               // acquire: the parked blocks of every segment warp
+        asm volatile("fence.proxy.async;" ::: "memory");   // ... also for the TMA reads below
+    } else {
+        const int done = p.hub_done[blockIdx.x];
+        __syncwarp();
+        if (lane == 0) { p.hub_done[blockIdx.x] = 0; if (s == 0) p.hub_cnt[hr] = 0; }   // also when stopped
+        if (done || stopped) return;
+    }
     const size_t B0 = (size_t)__ldg(p.hub_blk0 + hr);
     const int nleft = k - nblk * 8;
     float acc = 0.0f;
@@ -443,27 +530,35 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
         col = s * 32 + lane;
         act = col < p.limit;
         const int ccol = act ? col : 0;
-        float4* ringS = reinterpret_cast<float4*>(smem);                                  // [groups][16][32]
-        float2* wq = reinterpret_cast<float2*>(ringS + kChainGroups * kChainGroup * 32);  // [groups][16]
-        const unsigned ring_sa = smem_u32(ringS) + lane * 16;
-        const unsigned wq_sa = smem_u32(wq) + (lane & 15) * 8;
-        const float4* src = p.hubS + B0 * p.sld + (size_t)s * nblk * 32 + lane;   // contiguous 512 B per block
+        // The row's parked stream for this slab is contiguous: 512 bytes per block.  Lane 0 moves it with TMA
+        // bulk copies (one instruction per 8 KB chunk of 16 blocks, completion on an mbarrier), eight chunks in
+        // flight; the warp only runs the chain: two shared-memory loads and four dependent operations per block.
+        float4* ringS = reinterpret_cast<float4*>(smem);                                  // [stages][16][32]
+        float2* wq = reinterpret_cast<float2*>(ringS + kChainGroups * kChainGroup * 32);  // [stages][16]
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(wq + kChainGroups * kChainGroup);
+        const float4* src = p.hubS + B0 * p.sld + (size_t)s * nblk * 32;
         const float2* wsrc = p.hubW + B0;
         const int ngroups = (nblk + kChainGroup - 1) / kChainGroup;
-        auto issue = [&](int g) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kChainGroups; ++i) mbar_init(bars + i, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        auto issue = [&](int g) {   // lane 0 only
             if (g < ngroups) {
-                const int b0 = g * kChainGroup;
-                const unsigned dst = ring_sa + (unsigned)(g % kChainGroups) * (kChainGroup * 512);
-#pragma unroll
-                for (int j = 0; j < kChainGroup; ++j)
-                    if (b0 + j < nblk) cp_async16_sa(dst + j * 512, src + (size_t)(b0 + j) * 32);
-                if (lane < kChainGroup && b0 + lane < nblk)
-                    cp_async8_sa(wq_sa + (unsigned)(g % kChainGroups) * (kChainGroup * 8), wsrc + b0 + lane);
+                const int b0 = g * kChainGroup, st = g % kChainGroups;
+                const int cnt = min(kChainGroup, nblk - b0);
+                const unsigned wbytes = (unsigned)((cnt + 1) & ~1) * 8;   // 16-byte multiple; rows are padded to even blocks
+                mbar_expect_tx(bars + st, (unsigned)cnt * 512 + wbytes);
+                bulk_g2s(ringS + (size_t)st * kChainGroup * 32, src + (size_t)b0 * 32, (unsigned)cnt * 512, bars + st);
+                bulk_g2s(wq + st * kChainGroup, wsrc + b0, wbytes, bars + st);
             }
-            cp_async_commit();
         };
+        if (lane == 0) {
 #pragma unroll
-        for (int g = 0; g < kChainGroups - 1; ++g) issue(g);
+            for (int g = 0; g < kChainGroups; ++g) issue(g);
+        }
         // the k mod 8 leftovers: gathered now, added after the blocks
         float lz[7], lw[7];
 #pragma unroll
@@ -475,11 +570,10 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
             }
         }
         for (int g = 0; g < ngroups; ++g) {
-            issue(g + kChainGroups - 1);     // its slot held group g - 1: consumed (program order + syncwarp below)
-            cp_async_wait<kChainGroups - 1>();
-            __syncwarp();                    // wq of group g visible to all lanes
-            const float4* rs = ringS + (size_t)(g % kChainGroups) * kChainGroup * 32 + lane;
-            const float2* ws = wq + (g % kChainGroups) * kChainGroup;
+            const int st = g % kChainGroups;
+            mbar_wait(bars + st, (unsigned)(g / kChainGroups) & 1u);
+            const float4* rs = ringS + (size_t)st * kChainGroup * 32 + lane;
+            const float2* ws = wq + st * kChainGroup;
             const int cnt = min(kChainGroup, nblk - g * kChainGroup);
             if (cnt == kChainGroup) {
                 float4 v[kChainGroup];
@@ -503,9 +597,9 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
                     acc = fadd(acc, v.w);
                 }
             }
-            __syncwarp();                    // all lanes done with wq of this group before it is refilled
+            __syncwarp();                    // every lane has read this stage: refill it
+            if (lane == 0) issue(g + kChainGroups);
         }
-        cp_async_wait<0>();
 #pragma unroll
         for (int o = 0; o < 7; ++o)
             if (o < nleft) acc = ffma(lw[o], lz[o], acc);
@@ -561,6 +655,7 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
         const size_t off = (size_t)row * p.ld + col;
         p.Zn[off] = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
     }
+    if (kEarly && lane == 0) p.hub_done[blockIdx.x] = 1;
 }
 
 // Fused mode: the level-0 partial of every group that was not swept by a single warp (it holds

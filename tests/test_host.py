@@ -323,8 +323,18 @@ def emulate_task(task, descs):
         return True, False, [(blk_base + r0 + b, list(range(e_first + 8 * b, e_first + 8 * b + 8))) for b in range(nb)]
     meta = [None] * (128 + 8)             # (offset, w) ring with 8 mirrored entries -> stream offset held
     state = {"dwin": [int(dp[l]) if l < nb else 0 for l in range(32)],
-             "dnext": [int(dp[32 + l]) if 32 + l < nb else 0 for l in range(32)],
-             "window": list(range(32)), "win_q": 0}
+             "dnext": [int(dp[32 + l]) if 32 + l < nb else 0 for l in range(32)], "win_q": 0}
+
+    def publish(q):
+        base = (q & 3) * 32
+        for lane in range(32):
+            meta[base + lane] = q * 32 + lane if q * 32 + lane < e_total else None
+            if base == 0 and lane < 8:
+                meta[128 + lane] = meta[base + lane]
+
+    publish(0)
+    publish(1)
+    state["win_q"] = 2
 
     def next_desc(ib):
         if ib % 32 == 0 and ib > 0:
@@ -333,13 +343,9 @@ def emulate_task(task, descs):
         idesc = state["dwin"][ib & 31]
         assert idesc == int(dp[ib])
         if idesc & 32:
-            base = (state["win_q"] & 3) * 32
-            for lane in range(32):
-                meta[base + lane] = state["window"][lane] if state["window"][lane] < e_total else None
-                if base == 0 and lane < 8:
-                    meta[128 + lane] = meta[base + lane]
+            assert state["win_q"] * 32 < e_total, "published a window past the end of the stream"
+            publish(state["win_q"])
             state["win_q"] += 1
-            state["window"] = [state["win_q"] * 32 + lane for lane in range(32)]
         return idesc
 
     def issue(idesc):       # what the loads of this batch fetch
