@@ -66,6 +66,30 @@ struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + 
     }
 };
 
+// The <= 31 elements the finish kernel reads itself (everything past the last complete cascade row; the whole
+// array when n < 8), served from a 32-float buffer: a row-partitioned run all-reduces them with the level-1
+// slots, so the finish never touches Z (which a faster rank may already be overwriting with its next sweep).
+struct ElemValues {
+    static constexpr int NQ = 1;
+    const float* vals;
+    struct Base { int dummy; };
+    __device__ __forceinline__ Base prepare(int64_t) const { return Base{0}; }
+    __device__ __forceinline__ void load(const Base&, uint32_t off, float* v) const { v[0] = vals[off]; }
+};
+
+template <class Elem>
+__global__ void k_tail_values(Elem elem, CascadeShape sh, float* __restrict__ vals) {
+    const int64_t base = sh.n < 8 ? 0 : sh.ni * 32;
+    const int off = threadIdx.x;
+    float v[Elem::NQ];
+    v[0] = 0.0f;
+    if (base + off < sh.n) {
+        typename Elem::Base bs = elem.prepare(base);
+        elem.load(bs, (uint32_t)off, v);
+    }
+    vals[off] = v[0];
+}
+
 constexpr int kCascadeWarps = 16;
 
 // level-1 buffer layout (floats): P1[(n1_nodes + 1)][NQ][32] | R0[NQ][32]   (= n1_nodes + 2 slots)

@@ -265,9 +265,11 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     clane_plan* plan = new (std::nothrow) clane_plan();
     if (!plan) return (int)cudaErrorMemoryAllocation;
     plan->n = n; plan->e = e; plan->d = d; plan->ld = clane_padded_ld(d);
-    // hub rows bound the critical path of a sweep: a row of k neighbours is an in-order chain of k/8 batches
-    // on one warp (~30 ns per neighbour), so rows longer than ~E/4096 neighbours go to the segment + chain path
-    const int64_t auto_thr = std::min<int64_t>(16384, std::max<int64_t>(256, (e / 4096 + 7) / 8 * 8));
+    // Hub rows bound the critical path of a sweep: a row of k neighbours is an in-order chain of k/8 batches on
+    // one warp (~150 ns per neighbour), so rows longer than 1/4096 of the edges this plan sweeps (a few percent of
+    // the row kernel's duration) go to the segment + chain path.
+    const int64_t e_local = h_rowptr ? (int64_t)h_rowptr[row_hi] - h_rowptr[row_lo] : e;
+    const int64_t auto_thr = std::min<int64_t>(16384, std::max<int64_t>(256, (e_local / 4096 + 7) / 8 * 8));
     plan->hub_threshold = hub_threshold > 0 ? std::min(std::max(hub_threshold, 8), 1 << 20) : (int32_t)auto_thr;
     plan->span_edges = 128;
     // tuning aids (benchmark sweeps only)

@@ -300,6 +300,15 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.hubT = static_cast<float4*>(plan->d_hubT);
     p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
     p.st = d_state;
+    static const bool dbg_chain = getenv("CLANE_DEBUG_CHAIN") != nullptr;
+    p.dbg = dbg_chain ? 1 : 0;
+    p.n_remote = 0;
+    static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only
+    for (int t = 0; t < 2 && plan->n_peers > 1 && !no_peer_stores; ++t)
+        if (plan->peers[t][plan->self_rank] == d_Znext) {
+            for (int r = 0; r < plan->n_peers; ++r)
+                if (r != plan->self_rank) p.peer[p.n_remote++] = plan->peers[t][r];
+        }
     // Hub rows: their segments are the first tasks of the row kernel; the chains follow on the same stream.
     const int64_t chain_ctas = (int64_t)p.n_hub_rows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
     const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
@@ -309,7 +318,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     if (chain_ctas > 0 && overlap) {   // early chain pass: beside the row kernel, waiting on its segment warps
         CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
         CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-        k_hub_chain<true><<<(unsigned)chain_ctas, 32, kChainSmemBytes, plan->side>>>(p);
+        k_hub_chain<true><<<(unsigned)chain_ctas, kChainThreads, kChainSmemBytes, plan->side>>>(p);
         CLANE_LAUNCH_CHECK();
         CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
     }
@@ -322,7 +331,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     if (chain_ctas > 0 && overlap) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], st));
     if (chain_ctas > 0) {              // late pass: whatever the early one left, and the reset of its flags
-        k_hub_chain<false><<<(unsigned)chain_ctas, 32, kChainSmemBytes, st>>>(p);
+        k_hub_chain<false><<<(unsigned)chain_ctas, kChainThreads, kChainSmemBytes, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], st));
@@ -419,6 +428,38 @@ int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, floa
                     clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
     if (!plan || !d_Za || !d_Zb || !d_p1) return CLANE_EINVAL;
     ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
+    return cascade_launch_finish(el, (int64_t)plan->n * plan->d, d_p1, plan->d_p2, d_out, d_state, d_amounts_log,
+                                 log_cap, nullptr, (cudaStream_t)s);
+}
+
+int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
+                         const uint64_t* h_ptrs_b) {
+    if (!plan || n_peers < 0 || n_peers > kMaxPeers + 1 || (n_peers > 0 && (self_rank < 0 || self_rank >= n_peers)))
+        return CLANE_EINVAL;
+    if (n_peers > 0 && (!h_ptrs_a || !h_ptrs_b)) return CLANE_EINVAL;
+    plan->n_peers = n_peers;
+    plan->self_rank = self_rank;
+    for (int r = 0; r < n_peers; ++r) {
+        plan->peers[0][r] = reinterpret_cast<float*>(h_ptrs_a[r]);
+        plan->peers[1][r] = reinterpret_cast<float*>(h_ptrs_b[r]);
+    }
+    for (auto& g : plan->graphs)   // cached sweeps were captured with the old peer set
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    return CLANE_OK;
+}
+
+int clane_l1_tail_values(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_vals, clane_stream_t s) {
+    if (!plan || !d_Za || !d_Zb || !d_vals) return CLANE_EINVAL;
+    ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};
+    k_tail_values<<<1, 32, 0, (cudaStream_t)s>>>(el, cascade_shape((int64_t)plan->n * plan->d), d_vals);
+    CLANE_LAUNCH_CHECK();
+    return CLANE_OK;
+}
+
+int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, float* d_out, clane_patience* d_state,
+                           float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !d_p1 || !d_vals) return CLANE_EINVAL;
+    ElemValues el{d_vals};
     return cascade_launch_finish(el, (int64_t)plan->n * plan->d, d_p1, plan->d_p2, d_out, d_state, d_amounts_log,
                                  log_cap, nullptr, (cudaStream_t)s);
 }

@@ -32,6 +32,9 @@ struct clane_plan {
     int32_t* d_hub_done = nullptr;     // per chain CTA: produced by the early (overlapped) chain pass
     cudaStream_t side = nullptr;       // the early chain pass runs here, forked from / joined to the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // row-partitioned run: peer Znext buffers for the two Z ping-pong buffers (entry self = own buffer)
+    int32_t n_peers = 0, self_rank = 0;
+    float* peers[2][16] = {};
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
     // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between

@@ -31,6 +31,8 @@
 //               that contiguous stream (one warp per (hub row, 32 columns), cp.async ring).  Columns in
 //               the sequential regime (>= 16*floor(d/16)) are parked raw and chained by one more warp.
 #pragma once
+#include <cstdio>
+
 #include "common.cuh"
 #include "program.cuh"
 
@@ -63,10 +65,15 @@ struct SweepParams {
     int sld;                    // 32 * nslab32b: columns per block in hubS
     float4* hubS;               // per hub row [32-column slab][block][32] {z6, z4, X, Y}
     float2* hubW;               // [block] {w4, w6}
-    float4* hubT;               // [block * 8 + i][ntail4] raw z of the sequential-regime columns
+    float4* hubT;               // per hub row [sequential-regime column][neighbour] raw z (floats)
     int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
     int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
     const clane_patience* st;
+    // row-partitioned run: the other ranks' Znext buffers (peer memory over NVLink); every finished row is
+    // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
+    float* peer[kMaxPeers];
+    int n_remote;
+    int dbg;                    // CLANE_DEBUG_CHAIN: device printf of the hub pipeline's timestamps
 };
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA
@@ -76,15 +83,16 @@ constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512;
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 
 // hub chain kernel: one warp per CTA
-constexpr int kChainGroup = 16;                // blocks per TMA bulk copy (8 KB)
-constexpr int kChainGroups = 8;                // copies in flight (8 x 8 KB = 64 KB)
+constexpr int kChainGroup = 16;                // blocks per cp.async group (8 KB)
+constexpr int kChainGroups = 12;               // groups in flight (12 x 8 KB = 96 KB: two chain CTAs per SM)
 constexpr size_t kChainSmemBytes = (size_t)kChainGroups * kChainGroup * 32 * sizeof(float4) +
-                                   (size_t)kChainGroups * kChainGroup * sizeof(float2) + kChainGroups * 8;   // + mbarriers
+                                   (size_t)kChainGroups * kChainGroup * sizeof(float2);
 constexpr unsigned long long kChainSpinNs = 2000000ull;   // early chain pass: give up after 2 ms
-constexpr int kTailGroup = 32;                 // neighbours per group of the sequential-regime chain
-constexpr int kTailGroups = 16;
-constexpr size_t kTailSmemBytes = (size_t)kTailGroups * kTailGroup * (4 * sizeof(float4) + sizeof(float));
-static_assert(kTailSmemBytes <= kChainSmemBytes, "one dynamic shared memory size for both roles");
+constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
+constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
+constexpr int kMaxStages = 128;                // mbarrier pairs per chain CTA
+constexpr int kChainThreads = 64;              // producer warp + chain warp
+static_assert(kChainGroups <= kMaxStages, "mbarriers");
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -142,13 +150,17 @@ __device__ __forceinline__ void cp_async4_sa(unsigned smem_addr, const void* gsr
 }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// mbarrier + TMA bulk copy (global -> shared, completion counted in bytes on the mbarrier)
+// mbarriers of the hub chain's producer / consumer ring
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
@@ -157,10 +169,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
         "@!done bra WAIT_%=;\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -389,7 +397,10 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
         }
         if (last) {
             const float4 out = finish_row(xs, acc, p.gamma);
-            if (active) st4_hint(p.Zn + row_off, out, once);
+            if (active) {
+                st4_hint(p.Zn + row_off, out, once);
+                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
+            }
             if (kDirect) {
                 const float4 dl = active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
                 chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
@@ -413,7 +424,9 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     const size_t B0 = (size_t)t1.z;
     // lane's four columns c0..c0+3 sit in 32-column slab c0 / 32 of the row's scratch: [slab][block][32]
     float4* sdst = p.hubS + B0 * p.sld + ((size_t)(cc >> 5) * nblk_row + b_first) * 32 + (cc & 31);
-    float4* tdst = p.hubT + (B0 + b_first) * 8 * p.ntail4 + (col_blocked ? 0 : (cc - p.limit) >> 2);
+    // sequential-regime scratch of the row: [column][8 * nblk_row] floats; this lane's first column, this segment
+    float* tdst = reinterpret_cast<float*>(p.hubT) + B0 * 32 * p.ntail4 +
+                  (size_t)(col_blocked ? 0 : cc - p.limit) * nblk_row * 8 + (size_t)b_first * 8;
     float2* wdst = p.hubW + B0 + b_first;
     const int* __restrict__ offp = p.coloff + t0.z;
     const float* __restrict__ wp = p.w + t0.z;
@@ -447,9 +460,17 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
                 st4_hint(reinterpret_cast<float*>(o + 2), park8(w, A[0].z, A[1].z, A[2].z, A[3].z, A[4].z, A[5].z, A[6].z, A[7].z), keep);
                 st4_hint(reinterpret_cast<float*>(o + 3), park8(w, A[0].w, A[1].w, A[2].w, A[3].w, A[4].w, A[5].w, A[6].w, A[7].w), keep);
             } else {
-                float4* o = tdst + (size_t)cb * 8 * p.ntail4;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i * p.ntail4] = A[i];
+                // sequential regime: every column's values contiguous over the row's neighbours
+                float* o = tdst + (size_t)cb * 8;
+                const size_t cp = (size_t)nblk_row * 8;
+                *reinterpret_cast<float4*>(o) = make_float4(A[0].x, A[1].x, A[2].x, A[3].x);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(A[4].x, A[5].x, A[6].x, A[7].x);
+                *reinterpret_cast<float4*>(o + cp) = make_float4(A[0].y, A[1].y, A[2].y, A[3].y);
+                *reinterpret_cast<float4*>(o + cp + 4) = make_float4(A[4].y, A[5].y, A[6].y, A[7].y);
+                *reinterpret_cast<float4*>(o + 2 * cp) = make_float4(A[0].z, A[1].z, A[2].z, A[3].z);
+                *reinterpret_cast<float4*>(o + 2 * cp + 4) = make_float4(A[4].z, A[5].z, A[6].z, A[7].z);
+                *reinterpret_cast<float4*>(o + 3 * cp) = make_float4(A[0].w, A[1].w, A[2].w, A[3].w);
+                *reinterpret_cast<float4*>(o + 3 * cp + 4) = make_float4(A[4].w, A[5].w, A[6].w, A[7].w);
             }
         }
         if (slab == 0 && lane == 0) wdst[cb] = make_float2(w[4], w[6]);
@@ -457,13 +478,25 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
     __threadfence();
     __syncwarp();
-    if (lane == 0) atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
+    if (lane == 0) {
+        const int old = atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
+        if (p.dbg && (t1.y >> kTaskHubShift) < 2 && old + 1 == ((nblk_row + 15) / 16) * p.nslab) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            printf("[dbg] hub %d last segment parked at %llu (block %d)\n", t1.y >> kTaskHubShift, t, blockIdx.x);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        printf("[dbg] rows block %d start %llu\n", blockIdx.x, t);
+    }
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     int2* meta = reinterpret_cast<int2*>(mine);
     float* scratch = reinterpret_cast<float*>(meta + kMetaRing + 8);
@@ -483,15 +516,23 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
 // hub chain: one warp per (hub row, 32 columns below `limit`), plus one warp per hub row for the
 // sequential-regime columns.  Runs after k_sweep_rows (same stream).
 // ------------------------------------------------------------------------------------------
+// CTA = two warps: warp 1 copies the row's parked stream into a shared-memory ring (cp.async, completion
+// signalled on "full" mbarriers), warp 0 runs the in-order chain out of the ring and hands the stages back
+// ("empty" mbarriers) -- the chain warp issues nothing but the loads and the dependent operations of the chain.
+//   slab s < nslab32b : 32 columns in the 8-block order, lane = column;  per block {z6, z4, X, Y} + {w4, w6}
+//   slab s = nslab32b : the <= 16 sequential-regime columns, lane = column; per neighbour z (transposed by the
+//                       segment warps: every column's values are contiguous) + w
 // kEarly: launched on a side stream BEFORE k_sweep_rows and running beside it; every CTA waits (bounded) for
 //         its row's segment warps, then chains.  The hub rows' segments are the first tasks of the row kernel,
 //         so the chains finish long before the ordinary rows do and cost the sweep nothing.
 // !kEarly: launched after both; chains whatever the early pass did not (it timed out: kernels serialised by a
 //         profiler, or the device too busy to co-schedule), and resets the flags for the next sweep.
 template <bool kEarly>
-__global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
+__global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x;
+    __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
+    __shared__ int s_done;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = p.nslab32b + (p.ntail4 > 0 ? 1 : 0);
     const int hr = blockIdx.x / per, s = blockIdx.x - hr * per;
     const bool stopped = p.st != nullptr && p.st->stop;
@@ -504,6 +545,7 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
         const volatile int* cnt = p.hub_cnt + hr;
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        t1 = t0;
         bool ready = false;
         for (;;) {
             if (*cnt >= expect) { ready = true; break; }
@@ -511,151 +553,188 @@ __global__ void __launch_bounds__(32) k_hub_chain(SweepParams p) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > kChainSpinNs) break;
         }
+        ready = __syncthreads_and(ready);              // both warps agree
+        if (p.dbg && hr < 2 && threadIdx.x == 0) printf("[dbg] chain hr %d slab %d start %llu ready %llu (%d)\n", hr, s, t0, t1, (int)ready);
         if (!ready) return;                            // the late pass does it
         __threadfence();                               // acquire: the parked blocks of every segment warp
-        asm volatile("fence.proxy.async;" ::: "memory");   // ... also for the TMA reads below
     } else {
-        const int done = p.hub_done[blockIdx.x];
-        __syncwarp();
-        if (lane == 0) { p.hub_done[blockIdx.x] = 0; if (s == 0) p.hub_cnt[hr] = 0; }   // also when stopped
-        if (done || stopped) return;
+        if (threadIdx.x == 0) {
+            s_done = p.hub_done[blockIdx.x];
+            p.hub_done[blockIdx.x] = 0;                // also when stopped
+            if (s == 0) p.hub_cnt[hr] = 0;
+        }
+        __syncthreads();
+        if (s_done || stopped) return;
     }
     const size_t B0 = (size_t)__ldg(p.hub_blk0 + hr);
     const int nleft = k - nblk * 8;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const bool blocked = s < p.nslab32b;
+    const int nt = p.ntail4, ntc = p.ld - p.limit;                  // sequential-regime float4 pieces / columns
+    const int nnb = nblk * 8;
+    const int ngroups = blocked ? (nblk + kChainGroup - 1) / kChainGroup : (nnb + kTailGroup - 1) / kTailGroup;
+    float4* ringS = reinterpret_cast<float4*>(smem);                                  // blocked: [stage][16][32]
+    float2* wq = reinterpret_cast<float2*>(ringS + kChainGroups * kChainGroup * 32);  //          [stage][16]
+    // sequential regime: stage = [ntc columns][kTailPitch] z | [32] w; as many stages as the shared memory holds
+    float* zr = reinterpret_cast<float*>(smem);
+    const int tstride = ntc * kTailPitch + kTailGroup;
+    const int tstages = min(kMaxStages, (int)(kChainSmemBytes / sizeof(float)) / max(tstride, 1));
+
+    if (warp == 1) {
+        // ---------------- producer ----------------
+        if (blocked) {
+            const float4* src = p.hubS + B0 * p.sld + (size_t)s * nblk * 32 + lane;   // contiguous 512 B per block
+            const float2* wsrc = p.hubW + B0;
+            const unsigned ring_sa = smem_u32(ringS) + lane * 16;
+            const unsigned wq_sa = smem_u32(wq) + (lane & 15) * 8;
+            for (int g = 0; g < ngroups; ++g) {
+                const int st = g % kChainGroups;
+                if (g >= kChainGroups) mbar_wait(empty + st, (unsigned)(g / kChainGroups - 1) & 1u);
+                const int b0 = g * kChainGroup;
+                const unsigned dst = ring_sa + (unsigned)st * (kChainGroup * 512);
+#pragma unroll
+                for (int j = 0; j < kChainGroup; ++j)
+                    if (b0 + j < nblk) cp_async16_sa(dst + j * 512, src + (size_t)(b0 + j) * 32);
+                if (lane < kChainGroup && b0 + lane < nblk) cp_async8_sa(wq_sa + (unsigned)st * (kChainGroup * 8), wsrc + b0 + lane);
+                cp_async_arrive(full + st);
+            }
+        } else {
+            const float* tsrc = reinterpret_cast<const float*>(p.hubT) + B0 * 32 * nt;   // [column][nnb]
+            for (int g = 0; g < ngroups; ++g) {
+                const int st = g % tstages;
+                if (g >= tstages) mbar_wait(empty + st, (unsigned)(g / tstages - 1) & 1u);
+                const int i0 = g * kTailGroup;
+                const int cnt = min(kTailGroup, nnb - i0);            // multiple of 8
+                // 16-byte pieces: column q / 8, neighbours 4 * (q % 8) .. + 3
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int q = lane + 32 * t, c = q >> 3, pc = (q & 7) * 4;
+                    if (c < ntc && pc < cnt)
+                        cp_async16_sa(smem_u32(zr + (size_t)st * tstride + c * kTailPitch + pc), tsrc + (size_t)c * nnb + i0 + pc);
+                }
+                if (lane < cnt) cp_async4_sa(smem_u32(zr + (size_t)st * tstride + ntc * kTailPitch + lane), p.w + a + i0 + lane);
+                cp_async_arrive(full + st);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer: the chain ----------------
     float acc = 0.0f;
-    int col;
-    bool act;
-    if (s < p.nslab32b) {
+    const int col = blocked ? s * 32 + lane : p.limit + lane;
+    const bool act = blocked ? col < p.limit : col < p.ld;
+    const int ccol = act ? col : (blocked ? 0 : p.limit);
+    // the k mod 8 leftovers: gathered now, added after the blocks
+    float lz[7], lw[7];
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {
+        lz[o] = 0.0f; lw[o] = 0.0f;
+        if (o < nleft) {
+            lw[o] = __ldg(p.w + a + nnb + o);
+            lz[o] = __ldg(p.Zc + (size_t)__ldg(p.coloff + a + nnb + o) * 4 + ccol);
+        }
+    }
+    if (blocked) {
         // ---- 8-block order: a = fma(w6,z6,a); a = fma(w4,z4,a); a += X; a += Y per block ----
-        col = s * 32 + lane;
-        act = col < p.limit;
-        const int ccol = act ? col : 0;
-        // The row's parked stream for this slab is contiguous: 512 bytes per block.  Lane 0 moves it with TMA
-        // bulk copies (one instruction per 8 KB chunk of 16 blocks, completion on an mbarrier), eight chunks in
-        // flight; the warp only runs the chain: two shared-memory loads and four dependent operations per block.
-        float4* ringS = reinterpret_cast<float4*>(smem);                                  // [stages][16][32]
-        float2* wq = reinterpret_cast<float2*>(ringS + kChainGroups * kChainGroup * 32);  // [stages][16]
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(wq + kChainGroups * kChainGroup);
-        const float4* src = p.hubS + B0 * p.sld + (size_t)s * nblk * 32;
-        const float2* wsrc = p.hubW + B0;
-        const int ngroups = (nblk + kChainGroup - 1) / kChainGroup;
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < kChainGroups; ++i) mbar_init(bars + i, 1);
-            fence_mbar_init();
-        }
-        __syncwarp();
-        auto issue = [&](int g) {   // lane 0 only
-            if (g < ngroups) {
-                const int b0 = g * kChainGroup, st = g % kChainGroups;
-                const int cnt = min(kChainGroup, nblk - b0);
-                const unsigned wbytes = (unsigned)((cnt + 1) & ~1) * 8;   // 16-byte multiple; rows are padded to even blocks
-                mbar_expect_tx(bars + st, (unsigned)cnt * 512 + wbytes);
-                bulk_g2s(ringS + (size_t)st * kChainGroup * 32, src + (size_t)b0 * 32, (unsigned)cnt * 512, bars + st);
-                bulk_g2s(wq + st * kChainGroup, wsrc + b0, wbytes, bars + st);
-            }
-        };
-        if (lane == 0) {
-#pragma unroll
-            for (int g = 0; g < kChainGroups; ++g) issue(g);
-        }
-        // the k mod 8 leftovers: gathered now, added after the blocks
-        float lz[7], lw[7];
-#pragma unroll
-        for (int o = 0; o < 7; ++o) {
-            lz[o] = 0.0f; lw[o] = 0.0f;
-            if (o < nleft) {
-                lw[o] = __ldg(p.w + a + nblk * 8 + o);
-                lz[o] = __ldg(p.Zc + (size_t)__ldg(p.coloff + a + nblk * 8 + o) * 4 + ccol);
-            }
-        }
-        for (int g = 0; g < ngroups; ++g) {
-            const int st = g % kChainGroups;
-            mbar_wait(bars + st, (unsigned)(g / kChainGroups) & 1u);
+        // Register double buffer: the shared-memory loads of stage g + 1 are issued before the 64 dependent
+        // operations of stage g, so the chain itself never waits for the ring.
+        float4 v[kChainGroup], vn[kChainGroup];
+        float2 wv[kChainGroup], wn[kChainGroup];
+        auto fetch = [&](int g, float4 (&dv)[kChainGroup], float2 (&dw)[kChainGroup]) {
+            const bool live = g < ngroups;   // past the end: no wait, the loads below return stale data nobody uses
+            const int st = g % kChainGroups; //   (they stay unconditional: loads under a branch would be waited for at its join)
+            if (live) mbar_wait(full + st, (unsigned)(g / kChainGroups) & 1u);
             const float4* rs = ringS + (size_t)st * kChainGroup * 32 + lane;
             const float2* ws = wq + st * kChainGroup;
+#pragma unroll
+            for (int j = 0; j < kChainGroup; ++j) { dv[j] = rs[j * 32]; dw[j] = ws[j]; }   // past the row's end: stale, unused
+            __syncwarp();                    // every lane has read the stage
+            if (live && lane == 0) mbar_arrive(empty + st);
+        };
+        auto chain = [&](int g, const float4 (&dv)[kChainGroup], const float2 (&dw)[kChainGroup]) {
             const int cnt = min(kChainGroup, nblk - g * kChainGroup);
             if (cnt == kChainGroup) {
-                float4 v[kChainGroup];
-                float2 wv[kChainGroup];
-#pragma unroll
-                for (int j = 0; j < kChainGroup; ++j) { v[j] = rs[j * 32]; wv[j] = ws[j]; }
 #pragma unroll
                 for (int j = 0; j < kChainGroup; ++j) {
-                    acc = ffma(wv[j].y, v[j].x, acc);
-                    acc = ffma(wv[j].x, v[j].y, acc);
-                    acc = fadd(acc, v[j].z);
-                    acc = fadd(acc, v[j].w);
+                    acc = ffma(dw[j].y, dv[j].x, acc);
+                    acc = ffma(dw[j].x, dv[j].y, acc);
+                    acc = fadd(acc, dv[j].z);
+                    acc = fadd(acc, dv[j].w);
                 }
             } else {
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 v = rs[j * 32];
-                    const float2 wv = ws[j];
-                    acc = ffma(wv.y, v.x, acc);
-                    acc = ffma(wv.x, v.y, acc);
-                    acc = fadd(acc, v.z);
-                    acc = fadd(acc, v.w);
-                }
-            }
-            __syncwarp();                    // every lane has read this stage: refill it
-            if (lane == 0) issue(g + kChainGroups);
-        }
 #pragma unroll
-        for (int o = 0; o < 7; ++o)
-            if (o < nleft) acc = ffma(lw[o], lz[o], acc);
-    } else {
-        // ---- sequential regime: a = fma(w_i, z_i, a) over all neighbours ----
-        const int nt = p.ntail4;
-        col = p.limit + lane;
-        act = col < p.ld;
-        const int ccol = act ? col : p.limit;
-        float* zr = reinterpret_cast<float*>(smem);                                  // [groups][32][nt * 4]
-        float* wr = zr + (size_t)kTailGroups * kTailGroup * 16;                      // [groups][32]
-        const int nnb = nblk * 8;
-        const int ngroups = (nnb + kTailGroup - 1) / kTailGroup;
-        const float4* src = p.hubT + B0 * 8 * nt;
-        auto issue = [&](int g) {
-            if (g < ngroups) {
-                const int i0 = g * kTailGroup;
-                const int cnt = min(kTailGroup, nnb - i0);
-                const unsigned zdst = smem_u32(zr + (size_t)(g % kTailGroups) * kTailGroup * 16);
-                for (int q = lane; q < cnt * nt; q += 32) cp_async16_sa(zdst + q * 16, src + (size_t)i0 * nt + q);
-                if (lane < cnt) cp_async4_sa(smem_u32(wr + (g % kTailGroups) * kTailGroup + lane), p.w + a + i0 + lane);
+                for (int j = 0; j < kChainGroup; ++j)
+                    if (j < cnt) {
+                        acc = ffma(dw[j].y, dv[j].x, acc);
+                        acc = ffma(dw[j].x, dv[j].y, acc);
+                        acc = fadd(acc, dv[j].z);
+                        acc = fadd(acc, dv[j].w);
+                    }
             }
-            cp_async_commit();
         };
-#pragma unroll
-        for (int g = 0; g < kTailGroups - 1; ++g) issue(g);
-        float lz[7], lw[7];
-#pragma unroll
-        for (int o = 0; o < 7; ++o) {
-            lz[o] = 0.0f; lw[o] = 0.0f;
-            if (o < nleft) {
-                lw[o] = __ldg(p.w + a + nnb + o);
-                lz[o] = __ldg(p.Zc + (size_t)__ldg(p.coloff + a + nnb + o) * 4 + ccol);
-            }
+        fetch(0, v, wv);
+        for (int g = 0; g < ngroups; g += 2) {
+            fetch(g + 1, vn, wn);
+            chain(g, v, wv);
+            if (g + 1 >= ngroups) break;
+            fetch(g + 2, v, wv);
+            chain(g + 1, vn, wn);
         }
-        const int cl = min(lane, nt * 4 - 1);
-        for (int g = 0; g < ngroups; ++g) {
-            issue(g + kTailGroups - 1);
-            cp_async_wait<kTailGroups - 1>();
-            __syncwarp();
-            const float* zs = zr + (size_t)(g % kTailGroups) * kTailGroup * 16 + cl;
-            const float* ws = wr + (g % kTailGroups) * kTailGroup;
-            const int cnt = min(kTailGroup, nnb - g * kTailGroup);
-            for (int j = 0; j < cnt; ++j) acc = ffma(ws[j], zs[j * nt * 4], acc);
-            __syncwarp();
-        }
-        cp_async_wait<0>();
+    } else {
+        // ---- sequential regime: a = fma(w_i, z_i, a) over all neighbours (same register double buffer) ----
+        const int cl = min(lane, ntc - 1);
+        float4 zv[kTailGroup / 4], zn[kTailGroup / 4], wv[kTailGroup / 4], wn[kTailGroup / 4];
+        auto fetch = [&](int g, float4 (&dz)[kTailGroup / 4], float4 (&dw)[kTailGroup / 4]) {
+            const bool live = g < ngroups;
+            const int st = g % tstages;
+            if (live) mbar_wait(full + st, (unsigned)(g / tstages) & 1u);
+            const float4* zs = reinterpret_cast<const float4*>(zr + (size_t)st * tstride + cl * kTailPitch);
+            const float4* ws = reinterpret_cast<const float4*>(zr + (size_t)st * tstride + ntc * kTailPitch);
 #pragma unroll
-        for (int o = 0; o < 7; ++o)
-            if (o < nleft) acc = ffma(lw[o], lz[o], acc);
+            for (int j = 0; j < kTailGroup / 4; ++j) { dz[j] = zs[j]; dw[j] = ws[j]; }
+            __syncwarp();
+            if (live && lane == 0) mbar_arrive(empty + st);
+        };
+        auto chain = [&](int g, const float4 (&dz)[kTailGroup / 4], const float4 (&dw)[kTailGroup / 4]) {
+            const int cnt = min(kTailGroup, nnb - g * kTailGroup);   // multiple of 8
+#pragma unroll
+            for (int j = 0; j < kTailGroup / 4; ++j)
+                if (cnt == kTailGroup || 4 * j < cnt) {
+                    acc = ffma(dw[j].x, dz[j].x, acc);
+                    acc = ffma(dw[j].y, dz[j].y, acc);
+                    acc = ffma(dw[j].z, dz[j].z, acc);
+                    acc = ffma(dw[j].w, dz[j].w, acc);
+                }
+        };
+        fetch(0, zv, wv);
+        for (int g = 0; g < ngroups; g += 2) {
+            fetch(g + 1, zn, wn);
+            chain(g, zv, wv);
+            if (g + 1 >= ngroups) break;
+            fetch(g + 2, zv, wv);
+            chain(g + 1, zn, wn);
+        }
     }
+#pragma unroll
+    for (int o = 0; o < 7; ++o)
+        if (o < nleft) acc = ffma(lw[o], lz[o], acc);
     if (act) {
         const size_t off = (size_t)row * p.ld + col;
-        p.Zn[off] = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
+        const float v = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
+        p.Zn[off] = v;
+        for (int j = 0; j < p.n_remote; ++j) p.peer[j][off] = v;
     }
     if (kEarly && lane == 0) p.hub_done[blockIdx.x] = 1;
+    if (kEarly && p.dbg && hr < 2 && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        printf("[dbg] chain hr %d slab %d end %llu blocks %d\n", hr, s, t, nblk);
+    }
 }
 
 // Fused mode: the level-0 partial of every group that was not swept by a single warp (it holds

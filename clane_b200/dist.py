@@ -1,14 +1,24 @@
-"""Row-partitioned multi-GPU sweep: one process per GPU, NCCL over NVLink.
+"""Row-partitioned multi-GPU sweep: one process per GPU of one NVLink domain.
 
 Nodes are partitioned by contiguous id range; every rank keeps the full CSR and a full replica
-of Z (out-neighbours span all ranks), sweeps its own rows, and the ranks exchange their Znext
-slices with one all-gather per sweep.  The three global scalars stay bit-identical on every rank:
+of Z (out-neighbours span all ranks) and sweeps its own rows.  The exchange is fused into the
+sweep: the two Z ping-pong buffers live in peer-mapped symmetric memory, and the sweep kernel
+stores every finished row of Znext to ALL ranks' buffers (clane_plan_set_peers) -- NVLink writes
+issued row by row from inside the kernel, overlapping the gathers, no collective on the data
+path.  Where symmetric memory is unavailable the slices are exchanged with one NCCL all-gather
+per sweep instead.  The three global scalars stay bit-identical on every rank:
 
-  * L1 change per sweep (embedder.py:94): after the all-gather each rank reduces a disjoint range
-    of the ATen cascade's level-1 nodes over the full [N*d] array (clane_l1_partial), the ranks
-    all-reduce(SUM) the node slots -- every slot is written by exactly one rank and is +0
-    elsewhere, so the sum is exact -- and each rank finishes levels 2-3 and the patience state
-    machine itself (clane_l1_finish).  Patience is replicated, never broadcast.
+  * L1 change per sweep (embedder.py:94): the ATen cascade's level-1 nodes are independent, so
+    each rank reduces the nodes of its OWN rows right after its sweep, from local data only (the
+    row ranges are cut at multiples of lcm(node, d) / d rows so that no node straddles two
+    ranks); the ranks all-reduce(SUM) the node slots -- every slot is written by exactly one rank
+    and is +0 elsewhere, so the sum is exact -- together with the <= 31 trailing element values,
+    and each rank finishes levels 2-3 and the patience state machine itself
+    (clane_l1_finish_values).  That all-reduce is also the only inter-rank ordering a sweep
+    needs: once it completes on a rank, every rank has finished reading Zcur and its peer
+    stores of Znext have landed.  Patience is replicated, never broadcast.  When the shape
+    cannot be cut that way (d odd, tiny n) the ranks first synchronise, then reduce balanced
+    node ranges of the full array.
   * the two Frobenius norms of build_P (similarity.py:37) are computed redundantly by every rank
     over all E*d gathered elements (each rank holds the full Z and CSR); dots and softmax only for
     the rank's own rows.
@@ -18,6 +28,7 @@ The helpers at the top are pure host logic (tested under gloo on CPU); ShardedSw
 from __future__ import annotations
 
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -28,17 +39,48 @@ from . import _lib
 ROW_ALIGN = 8   # slices are cut at multiples of the sweep's row-group size
 
 
-def rows_per_rank(n: int, world: int) -> int:
-    """Equal slice length (a multiple of ROW_ALIGN) such that world * length >= n."""
+def node_align_rows(n: int, d: int) -> int:
+    """Rows per alignment unit such that a cut at a multiple of it never splits a level-1 node of
+    the ATen cascade over the flattened [n*d] array: lcm(node elements, d) / d."""
+    ni = (n * d) // 32
+    p = max(4, ((ni - 1).bit_length() if ni > 1 else 0) // 4)
+    node_elems = 32 * (1 << p) * (1 << p)
+    return node_elems // math.gcd(node_elems, d)
+
+
+def rows_per_rank(n: int, world: int, align: int = ROW_ALIGN) -> int:
+    """Equal slice length (a multiple of `align`) such that world * length >= n."""
     per = -(-n // world)
-    return -(-per // ROW_ALIGN) * ROW_ALIGN
+    return -(-per // align) * align
 
 
-def row_range(n: int, world: int, rank: int) -> tuple[int, int]:
+def aligned_rows_per_rank(n: int, d: int, world: int):
+    """Slice length cut at level-1 node boundaries, or None when the nodes are too coarse for this
+    shape (fewer than 4 alignment units per rank: the cut would unbalance the ranks)."""
+    a = node_align_rows(n, d)
+    if a % ROW_ALIGN or a * 4 * world > n:
+        return None
+    return rows_per_rank(n, world, a)
+
+
+def row_range(n: int, world: int, rank: int, per: int | None = None) -> tuple[int, int]:
     """Rows [lo, hi) owned by `rank`; trailing ranks may own fewer (or no) rows."""
-    per = rows_per_rank(n, world)
+    per = rows_per_rank(n, world) if per is None else per
     lo = min(rank * per, n)
     return lo, min(lo + per, n)
+
+
+def own_node_range(n: int, d: int, n_nodes: int, lo: int, hi: int) -> tuple[int, int]:
+    """Level-1 nodes covered by rows [lo, hi) of a node-aligned cut (the last rank takes the
+    trailing partial node)."""
+    ni = (n * d) // 32
+    p = max(4, ((ni - 1).bit_length() if ni > 1 else 0) // 4)
+    node_elems = 32 * (1 << p) * (1 << p)
+    if lo >= hi:
+        return n_nodes if lo >= n else 0, n_nodes if lo >= n else 0
+    nlo = (lo * d) // node_elems
+    nhi = n_nodes if hi >= n else (hi * d) // node_elems
+    return min(nlo, n_nodes), min(nhi, n_nodes)
 
 
 def node_range(n_nodes: int, world: int, rank: int) -> tuple[int, int]:
@@ -56,7 +98,7 @@ def gather_rows(local: torch.Tensor, full: torch.Tensor, group=None) -> None:
 class ShardedSweeper:
     """Sweeps of one propagate() call over this rank's rows, with the per-sweep exchange."""
 
-    def __init__(self, graph, similarity, gamma: float, tol: int = 10, max_sweeps: int = 0):
+    def __init__(self, graph, similarity, gamma: float, tol: int = 10, max_sweeps: int = 0, exchange: str = "auto"):
         self.g, self.sim, self.gamma = graph, similarity, float(np.float32(gamma))
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.dev = _lib.require_cuda()
@@ -64,8 +106,10 @@ class ShardedSweeper:
         n, e, d = graph._n, graph._nnz, int(graph.X.shape[1])
         ld = int(L.clane_padded_ld(d))
         self.n, self.e, self.d, self.ld = n, e, d, ld
-        self.per = rows_per_rank(n, self.world)
-        self.lo, self.hi = row_range(n, self.world, self.rank)
+        aligned = aligned_rows_per_rank(n, d, self.world)
+        self.aligned = aligned is not None
+        self.per = aligned if self.aligned else rows_per_rank(n, self.world)
+        self.lo, self.hi = row_range(n, self.world, self.rank, self.per)
         npad = self.per * self.world
         dev = self.dev
         self.rowptr = torch.from_numpy(graph._rowptr).to(dev)
@@ -73,7 +117,8 @@ class ShardedSweeper:
         self.erow = torch.zeros(max(e, 1), dtype=torch.int32, device=dev)
         self.X = torch.zeros([npad, ld], dtype=torch.float32, device=dev)
         self.X[:n, :d] = graph.X.to(dev)
-        self.Z = [self.X.clone(), self.X.clone()]
+        self.plan = _lib.Plan(n, e, d, graph._rowptr, self.lo, self.hi, 0)
+        self.exchange = self._alloc_z(npad, ld, exchange)
         self.cur = 0
         self.w = torch.zeros(max(e, 1), dtype=torch.float32, device=dev)
         self.norms2 = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -82,17 +127,48 @@ class ShardedSweeper:
         self.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.log_cap = 1 << 16
         self.log = torch.zeros(self.log_cap, dtype=torch.float32, device=dev)
-        self.plan = _lib.Plan(n, e, d, graph._rowptr, self.lo, self.hi, 0)
         nodes = ctypes.c_int64()
         _lib.check(L.clane_cascade_shape(n * d, ctypes.byref(nodes), None))
         self.n1 = int(nodes.value)
-        self.nlo, self.nhi = node_range(self.n1, self.world, self.rank)
-        self.p1 = torch.zeros((self.n1 + 2) * 32, dtype=torch.float32, device=dev)
+        if self.aligned:
+            self.nlo, self.nhi = own_node_range(n, d, self.n1, self.lo, self.hi)
+        else:
+            self.nlo, self.nhi = node_range(self.n1, self.world, self.rank)
+        # level-1 slots [n1 + 2][32] + the trailing element values [32]: one all-reduce
+        self.p1 = torch.zeros((self.n1 + 3) * 32, dtype=torch.float32, device=dev)
+        self.sync_token = torch.zeros(1, dtype=torch.float32, device=dev)
         s = _lib.stream_handle()
         _lib.check(L.clane_edge_rows(self.rowptr.data_ptr(), n, e, self.erow.data_ptr(), s))
         self.tol, self.max_sweeps = tol, max_sweeps
+        self.timing, self.phase_ms = False, {}     # measurement aid: CUDA-event brackets around the phases of a sweep
         self.build_p()
         _lib.check(L.clane_patience_reset(self.state.data_ptr(), tol, max_sweeps, s))
+
+    def _alloc_z(self, npad: int, ld: int, exchange: str) -> str:
+        """The two Z buffers: peer-mapped symmetric memory (exchange fused into the sweep kernel) when
+        available, plain device memory + NCCL all-gather otherwise."""
+        L = _lib.lib()
+        self.symm = None
+        if exchange in ("auto", "p2p") and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                bufs = [symm_mem.empty((npad, ld), dtype=torch.float32, device=self.dev) for _ in range(2)]
+                hdls = [symm_mem.rendezvous(b, dist.group.WORLD) for b in bufs]
+                ptrs = [(ctypes.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in hdls]
+                for b in bufs:
+                    b.copy_(self.X)
+                torch.cuda.synchronize()
+                dist.barrier()
+                _lib.check(L.clane_plan_set_peers(self.plan.handle, self.world, self.rank, ptrs[0], ptrs[1]),
+                           "clane_plan_set_peers")
+                self.Z, self.symm = bufs, hdls
+                return "p2p"
+            except Exception as exc:       # no VMM / fabric handles on this box: fall back to NCCL
+                if exchange == "p2p":
+                    raise
+                self.symm_error = repr(exc)
+        self.Z = [self.X.clone(), self.X.clone()]
+        return "nccl" if self.world > 1 else "none"
 
     def build_p(self) -> None:
         L = _lib.lib()
@@ -101,26 +177,55 @@ class ShardedSweeper:
                                           self.norms2.data_ptr(), _lib.stream_handle()), "clane_build_p_cosine")
 
     def sweep(self, with_l1: bool = True) -> int:
-        """One sweep: own rows, all-gather of the new slices, exact L1 + patience.  Returns the
-        number of kernels this rank launched."""
+        """One sweep: own rows (stored to every rank's Znext when the exchange is fused), exact L1 +
+        patience.  Returns the number of kernels this rank launched."""
         L = _lib.lib()
         s = _lib.stream_handle()
         zc, zn = self.Z[self.cur], self.Z[self.cur ^ 1]
+        marks = [] if self.timing else None
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         _lib.check(L.clane_sweep(self.plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
                                  self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
                    "clane_sweep")
-        launches = 1 + (1 if self.plan.n_hub_rows else 0)
-        lo = self.rank * self.per
-        gather_rows(zn[lo:lo + self.per], zn)
+        mark("sweep")
+        launches = 1 + (2 if self.plan.n_hub_rows else 0)
+        if self.exchange == "nccl":
+            lo = self.rank * self.per
+            gather_rows(zn[lo:lo + self.per], zn)
+            mark("all_gather")
+        vals = self.p1[(self.n1 + 2) * 32:]
         if with_l1:
+            if self.exchange == "p2p" and not self.aligned:
+                dist.all_reduce(self.sync_token)       # every rank's rows have landed before the full-array pass
             self.p1.zero_()
             _lib.check(L.clane_l1_partial(self.plan.handle, zn.data_ptr(), zc.data_ptr(), self.nlo, self.nhi,
                                           self.p1.data_ptr(), s), "clane_l1_partial")
+            if self.hi == self.n and self.lo < self.hi or (self.n == 0 and self.rank == 0):
+                _lib.check(L.clane_l1_tail_values(self.plan.handle, zn.data_ptr(), zc.data_ptr(), vals.data_ptr(), s),
+                           "clane_l1_tail_values")
+                launches += 1
+            mark("l1_partial")
             dist.all_reduce(self.p1, op=dist.ReduceOp.SUM)
-            _lib.check(L.clane_l1_finish(self.plan.handle, zn.data_ptr(), zc.data_ptr(), self.p1.data_ptr(),
-                                         self.amount.data_ptr(), 0, 0, 0, s), "clane_l1_finish")
+            mark("all_reduce")
+            _lib.check(L.clane_l1_finish_values(self.plan.handle, self.p1.data_ptr(), vals.data_ptr(),
+                                                self.amount.data_ptr(), 0, 0, 0, s), "clane_l1_finish_values")
+            mark("finish")
             launches += 3
+        elif self.exchange == "p2p":
+            dist.all_reduce(self.sync_token)           # order the ranks between sweeps
         self.cur ^= 1
+        if marks is not None:
+            marks[-1][1].synchronize()
+            for (_, a), (name, b) in zip(marks, marks[1:]):
+                self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
+            self.phase_ms["sweeps"] = self.phase_ms.get("sweeps", 0) + 1
         return launches
 
     def last_amount(self) -> float:

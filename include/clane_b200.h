@@ -86,8 +86,9 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
  *     (embedder.py:88-89: such rows are never updated);
  *   - the control flow of the sweep kernel (batch sizes, row ends, window refills) is
  *     precomputed into 32-bit batch descriptors: see clane_sweep_program.
- * hub_threshold <= 0 selects the default: E/4096 rounded up to a multiple of 8, clamped to
- * [256, 16384] (a row is an in-order chain on one warp; this bounds it to a few percent of a sweep).
+ * hub_threshold <= 0 selects the default: (edges of rows [row_lo, row_hi)) / 4096 rounded up to a
+ * multiple of 8, clamped to [256, 16384] (a row is an in-order chain on one warp; this bounds it
+ * to a few percent of a sweep).
  * h_rowptr may be NULL for a scores-only plan (clane_scores_cosine / clane_l1_*). */
 typedef struct clane_plan clane_plan;
 /* The schedule alone, on the host (what clane_plan_create uploads); every output has capacity
@@ -183,6 +184,24 @@ int clane_l1_partial(clane_plan* plan, const float* d_Za, const float* d_Zb, int
                      float* d_p1, clane_stream_t s);
 int clane_l1_finish(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_p1, float* d_out,
                     clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
+
+/* The <= 31 elements of |Za - Zb| that clane_l1_finish reads itself (everything past the last
+ * complete 32-element cascade row; the whole array when n*d < 8) -> d_vals[32] (rest +0), and a
+ * finish that takes them from that buffer instead of from Za / Zb: a row-partitioned run
+ * all-reduces the values with the level-1 slots, so that the finish never reads rows a faster
+ * rank may already be overwriting with its next sweep. */
+int clane_l1_tail_values(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_vals, clane_stream_t s);
+int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, float* d_out,
+                           clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
+
+/* Row-partitioned run on n_peers GPUs of one NVLink domain: the device addresses
+ * of every rank's two Z ping-pong buffers (peer-mapped, e.g. CUDA VMM / torch symmetric memory;
+ * entry self_rank = this rank's own buffers).  From then on clane_sweep stores every finished
+ * row of Znext to all ranks' buffers from inside the sweep kernel -- the exchange overlaps the
+ * sweep row by row and needs no collective; the caller only has to order the ranks between
+ * sweeps (the all-reduce of the L1 slots does).  n_peers = 0 turns it off. */
+int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
+                         const uint64_t* h_ptrs_b);
 
 /* Measurement aid: when enabled, clane_sweep brackets its kernels with CUDA events on the
  * streams they are launched on; clane_plan_profile_read waits for the last sweep and returns

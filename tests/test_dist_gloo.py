@@ -36,6 +36,35 @@ def test_partition_geometry():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_node_aligned_partition():
+    """Cuts at multiples of lcm(level-1 node, d) / d rows: every rank's rows cover whole level-1 nodes of the
+    cascade over [n*d], the ranks' node ranges tile [0, n1_nodes), and shapes whose nodes are too coarse fall
+    back (None)."""
+    import ctypes
+    from clane_b200 import _lib
+    L = _lib.lib()
+    for n, d, world, want in [(169343, 128, 2, True), (169343, 128, 8, True), (2449029, 100, 8, True), (19717, 500, 2, True),
+                              (2708, 1433, 2, False), (34, 2, 2, False), (50803, 128, 4, True)]:
+        per = cdist.aligned_rows_per_rank(n, d, world)
+        assert (per is not None) == want, (n, d, world, per)
+        if per is None:
+            continue
+        nodes, elems = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(L.clane_cascade_shape(n * d, ctypes.byref(nodes), ctypes.byref(elems)))
+        assert (cdist.node_align_rows(n, d) * d) % elems.value == 0 and per % cdist.node_align_rows(n, d) == 0
+        assert per % cdist.ROW_ALIGN == 0 and per * world >= n
+        prev = 0
+        for r in range(world):
+            lo, hi = cdist.row_range(n, world, r, per)
+            nlo, nhi = cdist.own_node_range(n, d, nodes.value, lo, hi)
+            assert nlo == prev and nlo <= nhi
+            if hi < n:
+                assert (hi * d) % elems.value == 0 and nhi == hi * d // elems.value   # no node straddles the cut
+            prev = nhi
+        assert prev == nodes.value
+        assert max(cdist.row_range(n, world, r, per)[1] - cdist.row_range(n, world, r, per)[0] for r in range(world)) <= 1.1 * n / world + per - n // world
+
+
 def _worker(rank, world, port, n, ld, nodes, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

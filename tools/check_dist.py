@@ -13,11 +13,14 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok = True
-for shape, scale in (("arxiv", 0.3), ("products", 0.01), ("pubmed", 1.0)):
+for shape, scale in (("arxiv", 0.3), ("products", 0.01), ("pubmed", 1.0), ("cora", 1.0)):
     n, src, dst, X = synth.make_graph(shape, seed=0, scale=scale)
     g = Graph.from_arrays(n, src, dst, X)
     sim = similarity.CosineSimilarity()
-    sw = cdist.ShardedSweeper(g, sim, 0.76)
+    sw = cdist.ShardedSweeper(g, sim, 0.76, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
+    if rank == 0:
+        print(f"exchange={sw.exchange} aligned={sw.aligned} rows/rank={sw.per}" +
+              (f" (symmetric memory unavailable: {sw.symm_error})" if hasattr(sw, "symm_error") else ""), flush=True)
     amounts = []
     for _ in range(4):
         sw.sweep(True)
