@@ -127,11 +127,13 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_tasks); cudaFree(plan->d_descs); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
-    cudaFree(plan->d_hub_blk0); cudaFree(plan->d_hubS); cudaFree(plan->d_hubW); cudaFree(plan->d_hubT);
+    cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubW); cudaFree(plan->d_hubT);
     cudaFree(plan->d_hub_cnt); cudaFree(plan->d_hub_done);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+    if (plan->ev_join2) cudaEventDestroy(plan->ev_join2);
     if (plan->side) cudaStreamDestroy(plan->side);
+    if (plan->side2) cudaStreamDestroy(plan->side2);
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
     for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int i = 0; i < 6; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
@@ -305,6 +307,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->n_spans = n_spans;
     plan->n_fix_groups = n_fix;
     plan->n_hub_rows = n_hrows;
+    plan->n_long_hub_rows = 0;
+    for (int32_t h = 0; h < n_hrows; ++h)
+        if ((h_rowptr[hrows[h] + 1] - h_rowptr[hrows[h]]) / 8 >= kLongBlocks) plan->n_long_hub_rows = h + 1;
 
     std::vector<SweepTask> tasks;
     std::vector<int32_t> descs, blk0;
@@ -317,13 +322,18 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     PLAN_CUDA(cudaMalloc(&plan->d_descs, std::max<size_t>(descs.size(), 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
-    PLAN_CUDA(cudaMalloc(&plan->d_hub_blk0, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
+    PLAN_CUDA(cudaMalloc(&plan->d_hub_info, std::max<size_t>(n_hrows, 1) * sizeof(int4)));
     if (!tasks.empty()) PLAN_CUDA(cudaMemcpy(plan->d_tasks, tasks.data(), tasks.size() * sizeof(SweepTask), cudaMemcpyHostToDevice));
     if (!descs.empty()) PLAN_CUDA(cudaMemcpy(plan->d_descs, descs.data(), descs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_fix) PLAN_CUDA(cudaMemcpy(plan->d_fix_groups, fix.data(), n_fix * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_hrows) {
         PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
-        PLAN_CUDA(cudaMemcpy(plan->d_hub_blk0, blk0.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));
+        std::vector<int4> info((size_t)n_hrows);
+        for (int32_t h = 0; h < n_hrows; ++h) {
+            const int32_t v = hrows[h];
+            info[h] = make_int4(v, h_rowptr[v], h_rowptr[v + 1] - h_rowptr[v], blk0[h]);
+        }
+        PLAN_CUDA(cudaMemcpy(plan->d_hub_info, info.data(), n_hrows * sizeof(int4), cudaMemcpyHostToDevice));
         const size_t nb = (size_t)plan->hub_blocks;
         PLAN_CUDA(cudaMalloc(&plan->d_hubS, std::max<size_t>(nb * plan->nslab32b * 32, 1) * 16));
         PLAN_CUDA(cudaMalloc(&plan->d_hubW, nb * 8));
@@ -337,8 +347,10 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
             int lo = 0, hi = 0;
             PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
+            PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side2, cudaStreamNonBlocking, hi));
             PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
             PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join2, cudaEventDisableTiming));
         }
     }
     if (plan->fuse) {

@@ -294,7 +294,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.G = plan->G; p.nslab = plan->nslab;
     p.fuse = (plan->fuse && want_l1) ? 1 : 0;
     p.P0 = plan->d_P0;
-    p.hub_rows = plan->d_hub_rows; p.hub_blk0 = plan->d_hub_blk0; p.n_hub_rows = plan->n_hub_rows;
+    p.hub_info = static_cast<const int4*>(plan->d_hub_info); p.n_hub_rows = plan->n_hub_rows;
     p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
     p.hubS = static_cast<float4*>(plan->d_hubS); p.hubW = static_cast<float2*>(plan->d_hubW);
     p.hubT = static_cast<float4*>(plan->d_hubT);
@@ -315,12 +315,24 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     const bool prof = plan->profile;
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[0], st));
     static const bool overlap = getenv("CLANE_NO_CHAIN_OVERLAP") == nullptr;
-    if (chain_ctas > 0 && overlap) {   // early chain pass: beside the row kernel, waiting on its segment warps
+    const int per_row = plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0);
+    const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
+    if (chain_ctas > 0 && overlap) {   // early chain passes: beside the row kernel, waiting on its segment warps
         CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
         CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-        k_hub_chain<true><<<(unsigned)chain_ctas, kChainThreads, kChainSmemBytes, plan->side>>>(p);
-        CLANE_LAUNCH_CHECK();
+        if (n_long > 0) {
+            p.hub_first = 0;
+            k_hub_chain<true, false><<<(unsigned)(n_long * per_row), kChainThreads, kChainSmemBytes, plan->side>>>(p);
+            CLANE_LAUNCH_CHECK();
+        }
         CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
+        if (n_short > 0) {             // its own stream: not behind the long rows' chains
+            CLANE_CUDA(cudaStreamWaitEvent(plan->side2, plan->ev_fork, 0));
+            p.hub_first = n_long;
+            k_hub_chain<true, true><<<(unsigned)(n_short * per_row), kChainThreads, chain_smem_bytes(kLightStages), plan->side2>>>(p);
+            CLANE_LAUNCH_CHECK();
+            CLANE_CUDA(cudaEventRecord(plan->ev_join2, plan->side2));
+        }
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[1], st));
     if (row_ctas > 0) {
@@ -328,10 +340,14 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[2], st));
-    if (chain_ctas > 0 && overlap) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+    if (chain_ctas > 0 && overlap) {
+        CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+        if (n_short > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join2, 0));
+    }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], st));
     if (chain_ctas > 0) {              // late pass: whatever the early one left, and the reset of its flags
-        k_hub_chain<false><<<(unsigned)chain_ctas, kChainThreads, kChainSmemBytes, st>>>(p);
+        p.hub_first = 0;
+        k_hub_chain<false, true><<<(unsigned)chain_ctas, kChainThreads, chain_smem_bytes(kLightStages), st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
     if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], st));
@@ -493,8 +509,7 @@ int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweep
 int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
-    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
-    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

@@ -15,6 +15,7 @@ struct clane_plan {
     int32_t n_groups = 0;       // groups covering [row_lo, row_hi)
     int32_t span_edges = 128;   // edge budget of a span
     int32_t n_spans = 0, n_fix_groups = 0, n_hub_rows = 0;
+    int32_t n_long_hub_rows = 0;   // the first n_long_hub_rows hub rows (degree-descending) have >= kLongBlocks blocks
     // the sweep's program (sweep.cuh): tasks sorted by work descending (hub segments first), batch descriptors
     void* d_tasks = nullptr;           // SweepTask[n_tasks]
     int32_t* d_descs = nullptr;
@@ -22,7 +23,7 @@ struct clane_plan {
     int64_t n_descs = 0;
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
-    int32_t* d_hub_blk0 = nullptr;     // first scratch block of each hub row
+    void* d_hub_info = nullptr;        // int4 per hub row: {row, first edge, degree, first scratch block}
     int64_t hub_blocks = 0;            // 8-neighbour blocks of all hub rows
     int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it
     void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
@@ -30,8 +31,8 @@ struct clane_plan {
     void* d_hubT = nullptr;            // float4[hub_blocks * 8][ntail4]  raw z, sequential-regime columns
     int32_t* d_hub_cnt = nullptr;      // per hub row: segment warps done this sweep
     int32_t* d_hub_done = nullptr;     // per chain CTA: produced by the early (overlapped) chain pass
-    cudaStream_t side = nullptr;       // the early chain pass runs here, forked from / joined to the caller's stream
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;   // the early chain passes (long rows / short rows) run here,
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;   // forked from / joined to the caller's stream
     // row-partitioned run: peer Znext buffers for the two Z ping-pong buffers (entry self = own buffer)
     int32_t n_peers = 0, self_rank = 0;
     float* peers[2][16] = {};

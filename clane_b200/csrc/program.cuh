@@ -33,6 +33,7 @@ constexpr int kDescRowShift = 6;      // 5 bits
 constexpr int kDescMetaShift = 19;    // 7 bits
 
 constexpr int kMaxPeers = 15;                  // remote ranks of a row-partitioned run (one NVLink domain)
+constexpr int kLongBlocks = 128;               // hub rows of >= 1024 neighbours take the heavy chain kernel
 constexpr int kSegEdges = 128;                 // neighbours per hub segment task (16 blocks)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs per warp, + 8 mirrored entries
 

@@ -56,8 +56,7 @@ struct SweepParams {
     int fuse;                   // 1: direct spans write one 32-lane |delta| partial per group to P0
     float* P0;
     // hub rows
-    const int32_t* hub_rows;    // rows of degree > hub_threshold, degree-descending
-    const int32_t* hub_blk0;    // first scratch block of each hub row
+    const int4* hub_info;       // per hub row (degree-descending): {row, first edge, degree, first scratch block}
     int n_hub_rows;
     int limit;                  // 16 * floor(d / 16): columns below it use the 8-block order
     int ntail4;                 // (ld - limit) / 4: float4 pieces per row in the sequential regime (0..4)
@@ -68,6 +67,7 @@ struct SweepParams {
     float4* hubT;               // per hub row [sequential-regime column][neighbour] raw z (floats)
     int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
     int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
+    int hub_first;              // first hub row of this chain launch
     const clane_patience* st;
     // row-partitioned run: the other ranks' Znext buffers (peer memory over NVLink); every finished row is
     // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
@@ -85,8 +85,11 @@ constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // hub chain kernel: one warp per CTA
 constexpr int kChainGroup = 16;                // blocks per cp.async group (8 KB)
 constexpr int kChainGroups = 12;               // groups in flight (12 x 8 KB = 96 KB: two chain CTAs per SM)
-constexpr size_t kChainSmemBytes = (size_t)kChainGroups * kChainGroup * 32 * sizeof(float4) +
-                                   (size_t)kChainGroups * kChainGroup * sizeof(float2);
+constexpr int kLightStages = 4;                // short hub rows
+__host__ __device__ constexpr size_t chain_smem_bytes(int stages) {
+    return (size_t)stages * kChainGroup * 32 * sizeof(float4) + (size_t)stages * kChainGroup * sizeof(float2);
+}
+constexpr size_t kChainSmemBytes = chain_smem_bytes(kChainGroups);
 constexpr unsigned long long kChainSpinNs = 2000000ull;   // early chain pass: give up after 2 ms
 constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
 constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
@@ -527,18 +530,22 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
 //         so the chains finish long before the ordinary rows do and cost the sweep nothing.
 // !kEarly: launched after both; chains whatever the early pass did not (it timed out: kernels serialised by a
 //         profiler, or the device too busy to co-schedule), and resets the flags for the next sweep.
-template <bool kEarly>
+// kLight: short rows -- 4-stage ring, no register double buffer: a CTA that costs an SM next to nothing while it
+//         waits.  !kLight: long rows (>= kLongBlocks blocks) -- 12 stages, the chain never waits for the ring.
+template <bool kEarly, bool kLight>
 __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
+    constexpr int kStages = kLight ? kLightStages : kChainGroups;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
     __shared__ int s_done;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = p.nslab32b + (p.ntail4 > 0 ? 1 : 0);
-    const int hr = blockIdx.x / per, s = blockIdx.x - hr * per;
+    const int hr = p.hub_first + blockIdx.x / per, s = blockIdx.x % per;
+    const int cta = hr * per + s;                      // index into hub_done
     const bool stopped = p.st != nullptr && p.st->stop;
     if (kEarly && stopped) return;
-    const int row = __ldg(p.hub_rows + hr);
-    const int a = __ldg(p.rowptr + row), k = __ldg(p.rowptr + row + 1) - a;
+    const int4 info = __ldg(p.hub_info + hr);          // one load: every access here queues behind the row kernel's
+    const int row = info.x, a = info.y, k = info.z;
     const int nblk = k >> 3;
     if (kEarly) {
         const int expect = ((nblk + kSegEdges / 8 - 1) / (kSegEdges / 8)) * p.nslab;
@@ -554,23 +561,23 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
             if (t1 - t0 > kChainSpinNs) break;
         }
         ready = __syncthreads_and(ready);              // both warps agree
-        if (p.dbg && hr < 2 && threadIdx.x == 0) printf("[dbg] chain hr %d slab %d start %llu ready %llu (%d)\n", hr, s, t0, t1, (int)ready);
+        if (p.dbg && (hr < 2 || hr >= p.n_hub_rows - 2) && threadIdx.x == 0) printf("[dbg] chain hr %d slab %d start %llu ready %llu (%d)\n", hr, s, t0, t1, (int)ready);
         if (!ready) return;                            // the late pass does it
         __threadfence();                               // acquire: the parked blocks of every segment warp
     } else {
         if (threadIdx.x == 0) {
-            s_done = p.hub_done[blockIdx.x];
-            p.hub_done[blockIdx.x] = 0;                // also when stopped
+            s_done = p.hub_done[cta];
+            p.hub_done[cta] = 0;                       // also when stopped
             if (s == 0) p.hub_cnt[hr] = 0;
         }
         __syncthreads();
         if (s_done || stopped) return;
     }
-    const size_t B0 = (size_t)__ldg(p.hub_blk0 + hr);
+    const size_t B0 = (size_t)info.w;
     const int nleft = k - nblk * 8;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }   // (unrolled: ~0.3 us)
         fence_mbar_init();
     }
     __syncthreads();
@@ -579,11 +586,11 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
     const int nnb = nblk * 8;
     const int ngroups = blocked ? (nblk + kChainGroup - 1) / kChainGroup : (nnb + kTailGroup - 1) / kTailGroup;
     float4* ringS = reinterpret_cast<float4*>(smem);                                  // blocked: [stage][16][32]
-    float2* wq = reinterpret_cast<float2*>(ringS + kChainGroups * kChainGroup * 32);  //          [stage][16]
+    float2* wq = reinterpret_cast<float2*>(ringS + kStages * kChainGroup * 32);       //          [stage][16]
     // sequential regime: stage = [ntc columns][kTailPitch] z | [32] w; as many stages as the shared memory holds
     float* zr = reinterpret_cast<float*>(smem);
     const int tstride = ntc * kTailPitch + kTailGroup;
-    const int tstages = min(kMaxStages, (int)(kChainSmemBytes / sizeof(float)) / max(tstride, 1));
+    const int tstages = min(kMaxStages, (int)(chain_smem_bytes(kStages) / sizeof(float)) / max(tstride, 1));
 
     if (warp == 1) {
         // ---------------- producer ----------------
@@ -593,8 +600,8 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
             const unsigned ring_sa = smem_u32(ringS) + lane * 16;
             const unsigned wq_sa = smem_u32(wq) + (lane & 15) * 8;
             for (int g = 0; g < ngroups; ++g) {
-                const int st = g % kChainGroups;
-                if (g >= kChainGroups) mbar_wait(empty + st, (unsigned)(g / kChainGroups - 1) & 1u);
+                const int st = g % kStages;
+                if (g >= kStages) mbar_wait(empty + st, (unsigned)(g / kStages - 1) & 1u);
                 const int b0 = g * kChainGroup;
                 const unsigned dst = ring_sa + (unsigned)st * (kChainGroup * 512);
 #pragma unroll
@@ -629,6 +636,7 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
     const int col = blocked ? s * 32 + lane : p.limit + lane;
     const bool act = blocked ? col < p.limit : col < p.ld;
     const int ccol = act ? col : (blocked ? 0 : p.limit);
+    const float xv = __ldg(p.X + (size_t)row * p.ld + ccol);   // needed last, fetched first
     // the k mod 8 leftovers: gathered now, added after the blocks
     float lz[7], lw[7];
 #pragma unroll
@@ -647,8 +655,8 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         float2 wv[kChainGroup], wn[kChainGroup];
         auto fetch = [&](int g, float4 (&dv)[kChainGroup], float2 (&dw)[kChainGroup]) {
             const bool live = g < ngroups;   // past the end: no wait, the loads below return stale data nobody uses
-            const int st = g % kChainGroups; //   (they stay unconditional: loads under a branch would be waited for at its join)
-            if (live) mbar_wait(full + st, (unsigned)(g / kChainGroups) & 1u);
+            const int st = g % kStages;      //   (they stay unconditional: loads under a branch would be waited for at its join)
+            if (live) mbar_wait(full + st, (unsigned)(g / kStages) & 1u);
             const float4* rs = ringS + (size_t)st * kChainGroup * 32 + lane;
             const float2* ws = wq + st * kChainGroup;
 #pragma unroll
@@ -677,13 +685,17 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
                     }
             }
         };
-        fetch(0, v, wv);
-        for (int g = 0; g < ngroups; g += 2) {
-            fetch(g + 1, vn, wn);
-            chain(g, v, wv);
-            if (g + 1 >= ngroups) break;
-            fetch(g + 2, v, wv);
-            chain(g + 1, vn, wn);
+        if (kLight) {
+            for (int g = 0; g < ngroups; ++g) { fetch(g, v, wv); chain(g, v, wv); }
+        } else {
+            fetch(0, v, wv);
+            for (int g = 0; g < ngroups; g += 2) {
+                fetch(g + 1, vn, wn);
+                chain(g, v, wv);
+                if (g + 1 >= ngroups) break;
+                fetch(g + 2, v, wv);
+                chain(g + 1, vn, wn);
+            }
         }
     } else {
         // ---- sequential regime: a = fma(w_i, z_i, a) over all neighbours (same register double buffer) ----
@@ -711,13 +723,17 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
                     acc = ffma(dw[j].w, dz[j].w, acc);
                 }
         };
-        fetch(0, zv, wv);
-        for (int g = 0; g < ngroups; g += 2) {
-            fetch(g + 1, zn, wn);
-            chain(g, zv, wv);
-            if (g + 1 >= ngroups) break;
-            fetch(g + 2, zv, wv);
-            chain(g + 1, zn, wn);
+        if (kLight) {
+            for (int g = 0; g < ngroups; ++g) { fetch(g, zv, wv); chain(g, zv, wv); }
+        } else {
+            fetch(0, zv, wv);
+            for (int g = 0; g < ngroups; g += 2) {
+                fetch(g + 1, zn, wn);
+                chain(g, zv, wv);
+                if (g + 1 >= ngroups) break;
+                fetch(g + 2, zv, wv);
+                chain(g + 1, zn, wn);
+            }
         }
     }
 #pragma unroll
@@ -725,12 +741,12 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         if (o < nleft) acc = ffma(lw[o], lz[o], acc);
     if (act) {
         const size_t off = (size_t)row * p.ld + col;
-        const float v = fadd(__ldg(p.X + off), fmul(p.gamma, acc));
+        const float v = fadd(xv, fmul(p.gamma, acc));
         p.Zn[off] = v;
         for (int j = 0; j < p.n_remote; ++j) p.peer[j][off] = v;
     }
-    if (kEarly && lane == 0) p.hub_done[blockIdx.x] = 1;
-    if (kEarly && p.dbg && hr < 2 && lane == 0) {
+    if (kEarly && lane == 0) p.hub_done[cta] = 1;
+    if (kEarly && p.dbg && (hr < 2 || hr >= p.n_hub_rows - 2) && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         printf("[dbg] chain hr %d slab %d end %llu blocks %d\n", hr, s, t, nblk);
