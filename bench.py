@@ -261,7 +261,8 @@ def run_gpu(args):
         _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.rowptr.data_ptr(),
                                  S.col.data_ptr(), S.w.data_ptr(), gamma, S.amount.data_ptr() if with_l1 else 0, 0, 0, 0,
                                  sh))
-        launches_per_step[0] = S.plan.launches_per_sweep if with_l1 else 1 + (1 if S.plan.n_hub_rows else 0)
+        launches_per_step[0] = S.plan.launches_per_sweep if with_l1 else S.plan.launches_per_sweep - 2 - (
+            1 if S.plan.fused_l1 and S.plan.n_fix_groups else 0)
 
     def barrier():
         if world > 1:
@@ -338,7 +339,8 @@ def run_gpu(args):
                     else "NCCL all-gather of Z per sweep"),
                    "l2": f"no flush: working set {(3 * n * d * 4 + 8 * e) / 1e6:.0f} MB exceeds the 126 MB L2"
                          if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",
-                   "step": "row + hub sweep kernels, exact L1 change (fused partials / cascade), device patience; P frozen",
+                   "step": "row kernel (+ hub segments) with the hub chains beside it, exact L1 change (fused partials / "
+                           "cascade), device patience; P frozen",
                    "plan": {"group_rows": (S.plan if runner is None else runner.plan).group_rows,
                             "spans": (S.plan if runner is None else runner.plan).n_spans,
                             "hub_rows": (S.plan if runner is None else runner.plan).n_hub_rows,

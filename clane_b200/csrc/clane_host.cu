@@ -370,9 +370,12 @@ int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_span
     if (n_hub_rows) *n_hub_rows = plan->n_hub_rows;
     if (n_fix_groups) *n_fix_groups = plan->n_fix_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    // row sweep, [hub chain], [chunk fix-up], level-1, finish
-    if (launches_per_sweep)
-        *launches_per_sweep = 3 + (plan->n_hub_rows > 0 ? 1 : 0) + ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
+    // row sweep, [early chain: long rows], [early chain: short rows], [late chain], [chunk fix-up], level-1, finish
+    if (launches_per_sweep) {
+        const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
+        *launches_per_sweep = 3 + (n_long > 0 ? 1 : 0) + (n_short > 0 ? 1 : 0) + (plan->n_hub_rows > 0 ? 1 : 0) +
+                              ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
+    }
     return CLANE_OK;
 }
 

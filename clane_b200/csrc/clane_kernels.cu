@@ -281,6 +281,14 @@ int clane_build_p_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ro
     return clane_row_softmax(d_w, d_norms2, plan->row_lo, plan->row_hi, d_rowptr, d_w, s);
 }
 
+// timing bracket: an ordinary record, or -- while the sweep is being captured -- an external event-record node of
+// the graph, so that the brackets measure the kernels as they run in the replayed graph
+static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    return cudaEventRecordWithFlags(ev, st, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext,
                          const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma, float* d_amount,
                          clane_patience* d_state, float* d_amounts_log, int32_t log_cap, cudaStream_t st) {
@@ -313,7 +321,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     const int64_t chain_ctas = (int64_t)p.n_hub_rows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
     const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
     const bool prof = plan->profile;
-    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[0], st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[0], st));
     static const bool overlap = getenv("CLANE_NO_CHAIN_OVERLAP") == nullptr;
     const int per_row = plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0);
     const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
@@ -334,26 +342,26 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
             CLANE_CUDA(cudaEventRecord(plan->ev_join2, plan->side2));
         }
     }
-    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[1], st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[1], st));
     if (row_ctas > 0) {
         k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, 0, st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
-    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[2], st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[2], st));
     if (chain_ctas > 0 && overlap) {
         CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
         if (n_short > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join2, 0));
     }
-    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[4], st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[4], st));
     if (chain_ctas > 0) {              // late pass: whatever the early one left, and the reset of its flags
         p.hub_first = 0;
         k_hub_chain<false, true><<<(unsigned)chain_ctas, kChainThreads, chain_smem_bytes(kLightStages), st>>>(p);
         CLANE_LAUNCH_CHECK();
     }
-    if (prof) CLANE_CUDA(cudaEventRecord(plan->ev_prof[5], st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[5], st));
     struct ProfTail {   // records the end-of-sweep event on every exit path below
         clane_plan* pl; cudaStream_t s;
-        ~ProfTail() { if (pl->profile) cudaEventRecord(pl->ev_prof[3], s); }
+        ~ProfTail() { if (pl->profile) prof_record(pl->ev_prof[3], s); }
     } prof_tail{plan, st};
     if (!want_l1) return CLANE_OK;
     const int64_t n_elems = (int64_t)plan->n * plan->d;
@@ -389,7 +397,7 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     static const bool env_graphs = getenv("CLANE_NO_GRAPHS") == nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    if (!plan->use_graphs || !env_graphs || plan->profile || cap != cudaStreamCaptureStatusNone || st == nullptr)
+    if (!plan->use_graphs || !env_graphs || cap != cudaStreamCaptureStatusNone || st == nullptr)
         return sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state, d_amounts_log,
                              log_cap, st);
     // One sweep = up to five kernels on two streams.  Replay it as a CUDA graph: a propagate() call
@@ -484,6 +492,9 @@ int clane_plan_profile(clane_plan* plan, int enable) {
     if (!plan) return CLANE_EINVAL;
     if (enable && !plan->ev_prof[0])
         for (int i = 0; i < 6; ++i) CLANE_CUDA(cudaEventCreate(&plan->ev_prof[i]));
+    if (plan->profile != (enable != 0))   // the brackets are event-record nodes of the replayed sweep graphs: re-capture
+        for (auto& g : plan->graphs)
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     plan->profile = enable != 0;
     return CLANE_OK;
 }

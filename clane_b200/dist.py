@@ -195,7 +195,7 @@ class ShardedSweeper:
                                  self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
                    "clane_sweep")
         mark("sweep")
-        launches = 1 + (2 if self.plan.n_hub_rows else 0)
+        launches = self.plan.launches_per_sweep - 2      # a rank's plan is never fused: no fix-up kernel; L1 counted below
         if self.exchange == "nccl":
             lo = self.rank * self.per
             gather_rows(zn[lo:lo + self.per], zn)
