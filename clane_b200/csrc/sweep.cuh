@@ -247,6 +247,13 @@ __device__ __forceinline__ void load_batch(float4 (&buf)[8], const int2* __restr
     for (int i = 0; i < M; ++i) buf[i] = gather4(zb, mp[i].x, keep);
 }
 
+// sequential fma chain over M <= 4 buffer entries starting at OFF (a short row: k < 8, every column sequential)
+template <int M, int OFF>
+__device__ __forceinline__ void reduce_short(const float4 (&z)[8], const int2* __restrict__ mp, float4& acc) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) fma4(__int_as_float(mp[i].y), z[OFF + i], acc);
+}
+
 template <int M>
 __device__ __forceinline__ void reduce_batch(const float4 (&z)[8], const int2* __restrict__ mp, float4& acc,
                                              bool col_blocked) {
@@ -380,14 +387,66 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
     for (int cb = 0; cb < nb; ++cb) {
         const int id = next_desc(p, s, cb, lane, meta);
         const int2* mp = meta + ((id >> kDescMetaShift) & 127);
-        const bool last = (id & kDescLast) != 0;
+        const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
         const int row_off = (r0 + ((id >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
+        const int m2 = (id >> kDescM2Shift) & 7;
+        if (m2) {
+            // ---- two short rows (<= 4 neighbours each) in one batch: one memory round trip for both.  The loads
+            //      are branch-free: entries past a row's length repeat its last neighbour (same sectors). ----
+            const int m1 = id & 15;
+            const int row_off2 = row_off + ((id >> kDescRow2Shift) & 31) * p.ld;
+            const int2* mp2 = mp + m1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) A[j] = gather4(zb, mp[min(j, m1 - 1)].x, keep);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) A[4 + j] = gather4(zb, mp2[min(j, m2 - 1)].x, keep);
+            float4 xs2, own2;
+            ldg4_stream_if(xs, p.X + row_off, true, once);
+            ldg4_stream_if(xs2, p.X + row_off2, true, once);
+            if (kDirect) {
+                ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), true, keep);
+                ldg4_if(own2, reinterpret_cast<const float4*>(p.Zc + row_off2), true, keep);
+            }
+            switch (m1) {
+                case 4: reduce_short<4, 0>(A, mp, acc); break;
+                case 3: reduce_short<3, 0>(A, mp, acc); break;
+                case 2: reduce_short<2, 0>(A, mp, acc); break;
+                default: reduce_short<1, 0>(A, mp, acc); break;
+            }
+            float4 out = finish_row(xs, acc, p.gamma);
+            if (active) {
+                st4_hint(p.Zn + row_off, out, once);
+                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
+            }
+            if (kDirect) {
+                const float4 dl = active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
+                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            switch (m2) {
+                case 4: reduce_short<4, 4>(A, mp2, acc); break;
+                case 3: reduce_short<3, 4>(A, mp2, acc); break;
+                case 2: reduce_short<2, 4>(A, mp2, acc); break;
+                default: reduce_short<1, 4>(A, mp2, acc); break;
+            }
+            out = finish_row(xs2, acc, p.gamma);
+            if (active) {
+                st4_hint(p.Zn + row_off2, out, once);
+                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off2) = out;
+            }
+            if (kDirect) {
+                const float4 dl = active ? absdiff4(out, own2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const bool last = (id & kDescLast) != 0;
         // ---- the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch
         //      here would make ptxas wait for them at the join, before the gathers are even issued) ----
         ldg4_stream_if(xs, p.X + row_off, last, once);
         if (kDirect) ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last, keep);
         // ---- m gathers, then the reduction in the reference's order ----
-        const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
         switch (id & 15) {
             case 8: load_batch<8>(A, mp, zb, keep); reduce_batch<8>(A, mp, acc, col_blocked); break;
             case 7: load_batch<7>(A, mp, zb, keep); reduce_batch<7>(A, mp, acc, col_blocked); break;
