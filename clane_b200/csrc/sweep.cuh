@@ -78,8 +78,9 @@ struct SweepParams {
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA
 constexpr int kRowWarps = 4;
-// row kernel shared memory per warp: (offset, w) ring | 512-byte transpose scratch (fused L1)
-constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512;
+// row kernel shared memory per warp: (offset, w) ring | 512-byte transpose scratch (fused L1) | 10 row-piece slots
+// (8 neighbours + X + own Zcur) of the batch that goes through cp.async
+constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512 + 10 * 512;
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 
 // hub chain kernel: one warp per CTA
@@ -254,6 +255,22 @@ __device__ __forceinline__ void reduce_short(const float4 (&z)[8], const int2* _
     for (int i = 0; i < M; ++i) fma4(__int_as_float(mp[i].y), z[OFF + i], acc);
 }
 
+__device__ __forceinline__ void cp_async16_hint(unsigned smem_addr, const void* gsrc, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "l"(pol) : "memory");
+}
+// the gathers of one batch through cp.async: slot i of the warp's shared-memory slots <- neighbour i's row piece
+template <int M>
+__device__ __forceinline__ void async_batch(unsigned slot_sa, const int2* __restrict__ mp, const float4* __restrict__ zb,
+                                            unsigned long long keep) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) cp_async16_hint(slot_sa + i * 512, zb + (unsigned)mp[i].x, keep);
+}
+template <int M>
+__device__ __forceinline__ void slot_batch(float4 (&buf)[8], const float4* __restrict__ myslot) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) buf[i] = myslot[i * 32];
+}
+
 template <int M>
 __device__ __forceinline__ void reduce_batch(const float4 (&z)[8], const int2* __restrict__ mp, float4& acc,
                                              bool col_blocked) {
@@ -368,7 +385,7 @@ __device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int i
 // tools/l1pf_probe.cu: deeper per-warp pipelines or L1 / L2 prefetching do not beat more warps).
 template <bool kDirect>
 __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, const int4 t1, int slab, int lane,
-                                         int2* meta, float* scratch) {
+                                         int2* meta, float* scratch, float4* slots) {
     const int c0 = slab * 128 + lane * 4;
     const bool active = c0 < p.ld;
     const bool col_blocked = c0 < p.limit;
@@ -379,75 +396,66 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
     open_streams(p, s, lane, meta);
 
     const unsigned long long keep = policy_evict_last(), once = policy_evict_first();
+    const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
+    const unsigned slot_sa = smem_u32(slots) + lane * 16;      // this lane's 16 bytes of slot 0
+    const float4* myslot = slots + lane;
     float4 A[8], xs, own;
     xs = own = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float chunk_acc = 0.0f;
     const int nb = s.nb;
-    for (int cb = 0; cb < nb; ++cb) {
-        const int id = next_desc(p, s, cb, lane, meta);
-        const int2* mp = meta + ((id >> kDescMetaShift) & 127);
-        const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
-        const int row_off = (r0 + ((id >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
-        const int m2 = (id >> kDescM2Shift) & 7;
-        if (m2) {
-            // ---- two short rows (<= 4 neighbours each) in one batch: one memory round trip for both.  The loads
-            //      are branch-free: entries past a row's length repeat its last neighbour (same sectors). ----
-            const int m1 = id & 15;
-            const int row_off2 = row_off + ((id >> kDescRow2Shift) & 31) * p.ld;
-            const int2* mp2 = mp + m1;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) A[j] = gather4(zb, mp[min(j, m1 - 1)].x, keep);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) A[4 + j] = gather4(zb, mp2[min(j, m2 - 1)].x, keep);
-            float4 xs2, own2;
-            ldg4_stream_if(xs, p.X + row_off, true, once);
-            ldg4_stream_if(xs2, p.X + row_off2, true, once);
-            if (kDirect) {
-                ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), true, keep);
-                ldg4_if(own2, reinterpret_cast<const float4*>(p.Zc + row_off2), true, keep);
-            }
-            switch (m1) {
-                case 4: reduce_short<4, 0>(A, mp, acc); break;
-                case 3: reduce_short<3, 0>(A, mp, acc); break;
-                case 2: reduce_short<2, 0>(A, mp, acc); break;
-                default: reduce_short<1, 0>(A, mp, acc); break;
-            }
-            float4 out = finish_row(xs, acc, p.gamma);
-            if (active) {
-                st4_hint(p.Zn + row_off, out, once);
-                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
-            }
-            if (kDirect) {
-                const float4 dl = active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
-                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
-            }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            switch (m2) {
-                case 4: reduce_short<4, 4>(A, mp2, acc); break;
-                case 3: reduce_short<3, 4>(A, mp2, acc); break;
-                case 2: reduce_short<2, 4>(A, mp2, acc); break;
-                default: reduce_short<1, 4>(A, mp2, acc); break;
-            }
-            out = finish_row(xs2, acc, p.gamma);
-            if (active) {
-                st4_hint(p.Zn + row_off2, out, once);
-                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off2) = out;
-            }
-            if (kDirect) {
-                const float4 dl = active ? absdiff4(out, own2) : make_float4(0.f, 0.f, 0.f, 0.f);
-                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
-            }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
+
+    auto finish = [&](const float4& xv, const float4& ov, int row_off) {
+        const float4 out = finish_row(xv, acc, p.gamma);
+        if (active) {
+            st4_hint(p.Zn + row_off, out, once);
+            for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
         }
-        const bool last = (id & kDescLast) != 0;
-        // ---- the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch
-        //      here would make ptxas wait for them at the join, before the gathers are even issued) ----
+        if (kDirect) {
+            const float4 dl = active ? absdiff4(out, ov) : make_float4(0.f, 0.f, 0.f, 0.f);
+            chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
+        }
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    // Two batches in flight per warp, on two independent completion mechanisms: the odd batch goes through
+    // cp.async into the warp's 10 shared-memory slots (completion = async group), the even batch straight into
+    // registers (completion = scoreboard).  Both are issued before either is reduced; the reductions then run in
+    // order.  (Two register buffers would cost 32 more registers, i.e. a fifth of the resident warps; and ptxas
+    // tracks all 128-bit loads of a warp on one scoreboard, so waiting for the first would wait for both anyway.)
+    for (int cb = 0; cb < nb; cb += 2) {
+        const int idr = next_desc(p, s, cb, lane, meta);
+        const bool has_s = cb + 1 < nb;
+        const int ids = has_s ? next_desc(p, s, cb + 1, lane, meta) : 0;
+        // ---- odd batch: cp.async ----
+        const int2* mps = meta + ((ids >> kDescMetaShift) & 127);
+        const int row_off_s = (r0 + ((ids >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
+        const bool last_s = (ids & kDescLast) != 0;
+        switch (ids & 15) {
+            case 8: async_batch<8>(slot_sa, mps, zb, keep); break;
+            case 7: async_batch<7>(slot_sa, mps, zb, keep); break;
+            case 6: async_batch<6>(slot_sa, mps, zb, keep); break;
+            case 5: async_batch<5>(slot_sa, mps, zb, keep); break;
+            case 4: async_batch<4>(slot_sa, mps, zb, keep); break;
+            case 3: async_batch<3>(slot_sa, mps, zb, keep); break;
+            case 2: async_batch<2>(slot_sa, mps, zb, keep); break;
+            case 1: async_batch<1>(slot_sa, mps, zb, keep); break;
+            default: break;
+        }
+        if (last_s) {
+            cp_async16_hint(slot_sa + 8 * 512, p.X + row_off_s, once);
+            if (kDirect) cp_async16_hint(slot_sa + 9 * 512, p.Zc + row_off_s, keep);
+        }
+        cp_async_commit();
+        // ---- even batch: registers; loads and reduction in the same switch case ----
+        const int2* mp = meta + ((idr >> kDescMetaShift) & 127);
+        const bool last = (idr & kDescLast) != 0;
+        const int row_off = (r0 + ((idr >> kDescRowShift) & 31)) * p.ld + cc;
+        // the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch here
+        // would make ptxas wait for them at the join, before the gathers are even issued)
         ldg4_stream_if(xs, p.X + row_off, last, once);
         if (kDirect) ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last, keep);
-        // ---- m gathers, then the reduction in the reference's order ----
-        switch (id & 15) {
+        switch (idr & 15) {
             case 8: load_batch<8>(A, mp, zb, keep); reduce_batch<8>(A, mp, acc, col_blocked); break;
             case 7: load_batch<7>(A, mp, zb, keep); reduce_batch<7>(A, mp, acc, col_blocked); break;
             case 6: load_batch<6>(A, mp, zb, keep); reduce_batch<6>(A, mp, acc, col_blocked); break;
@@ -457,17 +465,21 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
             case 2: load_batch<2>(A, mp, zb, keep); reduce_batch<2>(A, mp, acc, col_blocked); break;
             default: load_batch<1>(A, mp, zb, keep); reduce_batch<1>(A, mp, acc, col_blocked); break;
         }
-        if (last) {
-            const float4 out = finish_row(xs, acc, p.gamma);
-            if (active) {
-                st4_hint(p.Zn + row_off, out, once);
-                for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
+        if (last) finish(xs, own, row_off);
+        // ---- reduce the odd batch out of shared memory (each lane reads the 16 bytes it copied: no barrier) ----
+        cp_async_wait<0>();
+        if (has_s) {
+            switch (ids & 15) {
+                case 8: slot_batch<8>(A, myslot); reduce_batch<8>(A, mps, acc, col_blocked); break;
+                case 7: slot_batch<7>(A, myslot); reduce_batch<7>(A, mps, acc, col_blocked); break;
+                case 6: slot_batch<6>(A, myslot); reduce_batch<6>(A, mps, acc, col_blocked); break;
+                case 5: slot_batch<5>(A, myslot); reduce_batch<5>(A, mps, acc, col_blocked); break;
+                case 4: slot_batch<4>(A, myslot); reduce_batch<4>(A, mps, acc, col_blocked); break;
+                case 3: slot_batch<3>(A, myslot); reduce_batch<3>(A, mps, acc, col_blocked); break;
+                case 2: slot_batch<2>(A, myslot); reduce_batch<2>(A, mps, acc, col_blocked); break;
+                default: slot_batch<1>(A, myslot); reduce_batch<1>(A, mps, acc, col_blocked); break;
             }
-            if (kDirect) {
-                const float4 dl = active ? absdiff4(out, own) : make_float4(0.f, 0.f, 0.f, 0.f);
-                chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
-            }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (last_s) finish(myslot[8 * 32], myslot[9 * 32], row_off_s);
         }
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
@@ -562,6 +574,7 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     int2* meta = reinterpret_cast<int2*>(mine);
     float* scratch = reinterpret_cast<float*>(meta + kMetaRing + 8);
+    float4* slots = reinterpret_cast<float4*>(scratch + 128);
     const int wtask = blockIdx.x * kRowWarps + warp;
     int ti = wtask, slab = 0;
     if (p.nslab > 1) { ti = wtask / p.nslab; slab = wtask - ti * p.nslab; }
@@ -570,8 +583,8 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
     prefetch_task(p, ti + kPrefetchAhead, slab, lane);
     if (t1.y & kTaskSegment) run_segment(p, t0, t1, slab, lane, meta);
-    else if (t1.y & kTaskDirect) run_span<true>(p, t0, t1, slab, lane, meta, scratch);
-    else run_span<false>(p, t0, t1, slab, lane, meta, scratch);
+    else if (t1.y & kTaskDirect) run_span<true>(p, t0, t1, slab, lane, meta, scratch, slots);
+    else run_span<false>(p, t0, t1, slab, lane, meta, scratch, slots);
 }
 
 // ------------------------------------------------------------------------------------------
