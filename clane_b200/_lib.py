@@ -36,6 +36,10 @@ SIGNATURES = {
     "clane_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "clane_padded_ld": (C.c_int32, [C.c_int32]),
     "clane_csr_from_edges": (C.c_int64, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "clane_edges_open": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int32, C.POINTER(c_vp), c_i64p, c_i64p,
+                                   C.c_char_p, C.c_int32]),
+    "clane_edges_read": (C.c_int, [c_vp, c_vp, c_vp]),
+    "clane_edges_close": (C.c_int, [c_vp]),
     "clane_group_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp,
                                        c_i32p, c_vp, c_i32p, c_vp, c_i32p, c_i32p, c_i32p]),
     "clane_sweep_program": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, C.c_int64,

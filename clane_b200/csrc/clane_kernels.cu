@@ -206,6 +206,10 @@ const char* clane_error_string(int code) {
         case CLANE_ERANGE: return "clane: index out of range";
         case CLANE_EWORKSPACE: return "clane: workspace too small";
         case CLANE_ENODEVICE: return "clane: no sm_100 CUDA device";
+        case CLANE_ENOENT: return "clane: cannot open file";
+        case CLANE_EPARSE: return "clane: malformed edge line";
+        case CLANE_EUNKNOWNID: return "clane: edge endpoint not in V";
+        case CLANE_ENOMEM: return "clane: out of host memory";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "clane: unknown error";
     }
 }

@@ -16,6 +16,7 @@ without a CUDA device.
 """
 from __future__ import annotations
 
+import ctypes
 import random
 from pathlib import Path
 
@@ -93,21 +94,27 @@ def _parse_vertex_ids(path: Path):
 
 def _parse_edges(path: Path, vertex_ids):
     """graph.py:73-81: lines ``src_id<TAB>dst_id``; ids map to their FIRST position in V;
-    a line without exactly one tab or with an unknown id raises ValueError."""
-    with open(path, "r") as io:
-        lines = io.read().strip().split("\n")
-    first = {}
-    for i, vid in enumerate(vertex_ids):
-        first.setdefault(vid, i)
-    src = np.empty(len(lines), np.int64)
-    dst = np.empty(len(lines), np.int64)
-    for k, line in enumerate(lines):
-        src_id, dst_id = line.split("\t")  # ValueError unless exactly two fields
-        try:
-            src[k] = first[src_id]
-            dst[k] = first[dst_id]
-        except KeyError as exc:
-            raise ValueError(f"{exc.args[0]!r} is not in list") from None
+    a line without exactly one tab or with an unknown id raises ValueError.  Parsed natively
+    (clane_edges_open: hash map over V, one file piece per host thread) -- the reference's
+    ``vertex_ids.index`` loop is O(E*N)."""
+    open(path, "r").close()                     # FileNotFoundError etc. exactly as the reference raises them
+    L = _lib.lib()
+    joined = "\n".join(vertex_ids).encode("utf-8")
+    handle, e_raw, err_line = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64(-1)
+    err = ctypes.create_string_buffer(512)
+    rc = L.clane_edges_open(joined, len(joined), len(vertex_ids), str(path).encode(), 0, ctypes.byref(handle),
+                            ctypes.byref(e_raw), ctypes.byref(err_line), err, len(err))
+    if rc == -6:                                # CLANE_EPARSE: the reference's tuple-unpacking error
+        raise ValueError(err.value.decode("utf-8", "replace"))
+    if rc == -7:                                # CLANE_EUNKNOWNID: list.index's error
+        raise ValueError(f"{err.value.decode('utf-8', 'replace')!r} is not in list")
+    _lib.check(rc, "clane_edges_open")
+    try:
+        src = np.empty(e_raw.value, np.int64)
+        dst = np.empty(e_raw.value, np.int64)
+        _lib.check(L.clane_edges_read(handle, src.ctypes.data, dst.ctypes.data), "clane_edges_read")
+    finally:
+        L.clane_edges_close(handle)
     return src, dst
 
 

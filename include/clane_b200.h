@@ -40,6 +40,10 @@ extern "C" {
 #define CLANE_ERANGE (-2)      /* edge endpoint outside [0, n) / size exceeds int32 indexing */
 #define CLANE_EWORKSPACE (-3)  /* caller-provided buffer too small */
 #define CLANE_ENODEVICE (-4)   /* no CUDA device / not an sm_100 class device */
+#define CLANE_ENOENT (-5)      /* file cannot be opened */
+#define CLANE_EPARSE (-6)      /* edge line without exactly one TAB */
+#define CLANE_EUNKNOWNID (-7)  /* edge endpoint that is not in V */
+#define CLANE_ENOMEM (-8)      /* host allocation failed */
 
 typedef void* clane_stream_t;  /* cudaStream_t */
 
@@ -70,6 +74,23 @@ int32_t     clane_padded_ld(int32_t d);
  * capacity e_raw.  Returns the number of coalesced edges E >= 0, or CLANE_E* (< 0). */
 int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t e_raw, int64_t n,
                              int32_t* h_rowptr, int32_t* h_col);
+
+/* Replaces the edge-file loop of Graph.__init__ (/root/reference/clane/graph.py:73-81):
+ *   lines = io.read().strip().split("\n"); src_id, dst_id = line.split("\t"); vertex_ids.index(id)
+ * -- text mode (universal newlines), the file's surrounding whitespace stripped, exactly one TAB
+ * per line, ids resolved to their FIRST position in V -- with a hash map and one file piece per
+ * thread instead of O(E*N) list.index calls.  v_ids = the n_vertices ids of V (parsed by the
+ * caller with the reference's own expression) joined by "\n", v_bytes long.  threads <= 0:
+ * all host threads.  On CLANE_EPARSE / CLANE_EUNKNOWNID *err_line is the 0-based line (the first
+ * offending one in file order, as the reference's loop would hit it) and err_text the
+ * reference's message / the unknown id; on CLANE_ENOENT err_text is the path.  The parsed
+ * (src, dst) position pairs, in file order with duplicates and self-loops kept, are copied out
+ * by clane_edges_read (capacity *e_raw each) and released by clane_edges_close. */
+typedef struct clane_edge_file clane_edge_file;
+int clane_edges_open(const char* v_ids, int64_t v_bytes, int64_t n_vertices, const char* e_path, int32_t threads,
+                     clane_edge_file** out, int64_t* e_raw, int64_t* err_line, char* err_text, int32_t err_cap);
+int clane_edges_read(const clane_edge_file* f, int64_t* h_src, int64_t* h_dst);
+int clane_edges_close(clane_edge_file* f);
 
 /* ---- plan: degree-sorted row blocks + scratch ----------------------------------------- */
 /* A plan holds, on the device, the schedule of the sweep over rows [row_lo, row_hi) of an

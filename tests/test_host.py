@@ -431,3 +431,98 @@ def test_sweep_program_covers_every_edge_in_order(d, lo, hi, hub):
         blk += (k[v] // 8 + 1) & ~1
     assert nblocks == len(seen_blocks)
     assert n_seg == sum(-(-(k[v] // 8) // 16) for v in hr)
+
+
+# ---------------------------------------------------------------------------------------------
+# native edge-file ingest (clane_edges_open) against the reference's own parsing expression
+# ---------------------------------------------------------------------------------------------
+def reference_parse(data_root):
+    """graph.py:44-45 and :73-81 of the reference, verbatim semantics (list.index replaced by a first-position
+    dict, which returns the same positions)."""
+    with open(data_root / "V", "r") as io:
+        vertex_ids = io.read().strip().split("\n")
+    with open(data_root / "E", "r") as io:
+        lines = io.read().strip().split("\n")
+    first = {}
+    for i, vid in enumerate(vertex_ids):
+        first.setdefault(vid, i)
+    src, dst = [], []
+    for line in lines:
+        src_id, dst_id = line.split("\t")
+        for k, out in ((src_id, src), (dst_id, dst)):
+            if k not in first:
+                raise ValueError(f"{k!r} is not in list")
+            out.append(first[k])
+    return vertex_ids, np.array(src, np.int64), np.array(dst, np.int64)
+
+
+def _write(tmp_path, v_bytes, e_bytes):
+    (tmp_path / "V").write_bytes(v_bytes)
+    (tmp_path / "E").write_bytes(e_bytes)
+    np.save(tmp_path / "C.npy", np.zeros((len(v_bytes.decode().strip().split("\n")), 4), np.float32))
+    return tmp_path
+
+
+@pytest.mark.parametrize("v,e", [
+    (b"a\nb\nc\n", b"a\tb\nb\tc\nc\ta\n"),
+    (b"a\nb\nc", b"\n\n  a\tb\r\nb\tc\rc\ta\r\n\r\n"),                  # CRLF, lone CR, surrounding whitespace
+    (b"x y\n\nz\nx y\n", b"x y\tz\n\tz\nz\t\nz\tx y\n"),                          # ids with spaces, the empty id, a repeated id
+    ("é\n日本\nq\n".encode(), "日本\té\nq\t日本".encode()),                 # non-ASCII ids
+    (b"0\n1\n2\n3\n", b"0\t1\n0\t1\n2\t2\n3\t0"),                         # duplicates and a self-loop are kept
+])
+def test_native_edge_ingest_matches_reference_expression(tmp_path, v, e):
+    root = _write(tmp_path, v, e)
+    ids, src, dst = reference_parse(root)
+    g = Graph(root, 4)
+    assert g.vertex_ids == ids and len(g.E) == len(src)
+    assert np.array_equal(g._raw_src, src) and np.array_equal(g._raw_dst, dst)
+
+
+@pytest.mark.parametrize("e,msg", [
+    (b"a\tb\nab\nb\tc", "not enough values to unpack (expected 2, got 1)"),
+    (b"a\tb\tc\nzz\tq", "too many values to unpack (expected 2)"),       # the FIRST bad line wins
+    (b"a\tb\n\nb\tc", "not enough values to unpack (expected 2, got 1)"),  # a blank line in the middle
+    (b"", "not enough values to unpack (expected 2, got 1)"),              # an empty E file, as upstream
+    (b"a\tb\nb\tzz\nyy\ta", "'zz' is not in list"),
+    (b"qq\tzz", "'qq' is not in list"),                                   # src is looked up before dst
+])
+def test_native_edge_ingest_errors_like_the_reference(tmp_path, e, msg):
+    root = _write(tmp_path, b"a\nb\nc\n", e)
+    with pytest.raises(ValueError) as ref:
+        reference_parse(root)
+    assert str(ref.value) == msg
+    with pytest.raises(ValueError) as ours:
+        Graph(root, 4)
+    assert str(ours.value) == msg
+
+
+def test_native_edge_ingest_large_file_many_pieces(tmp_path):
+    """~3 MB of edges: cut into one piece per host thread; mixed line terminators across the cuts."""
+    rng = np.random.default_rng(11)
+    n, e = 5000, 200000
+    ids = [f"node-{i * 7919 % 100003}" for i in range(n)]
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    term = np.array(["\n", "\r\n", "\r"])[rng.integers(0, 3, e)]
+    body = "".join(f"{ids[a]}\t{ids[b]}{t}" for a, b, t in zip(src, dst, term))
+    root = _write(tmp_path, ("\n".join(ids) + "\n").encode(), body.encode())
+    _, rs, rd = reference_parse(root)
+    g = Graph(root, 4)
+    assert np.array_equal(g._raw_src, rs) and np.array_equal(g._raw_dst, rd) and np.array_equal(rs, src)
+    # an unknown id deep inside the file: same error, whichever thread finds it
+    bad = body.replace(f"{ids[src[150000]]}\t{ids[dst[150000]]}", f"{ids[src[150000]]}\tnope", 1)
+    (tmp_path / "E").write_bytes(bad.encode())
+    with pytest.raises(ValueError, match="'nope' is not in list"):
+        Graph(root, 4)
+
+
+def test_native_edge_ingest_missing_file(tmp_path):
+    (tmp_path / "V").write_bytes(b"a\nb\n")
+    np.save(tmp_path / "C.npy", np.zeros((2, 4), np.float32))
+    with pytest.raises(FileNotFoundError):
+        Graph(tmp_path, 4)
+    L = _lib.lib()
+    h, n, line = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64()
+    err = ctypes.create_string_buffer(256)
+    assert L.clane_edges_open(b"a\nb", 3, 2, str(tmp_path / "E").encode(), 0, ctypes.byref(h), ctypes.byref(n),
+                              ctypes.byref(line), err, 256) == -5
+    assert err.value.decode().endswith("/E")
