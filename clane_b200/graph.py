@@ -17,6 +17,7 @@ without a CUDA device.
 from __future__ import annotations
 
 import ctypes
+import os
 import random
 from pathlib import Path
 
@@ -102,7 +103,8 @@ def _parse_edges(path: Path, vertex_ids):
     joined = "\n".join(vertex_ids).encode("utf-8")
     handle, e_raw, err_line = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64(-1)
     err = ctypes.create_string_buffer(512)
-    rc = L.clane_edges_open(joined, len(joined), len(vertex_ids), str(path).encode(), 0, ctypes.byref(handle),
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rc = L.clane_edges_open(joined, len(joined), len(vertex_ids), str(path).encode(), threads, ctypes.byref(handle),
                             ctypes.byref(e_raw), ctypes.byref(err_line), err, len(err))
     if rc == -6:                                # CLANE_EPARSE: the reference's tuple-unpacking error
         raise ValueError(err.value.decode("utf-8", "replace"))
