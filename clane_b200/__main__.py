@@ -53,15 +53,14 @@ def embedding(args):
         embedder = IterativeEmbedder(num_workers=args.num_workers, **common, **hparams["embedder"])
     else:
         embedder = Embedder(**common, **hparams["embedder"])
+    args.output_root.mkdir(parents=True, exist_ok=True)
+    if args.save_history:
+        # output_root/{outer}/Z_{sweep}.npy (__main__.py:73-82 of the reference) is written while the sweeps run:
+        # at products shape one sweep's Z is ~1 GB, and the reference keeps every one of them in memory until the end
+        embedder.history_root = args.output_root
     embedder.iterate()
 
     print("Saving the results.")
-    args.output_root.mkdir(parents=True, exist_ok=True)
-    if args.save_history:
-        for outer, history_Z in enumerate(embedder.history["Z"]):
-            args.output_root.joinpath(f'{outer}').mkdir(parents=True, exist_ok=True)
-            for sweep, Z in enumerate(history_Z):
-                np.save(args.output_root.joinpath(f'{outer}/Z_{sweep}.npy'), Z.cpu().numpy())
     np.save(args.output_root.joinpath('Z.npy'), g.Z.cpu().numpy())
     print(f"The embeddings are stored in {args.output_root.joinpath('Z.npy').absolute()}.")
 

@@ -10,6 +10,9 @@ is exactly the reference's (same sweep count, same Z).
 from __future__ import annotations
 
 import ctypes
+import queue
+import threading
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -19,6 +22,66 @@ from .graph import Graph
 from .similarity import Similarity
 
 Inf = float("inf")
+
+
+class SavedZ(object):
+    """History entry that lives on disk (streamed ``--save_history``): quacks like the tensor the reference keeps
+    in ``history["Z"]`` as far as its CLI uses it (``.cpu().numpy()``), and loads on demand."""
+
+    def __init__(self, path: Path) -> None:
+        self.path = Path(path)
+
+    def cpu(self):
+        return self
+
+    def numpy(self) -> np.ndarray:
+        return np.load(self.path)
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.load(self.path)
+        return a if dtype is None else a.astype(dtype)
+
+
+class HistoryWriter(object):
+    """Streams the per-sweep embeddings of ``--save_history`` to ``root/{outer}/Z_{sweep}.npy`` (the layout of
+    /root/reference/clane/__main__.py:73-82) while the sweeps run: each sweep's Z goes device -> one of three pinned
+    host buffers -> a writer thread, instead of accumulating N*d*4 bytes per sweep in host memory until the end."""
+
+    def __init__(self, root: Path, n: int, d: int) -> None:
+        self.root = Path(root)
+        self.free, self.work = queue.Queue(), queue.Queue()
+        for _ in range(3):
+            self.free.put(torch.empty([n, d], dtype=torch.float32).pin_memory())
+        self.error = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self) -> None:
+        while True:
+            item = self.work.get()
+            if item is None:
+                return
+            buf, path = item
+            try:
+                path.parent.mkdir(parents=True, exist_ok=True)
+                np.save(path, buf.numpy())
+            except Exception as exc:          # surfaced by close()
+                self.error = exc
+            self.free.put(buf)
+
+    def put(self, z_dev: torch.Tensor, outer: int, sweep: int) -> SavedZ:
+        """``z_dev`` [n, d] (a view of the padded device matrix), already final on the current stream's timeline."""
+        buf = self.free.get()                 # back-pressure: at most three sweeps in flight
+        buf.copy_(z_dev)                      # synchronous device -> pinned copy
+        path = self.root.joinpath(f"{outer}", f"Z_{sweep}.npy")
+        self.work.put((buf, path))
+        return SavedZ(path)
+
+    def close(self) -> None:
+        self.work.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
 
 
 class Embedder(object):
@@ -50,6 +113,8 @@ class Embedder(object):
         if save_history:
             self.history = {"Z": [], "loss_P": []}
         self.minimum_amount_updated_Z = Inf
+        self.history_root = None       # set (a directory) to stream history["Z"] to disk while iterating
+        self._history_writer = None
         self.verbose = True            # the reference prints `amount counter` per sweep (embedder.py:104)
         self.sweeps_per_call = []      # bookkeeping the parity tests read
         self.amounts_per_call = []
@@ -72,6 +137,16 @@ class Embedder(object):
         L = _lib.lib()
         S = g._device_state()
         prev = torch.empty_like(S.Z[0])
+        if self.save_history and self.history_root is not None:
+            self._history_writer = HistoryWriter(self.history_root, S.n, S.d)
+        try:
+            self._iterate(g, L, S, prev)
+        finally:
+            if self._history_writer is not None:
+                writer, self._history_writer = self._history_writer, None
+                writer.close()
+
+    def _iterate(self, g, L, S, prev):
         while True:
             prev.copy_(S.Z[S.cur])
             self.propagate()
@@ -119,7 +194,10 @@ class Embedder(object):
             S.stream.synchronize()
             st = _lib.Patience.from_buffer_copy(S.state_host.numpy().tobytes())
             if history_Z is not None:
-                history_Z.append(dst[:S.n, :S.d].cpu())
+                if self._history_writer is not None:
+                    history_Z.append(self._history_writer.put(dst[:S.n, :S.d], len(self.history['Z']), len(history_Z)))
+                else:
+                    history_Z.append(dst[:S.n, :S.d].cpu())
             if st.stop:
                 break
         done = int(st.sweeps)
