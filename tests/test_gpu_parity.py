@@ -427,3 +427,17 @@ def test_value_finish_small_and_ragged(n, d):
     out = torch.zeros(1, device="cuda")
     _lib.check(L.clane_l1_finish_values(plan.handle, p1.data_ptr(), vals.data_ptr(), out.data_ptr(), 0, 0, 0, s))
     assert np.float32(out.cpu().numpy()[0]) == O.l1_diff(a, b)
+
+
+def test_sharded_run_equals_single_gpu_when_two_gpus_are_present():
+    """tools/check_dist.py under torchrun (2 ranks, fused peer-store exchange): bit-identical to the single-GPU
+    run at four shapes.  Skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "tools" / "check_dist.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("sharded == single-GPU: True") == 4
