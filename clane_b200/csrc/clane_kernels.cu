@@ -312,8 +312,6 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.hubT = static_cast<float4*>(plan->d_hubT);
     p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
     p.st = d_state;
-    static const bool dbg_chain = getenv("CLANE_DEBUG_CHAIN") != nullptr;
-    p.dbg = dbg_chain ? 1 : 0;
     p.n_remote = 0;
     static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only
     for (int t = 0; t < 2 && plan->n_peers > 1 && !no_peer_stores; ++t)

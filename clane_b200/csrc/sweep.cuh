@@ -31,8 +31,6 @@
 //               that contiguous stream (one warp per (hub row, 32 columns), cp.async ring).  Columns in
 //               the sequential regime (>= 16*floor(d/16)) are parked raw and chained by one more warp.
 #pragma once
-#include <cstdio>
-
 #include "common.cuh"
 #include "program.cuh"
 
@@ -73,7 +71,6 @@ struct SweepParams {
     // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
     float* peer[kMaxPeers];
     int n_remote;
-    int dbg;                    // CLANE_DEBUG_CHAIN: device printf of the hub pipeline's timestamps
 };
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA
@@ -246,13 +243,6 @@ __device__ __forceinline__ void load_batch(float4 (&buf)[8], const int2* __restr
                                            unsigned long long keep) {
 #pragma unroll
     for (int i = 0; i < M; ++i) buf[i] = gather4(zb, mp[i].x, keep);
-}
-
-// sequential fma chain over M <= 4 buffer entries starting at OFF (a short row: k < 8, every column sequential)
-template <int M, int OFF>
-__device__ __forceinline__ void reduce_short(const float4 (&z)[8], const int2* __restrict__ mp, float4& acc) {
-#pragma unroll
-    for (int i = 0; i < M; ++i) fma4(__int_as_float(mp[i].y), z[OFF + i], acc);
 }
 
 __device__ __forceinline__ void cp_async16_hint(unsigned smem_addr, const void* gsrc, unsigned long long pol) {
@@ -552,25 +542,13 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
     __threadfence();
     __syncwarp();
-    if (lane == 0) {
-        const int old = atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
-        if (p.dbg && (t1.y >> kTaskHubShift) < 2 && old + 1 == ((nblk_row + 15) / 16) * p.nslab) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            printf("[dbg] hub %d last segment parked at %llu (block %d)\n", t1.y >> kTaskHubShift, t, blockIdx.x);
-        }
-    }
+    if (lane == 0) atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
 }
 
 __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        printf("[dbg] rows block %d start %llu\n", blockIdx.x, t);
-    }
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     int2* meta = reinterpret_cast<int2*>(mine);
     float* scratch = reinterpret_cast<float*>(meta + kMetaRing + 8);
@@ -633,7 +611,6 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
             if (t1 - t0 > kChainSpinNs) break;
         }
         ready = __syncthreads_and(ready);              // both warps agree
-        if (p.dbg && (hr < 2 || hr >= p.n_hub_rows - 2) && threadIdx.x == 0) printf("[dbg] chain hr %d slab %d start %llu ready %llu (%d)\n", hr, s, t0, t1, (int)ready);
         if (!ready) return;                            // the late pass does it
         __threadfence();                               // acquire: the parked blocks of every segment warp
     } else {
@@ -818,11 +795,6 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         for (int j = 0; j < p.n_remote; ++j) p.peer[j][off] = v;
     }
     if (kEarly && lane == 0) p.hub_done[cta] = 1;
-    if (kEarly && p.dbg && (hr < 2 || hr >= p.n_hub_rows - 2) && lane == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        printf("[dbg] chain hr %d slab %d end %llu blocks %d\n", hr, s, t, nblk);
-    }
 }
 
 // Fused mode: the level-0 partial of every group that was not swept by a single warp (it holds
