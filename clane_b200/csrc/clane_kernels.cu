@@ -324,7 +324,14 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
     const bool prof = plan->profile;
     if (prof) CLANE_CUDA(prof_record(plan->ev_prof[0], st));
-    static const bool overlap = getenv("CLANE_NO_CHAIN_OVERLAP") == nullptr;
+    // The early chain passes only help if the device runs them beside the row kernel; with a single hardware work
+    // queue (CUDA_DEVICE_MAX_CONNECTIONS=1) kernels of different streams run in submission order and the early pass
+    // would just spin into its time-out before every row kernel.
+    static const bool overlap = [] {
+        if (getenv("CLANE_NO_CHAIN_OVERLAP") != nullptr) return false;
+        const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        return !(q != nullptr && atoi(q) == 1);
+    }();
     const int per_row = plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0);
     const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
     if (chain_ctas > 0 && overlap) {   // early chain passes: beside the row kernel, waiting on its segment warps

@@ -88,7 +88,7 @@ __host__ __device__ constexpr size_t chain_smem_bytes(int stages) {
     return (size_t)stages * kChainGroup * 32 * sizeof(float4) + (size_t)stages * kChainGroup * sizeof(float2);
 }
 constexpr size_t kChainSmemBytes = chain_smem_bytes(kChainGroups);
-constexpr unsigned long long kChainSpinNs = 2000000ull;   // early chain pass: give up after 2 ms
+constexpr unsigned long long kChainSpinNs = 400000ull;    // early chain pass: give up after 0.4 ms (the late pass takes over)
 constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
 constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
 constexpr int kMaxStages = 128;                // mbarrier pairs per chain CTA
