@@ -330,6 +330,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     rc = build_program(h_rowptr, plan->fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, descs, blk0,
                        &plan->hub_blocks);
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
+    // the segments (8 neighbours per block, ~5 G neighbours/s while they are the only tasks running) come first in the
+    // row kernel; a chain CTA that has waited twice that long gives up and leaves its row to the late pass
+    plan->chain_spin_ns = std::min<unsigned long long>(5000000ull, 300000ull + (unsigned long long)(plan->hub_blocks * 8 * 0.4));
     plan->n_tasks = (int32_t)tasks.size();
     plan->n_descs = (int64_t)descs.size();
     PLAN_CUDA(cudaMalloc(&plan->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(SweepTask)));

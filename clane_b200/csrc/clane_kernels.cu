@@ -311,6 +311,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.hubS = static_cast<float4*>(plan->d_hubS); p.hubW = static_cast<float2*>(plan->d_hubW);
     p.hubT = static_cast<float4*>(plan->d_hubT);
     p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
+    p.chain_spin_ns = plan->chain_spin_ns;
     p.st = d_state;
     p.n_remote = 0;
     static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only

@@ -25,6 +25,7 @@ struct clane_plan {
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     void* d_hub_info = nullptr;        // int4 per hub row: {row, first edge, degree, first scratch block}
     int64_t hub_blocks = 0;            // 8-neighbour blocks of all hub rows
+    unsigned long long chain_spin_ns = 400000;   // early chain pass time-out: ~2x the expected time of all segment tasks
     int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it
     void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
     void* d_hubW = nullptr;            // float2[hub_blocks]      {w4, w6}

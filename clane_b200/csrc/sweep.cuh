@@ -66,6 +66,7 @@ struct SweepParams {
     int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
     int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
     int hub_first;              // first hub row of this chain launch
+    unsigned long long chain_spin_ns;   // early chain pass: give up waiting after this long (the late pass takes over)
     const clane_patience* st;
     // row-partitioned run: the other ranks' Znext buffers (peer memory over NVLink); every finished row is
     // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
@@ -88,7 +89,6 @@ __host__ __device__ constexpr size_t chain_smem_bytes(int stages) {
     return (size_t)stages * kChainGroup * 32 * sizeof(float4) + (size_t)stages * kChainGroup * sizeof(float2);
 }
 constexpr size_t kChainSmemBytes = chain_smem_bytes(kChainGroups);
-constexpr unsigned long long kChainSpinNs = 400000ull;    // early chain pass: give up after 0.4 ms (the late pass takes over)
 constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
 constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
 constexpr int kMaxStages = 128;                // mbarrier pairs per chain CTA
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
             if (*cnt >= expect) { ready = true; break; }
             __nanosleep(200);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > kChainSpinNs) break;
+            if (t1 - t0 > p.chain_spin_ns) break;
         }
         ready = __syncthreads_and(ready);              // both warps agree
         if (!ready) return;                            // the late pass does it
