@@ -388,6 +388,19 @@ def run_gpu(args):
                                "wall clock, max over ranks; upload, plan build, build_P and the download are inside the "
                                "timed region and amortised over the steps of the call"}
         del r2
+        if not args.no_converge:
+            # time-to-converge of the sharded Embedder.iterate() (build_P calls + sweeps + patience on every rank)
+            r3 = cdist.ShardedSweeper(g, sim, GAMMA, tol=10, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            spc, _ = r3.iterate()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            line["time_to_converge"] = {"seconds": float(dt.item()), "outer_iterations": len(spc), "sweeps": int(sum(spc)),
+                                        "sweeps_per_call": spc, "tolerence": 10}
+            del r3
 
     if not args.no_converge and world == 1:
         g.set_Z(g.X)

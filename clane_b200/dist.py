@@ -231,5 +231,46 @@ class ShardedSweeper:
     def last_amount(self) -> float:
         return float(self.amount.cpu()[0])
 
+    # -- the reference's loops, replicated on every rank (never broadcast: the amounts are bit-identical) ----
+    def propagate(self, max_sweeps: int = 0) -> list:
+        """One Embedder.propagate() call (/root/reference/clane/embedder.py:71-108): build_P once, then sweeps
+        until the strict-minimum patience counter reaches 0.  Returns the per-sweep L1 amounts.  The counter
+        runs on the host here (one scalar read per sweep: microseconds against a multi-millisecond sharded
+        sweep), on fp32 values, exactly as the reference compares them."""
+        self.build_p()
+        minimum, patience, amounts = np.float32(np.inf), self.tol, []
+        while True:
+            self.sweep(True)
+            amount = np.float32(self.amount.cpu().numpy()[0])
+            amounts.append(amount)
+            if minimum > amount:
+                patience, minimum = self.tol, amount
+            else:
+                patience -= 1
+            if patience == 0 or (max_sweeps and len(amounts) >= max_sweeps):
+                return amounts
+
+    def iterate(self, max_outer: int = 0):
+        """Embedder.iterate() (embedder.py:56-69).  Returns (sweeps per propagate() call, outer amounts)."""
+        L = _lib.lib()
+        minimum, patience = np.float32(np.inf), self.tol
+        sweeps_per_call, outer_amounts = [], []
+        prev = torch.empty_like(self.Z[0])
+        outer = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        while True:
+            prev.copy_(self.Z[self.cur])
+            sweeps_per_call.append(len(self.propagate()))
+            # every rank holds the full Z after the sweep's all-reduce: the outer L1 needs no exchange
+            _lib.check(L.clane_l1_diff(self.plan.handle, self.Z[self.cur].data_ptr(), prev.data_ptr(), outer.data_ptr(),
+                                       _lib.stream_handle()), "clane_l1_diff")
+            amount = np.float32(outer.cpu().numpy()[0])
+            outer_amounts.append(amount)
+            if minimum > amount:
+                patience, minimum = self.tol, amount
+            else:
+                patience -= 1
+            if patience == 0 or (max_outer and len(sweeps_per_call) >= max_outer):
+                return sweeps_per_call, outer_amounts
+
     def Z_host(self) -> torch.Tensor:
         return self.Z[self.cur][:self.n, :self.d].cpu()

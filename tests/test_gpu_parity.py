@@ -440,4 +440,4 @@ def test_sharded_run_equals_single_gpu_when_two_gpus_are_present():
            "--master-port", "29533", str(ROOT / "tools" / "check_dist.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("sharded == single-GPU: True") == 4
+    assert r.stdout.count("sharded == single-GPU: True") == 5

@@ -36,5 +36,20 @@ for shape, scale in (("arxiv", 0.3), ("products", 0.01), ("pubmed", 1.0), ("cora
     if rank == 0:
         print(f"{shape} x{scale}: n={n} e={g._nnz} world={world} sharded == single-GPU: {bool(t.item())}", flush=True)
     ok &= bool(t.item())
+# the whole iterate() loop, sharded vs single GPU: same sweep counts per call, same final embeddings
+n, src, dst, X = synth.make_graph("arxiv", seed=1, scale=0.05)
+g = Graph.from_arrays(n, src, dst, X)
+sw = cdist.ShardedSweeper(g, similarity.CosineSimilarity(), 0.76, tol=3, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
+spc, outer_amounts = sw.iterate()
+g1 = Graph.from_arrays(n, src, dst, X)
+e = Embedder(g1, similarity.CosineSimilarity(), device=torch.device("cuda", lr), gamma=0.76, tolerence=3)
+e.verbose = False
+e.iterate()
+same = spc == e.sweeps_per_call and np.array_equal(sw.Z_host().numpy(), g1.Z.numpy())
+t = torch.tensor([int(same)], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"iterate(): outer={len(spc)} sweeps={sum(spc)} world={world} sharded == single-GPU: {bool(t.item())}", flush=True)
+ok &= bool(t.item())
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
