@@ -310,6 +310,7 @@ def run_gpu(args):
     total_ms = timed_loop(args.steps)                                  # the metric: whole steps
     kern = kernel_loop(min(args.steps, 200))                           # per-kernel durations (roofline)
     phases = None
+    exch = runner.exchange if runner is not None else "none"
     if runner is not None:                                             # phases of a sharded sweep (events, this rank)
         runner.timing, runner.phase_ms = True, {}
         for i in range(min(args.steps, 20)):
@@ -335,7 +336,9 @@ def run_gpu(args):
                    "parallelism": "single GPU" if world == 1 else
                    f"rows partitioned by contiguous id over {world} GPUs; exchange: " +
                    ("every finished row stored to all ranks' Z (NVLink peer memory) from inside the sweep kernel, "
-                    "one all-reduce of the L1 slots per sweep" if runner.exchange == "p2p"
+                    "one all-reduce of the L1 slots per sweep" + (" (multimem.st through the NVSwitch multicast mapping)"
+                                                                 if exch == "multicast" else "")
+                    if exch in ("p2p", "multicast")
                     else "NCCL all-gather of Z per sweep"),
                    "l2": f"no flush: working set {(3 * n * d * 4 + 8 * e) / 1e6:.0f} MB exceeds the 126 MB L2"
                          if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",

@@ -315,8 +315,10 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.st = d_state;
     p.n_remote = 0;
     static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only
+    p.mc = nullptr;
     for (int t = 0; t < 2 && plan->n_peers > 1 && !no_peer_stores; ++t)
         if (plan->peers[t][plan->self_rank] == d_Znext) {
+            if (plan->mc[t] != nullptr) { p.mc = plan->mc[t]; continue; }   // one multicast store instead of n - 1 unicast ones
             for (int r = 0; r < plan->n_peers; ++r)
                 if (r != plan->self_rank) p.peer[p.n_remote++] = plan->peers[t][r];
         }
@@ -478,6 +480,15 @@ int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, c
         plan->peers[1][r] = reinterpret_cast<float*>(h_ptrs_b[r]);
     }
     for (auto& g : plan->graphs)   // cached sweeps were captured with the old peer set
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    return CLANE_OK;
+}
+
+int clane_plan_set_multicast(clane_plan* plan, uint64_t mc_a, uint64_t mc_b) {
+    if (!plan) return CLANE_EINVAL;
+    plan->mc[0] = reinterpret_cast<float*>(mc_a);
+    plan->mc[1] = reinterpret_cast<float*>(mc_b);
+    for (auto& g : plan->graphs)
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     return CLANE_OK;
 }

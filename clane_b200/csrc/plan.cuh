@@ -37,6 +37,7 @@ struct clane_plan {
     // row-partitioned run: peer Znext buffers for the two Z ping-pong buffers (entry self = own buffer)
     int32_t n_peers = 0, self_rank = 0;
     float* peers[2][16] = {};
+    float* mc[2] = {nullptr, nullptr};   // multicast (NVLS) addresses of the two buffers, or null
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
     // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between

@@ -72,6 +72,7 @@ struct SweepParams {
     // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
     float* peer[kMaxPeers];
     int n_remote;
+    float* mc;                  // multicast (NVLS) address of Znext: one store reaches every rank; replaces peer[]
 };
 
 constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA
@@ -149,6 +150,15 @@ __device__ __forceinline__ void cp_async8_sa(unsigned smem_addr, const void* gsr
 __device__ __forceinline__ void cp_async4_sa(unsigned smem_addr, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
+// one store, replicated by the NVSwitch into every rank's buffer (multicast mapping of symmetric memory)
+__device__ __forceinline__ void multimem_st4(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st1(float* mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // mbarriers of the hub chain's producer / consumer ring
@@ -378,6 +388,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
         const float4 out = finish_row(xv, acc, p.gamma);
         if (active) {
             st_stream4(p.Zn + row_off, out);
+            if (p.mc != nullptr) multimem_st4(p.mc + row_off, out);
             for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
         }
         if (kDirect) {
@@ -770,6 +781,7 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         const size_t off = (size_t)row * p.ld + col;
         const float v = fadd(xv, fmul(p.gamma, acc));
         p.Zn[off] = v;
+        if (p.mc != nullptr) multimem_st1(p.mc + off, v);
         for (int j = 0; j < p.n_remote; ++j) p.peer[j][off] = v;
     }
     if (kEarly && lane == 0) p.hub_done[cta] = 1;

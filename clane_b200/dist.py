@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -149,7 +150,7 @@ class ShardedSweeper:
         available, plain device memory + NCCL all-gather otherwise."""
         L = _lib.lib()
         self.symm = None
-        if exchange in ("auto", "p2p") and self.world > 1:
+        if exchange in ("auto", "p2p", "multicast") and self.world > 1:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 bufs = [symm_mem.empty((npad, ld), dtype=torch.float32, device=self.dev) for _ in range(2)]
@@ -162,6 +163,10 @@ class ShardedSweeper:
                 _lib.check(L.clane_plan_set_peers(self.plan.handle, self.world, self.rank, ptrs[0], ptrs[1]),
                            "clane_plan_set_peers")
                 self.Z, self.symm = bufs, hdls
+                mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in hdls]
+                if exchange != "p2p" and os.environ.get("CLANE_NO_MULTICAST") is None and all(mc):
+                    _lib.check(L.clane_plan_set_multicast(self.plan.handle, mc[0], mc[1]), "clane_plan_set_multicast")
+                    return "multicast"
                 return "p2p"
             except Exception as exc:       # no VMM / fabric handles on this box: fall back to NCCL
                 if exchange == "p2p":
@@ -202,7 +207,7 @@ class ShardedSweeper:
             mark("all_gather")
         vals = self.p1[(self.n1 + 2) * 32:]
         if with_l1:
-            if self.exchange == "p2p" and not self.aligned:
+            if self.exchange in ("p2p", "multicast") and not self.aligned:
                 dist.all_reduce(self.sync_token)       # every rank's rows have landed before the full-array pass
             self.p1.zero_()
             _lib.check(L.clane_l1_partial(self.plan.handle, zn.data_ptr(), zc.data_ptr(), self.nlo, self.nhi,
@@ -218,7 +223,7 @@ class ShardedSweeper:
                                                 self.amount.data_ptr(), 0, 0, 0, s), "clane_l1_finish_values")
             mark("finish")
             launches += 3
-        elif self.exchange == "p2p":
+        elif self.exchange in ("p2p", "multicast"):
             dist.all_reduce(self.sync_token)           # order the ranks between sweeps
         self.cur ^= 1
         if marks is not None:

@@ -224,6 +224,12 @@ int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, f
 int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
                          const uint64_t* h_ptrs_b);
 
+/* Optional, after clane_plan_set_peers: the multicast (NVLS) addresses of the two Z buffers (e.g.
+ * torch symmetric memory's multicast_ptr; 0 = none).  The sweep then reaches all ranks with one
+ * multimem.st per finished row piece (replicated inside the NVSwitch) instead of n_peers - 1
+ * unicast stores; the local buffer is still written directly. */
+int clane_plan_set_multicast(clane_plan* plan, uint64_t mc_a, uint64_t mc_b);
+
 /* Measurement aid: when enabled, clane_sweep brackets its kernels with CUDA events on the
  * streams they are launched on; clane_plan_profile_read waits for the last sweep and returns
  * h_ms[0] = row kernel (k_sweep_rows), h_ms[1] = whole sweep, h_ms[2] = exact L1 tail (fix-up,
