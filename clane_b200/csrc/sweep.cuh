@@ -363,7 +363,6 @@ __device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int i
 // span task: one batch per round -- descriptor, <= 10 loads straight into registers, reduction.  A warp has one
 // batch of loads in flight; the memory-level parallelism comes from the resident warps per SM (measured with
 // tools/l1pf_probe.cu: deeper per-warp pipelines or L1 / L2 prefetching do not beat more warps).
-template <bool kDirect>
 __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, const int4 t1, int slab, int lane,
                                          int2* meta, float* scratch, float4* slots) {
     const int c0 = slab * 128 + lane * 4;
@@ -371,6 +370,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
     const bool col_blocked = c0 < p.limit;
     const int cc = active ? c0 : 0;            // idle lanes shadow lane 0 (same sectors: no extra traffic)
     const int r0 = t1.x;
+    const bool direct = (t1.y & kTaskDirect) != 0;   // runtime, not a template: one copy of the code in the instruction cache
     Streams s;
     s.desc_first = t0.x; s.nb = t0.y; s.e_first = t0.z; s.e_total = t0.w;
     open_streams(p, s, lane, meta);
@@ -391,7 +391,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
             if (p.mc != nullptr) multimem_st4(p.mc + row_off, out);
             for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
         }
-        if (kDirect) {
+        if (direct) {
             const float4 dl = active ? absdiff4(out, ov) : make_float4(0.f, 0.f, 0.f, 0.f);
             chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
         }
@@ -424,7 +424,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
         }
         if (last_s) {
             cp_async16_cg(slot_sa + 8 * 512, p.X + row_off_s);
-            if (kDirect) cp_async16_cg(slot_sa + 9 * 512, p.Zc + row_off_s);
+            if (direct) cp_async16_cg(slot_sa + 9 * 512, p.Zc + row_off_s);
         }
         cp_async_commit();
         // ---- even batch: registers; loads and reduction in the same switch case ----
@@ -434,7 +434,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
         // the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch here
         // would make ptxas wait for them at the join, before the gathers are even issued)
         ldg4_stream_if(xs, p.X + row_off, last);
-        if (kDirect) ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last);
+        ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last && direct);
         switch (idr & 15) {
             case 8: load_batch<8>(A, mp, zb); reduce_batch<8>(A, mp, acc, col_blocked); break;
             case 7: load_batch<7>(A, mp, zb); reduce_batch<7>(A, mp, acc, col_blocked); break;
@@ -463,7 +463,7 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
         }
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
-    if (kDirect && p.fuse) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
+    if (direct && p.fuse) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
 }
 
 // hub segment task: up to 16 full 8-blocks of one hub row; park {z6, z4, X, Y} per (block, column), or the
@@ -550,8 +550,7 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
     prefetch_task(p, ti + kPrefetchAhead, slab, lane);
     if (t1.y & kTaskSegment) run_segment(p, t0, t1, slab, lane, meta);
-    else if (t1.y & kTaskDirect) run_span<true>(p, t0, t1, slab, lane, meta, scratch, slots);
-    else run_span<false>(p, t0, t1, slab, lane, meta, scratch, slots);
+    else run_span(p, t0, t1, slab, lane, meta, scratch, slots);
 }
 
 // ------------------------------------------------------------------------------------------
