@@ -342,7 +342,7 @@ __device__ __forceinline__ void open_streams(const SweepParams& p, Streams& s, i
 __device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int ib, int lane, int2* meta) {
     const bool roll = (ib & 31) == 0 && ib > 0;
     if (roll) { s.dwin = s.dnext; s.dnext = 0; }
-    ldg_i32_if(s.dnext, p.descs + s.desc_first + ib + 32 + lane, roll && ib + 32 + lane < s.nb);
+    ldg_i32_if(s.dnext, p.descs + (s.desc_first + ib + 32 + lane), roll && ib + 32 + lane < s.nb);   // int index first: one IMAD.WIDE
     const int id = __shfl_sync(kFull, s.dwin, ib & 31);
     const bool pub = (id & kDescPub) != 0;
     if (pub) {
@@ -355,8 +355,9 @@ __device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int i
     }
     const int off = s.win_q * 32 + lane;
     const bool fetch = pub && off < s.e_total;
-    ldg_i32_if(s.pc, p.coloff + s.e_first + off, fetch);
-    ldg_f32_if(s.pw, p.w + s.e_first + off, fetch);
+    const int eidx = s.e_first + off;
+    ldg_i32_if(s.pc, p.coloff + eidx, fetch);
+    ldg_f32_if(s.pw, p.w + eidx, fetch);
     return id;
 }
 
