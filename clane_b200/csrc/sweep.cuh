@@ -265,32 +265,6 @@ __device__ __forceinline__ void reduce_batch(const float4 (&z)[8], const int2* _
     }
 }
 
-// Warm L2 with what a later task needs first: its descriptors, the head of its (offset, w) stream, its X
-// rows and -- fused L1 -- its own Zcur rows.  Called by the warp that runs `kPrefetchAhead` places earlier
-// in the schedule: those cold, streaming reads are otherwise serial DRAM round trips at the start of a task.
-constexpr int kPrefetchAhead = 2048;
-__device__ __forceinline__ void prefetch_task(const SweepParams& p, int ti, int slab, int lane) {
-    if (ti >= p.n_tasks) return;
-    const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
-    const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
-    const int desc_first = t0.x, nb = t0.y, e_first = t0.z, e_total = t0.w, r0 = t1.x, flags = t1.y;
-    if (lane < 4) {   // first 128 edges of the stream
-        if (lane * 32 < e_total) { prefetch_l2(p.coloff + e_first + lane * 32); prefetch_l2(p.w + e_first + lane * 32); }
-    } else if (lane < 8) {
-        if ((lane - 4) * 32 < nb) prefetch_l2(p.descs + desc_first + (lane - 4) * 32);
-    }
-    if (flags & kTaskSegment) return;
-    // rows: lane -> (row lane / 4, 128-byte line lane % 4) of the slab
-    const int nrows = flags & 0xff;
-    const int line = lane & 3;
-    if (slab * 128 + line * 32 < p.ld)
-        for (int r = lane >> 2; r < nrows; r += 8) {
-            const size_t off = (size_t)(r0 + r) * p.ld + slab * 128 + line * 32;
-            prefetch_l2(p.X + off);
-            if (flags & kTaskDirect) prefetch_l2(p.Zc + off);
-        }
-}
-
 // ------------------------------------------------------------------------------------------
 // row kernel: one warp per (task, 128-column slab)
 // ------------------------------------------------------------------------------------------
@@ -549,7 +523,6 @@ __global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(Sweep
     if (ti >= p.n_tasks) return;
     const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
-    prefetch_task(p, ti + kPrefetchAhead, slab, lane);
     if (t1.y & kTaskSegment) run_segment(p, t0, t1, slab, lane, meta);
     else run_span(p, t0, t1, slab, lane, meta, scratch, slots);
 }
