@@ -75,8 +75,11 @@ struct SweepParams {
     float* mc;                  // multicast (NVLS) address of Znext: one store reaches every rank; replaces peer[]
 };
 
-constexpr int kRowThreads = 128;               // row kernel: 4 warps per CTA
-constexpr int kRowWarps = 4;
+#ifndef CLANE_ROW_WARPS
+#define CLANE_ROW_WARPS 2
+#endif
+constexpr int kRowWarps = CLANE_ROW_WARPS;     // row kernel: warps (= tasks) per CTA
+constexpr int kRowThreads = 32 * kRowWarps;
 // row kernel shared memory per warp: (offset, w) ring | 512-byte transpose scratch (fused L1) | 10 row-piece slots
 // (8 neighbours + X + own Zcur) of the batch that goes through cp.async
 constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512 + 10 * 512;
@@ -509,7 +512,7 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     if (lane == 0) atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
 }
 
-__global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC) k_sweep_rows(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC * 4 / kRowWarps) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
