@@ -316,10 +316,14 @@ __device__ __forceinline__ void open_streams(const SweepParams& p, Streams& s, i
 }
 
 // descriptor of batch ib; afterwards the (offset, w) ring holds the batch's edges
+// kMayRoll = false for odd batch indices: the 32-descriptor window only rolls over at multiples of 32
+template <bool kMayRoll>
 __device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int ib, int lane, int2* meta) {
-    const bool roll = (ib & 31) == 0 && ib > 0;
-    if (roll) { s.dwin = s.dnext; s.dnext = 0; }
-    ldg_i32_if(s.dnext, p.descs + (s.desc_first + ib + 32 + lane), roll && ib + 32 + lane < s.nb);   // int index first: one IMAD.WIDE
+    if (kMayRoll) {
+        const bool roll = (ib & 31) == 0 && ib > 0;
+        if (roll) { s.dwin = s.dnext; s.dnext = 0; }
+        ldg_i32_if(s.dnext, p.descs + (s.desc_first + ib + 32 + lane), roll && ib + 32 + lane < s.nb);   // int index first: one IMAD.WIDE
+    }
     const int id = __shfl_sync(kFull, s.dwin, ib & 31);
     const bool pub = (id & kDescPub) != 0;
     if (pub) {
@@ -382,9 +386,9 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, co
     // order.  (Two register buffers would cost 32 more registers, i.e. a fifth of the resident warps; and ptxas
     // tracks all 128-bit loads of a warp on one scoreboard, so waiting for the first would wait for both anyway.)
     for (int cb = 0; cb < nb; cb += 2) {
-        const int idr = next_desc(p, s, cb, lane, meta);
+        const int idr = next_desc<true>(p, s, cb, lane, meta);
         const bool has_s = cb + 1 < nb;
-        const int ids = has_s ? next_desc(p, s, cb + 1, lane, meta) : 0;
+        const int ids = has_s ? next_desc<false>(p, s, cb + 1, lane, meta) : 0;
         // ---- odd batch: cp.async ----
         const int2* mps = meta + ((ids >> kDescMetaShift) & 127);
         const int row_off_s = (r0 + ((ids >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
