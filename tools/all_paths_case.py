@@ -1,4 +1,4 @@
-"""compute-sanitizer target: small graphs through every kernel path (spans, paired/ordinary batches, hub segments,
+"""Small graphs through every kernel path (spans, paired/ordinary batches, hub segments,
 heavy and light chains, sequential-regime columns, fused and cascade L1, build_P)."""
 import sys
 from pathlib import Path
