@@ -155,7 +155,7 @@ int clane_plan_destroy(clane_plan* plan) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct Batch { int m, last, row, u, m2 = 0, row2 = 0; };   // m2 > 0: a second short row rides in the same batch
+struct Batch { int m, last, row, u; };
 
 // Descriptors of a task's batches.  The kernel has one batch of loads in flight per warp;
 // the only other decision is when the next 32-edge (offset, w) window is published to the warp's 4-window
@@ -166,10 +166,9 @@ void emit_descriptors(const std::vector<Batch>& bs, int e_total, std::vector<int
     int published = 2;
     for (const Batch& b : bs) {
         int pub = 0;
-        const int touched = (b.u + b.m + b.m2 - 1) / 32;
+        const int touched = (b.u + b.m - 1) / 32;
         if (touched + 1 >= published && published * 32 < e_total) { pub = 1; ++published; }
         out.push_back(b.m | (b.last ? kDescLast : 0) | (pub ? kDescPub : 0) | (b.row << kDescRowShift) |
-                      (b.m2 << kDescM2Shift) | ((b.m2 ? b.row2 - b.row : 0) << kDescRow2Shift) |
                       ((b.u & (kMetaRing - 1)) << kDescMetaShift));
     }
 }
@@ -204,19 +203,6 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
             bs.clear();
             for (int32_t r = 0; r < nrows; ++r) {
                 const int32_t a = h_rowptr[r0 + r], k = h_rowptr[r0 + r + 1] - a;
-                if (k >= 1 && k <= kPairMax) {
-                    // two short rows share one batch (one round trip instead of two): the next non-sink row
-                    int32_t r2 = r + 1;
-                    while (r2 < nrows && h_rowptr[r0 + r2 + 1] == h_rowptr[r0 + r2]) ++r2;
-                    const int32_t k2 = r2 < nrows ? h_rowptr[r0 + r2 + 1] - h_rowptr[r0 + r2] : 0;
-                    if (k2 >= 1 && k2 <= kPairMax) {
-                        Batch b{k, 1, r, a - e0};
-                        b.m2 = k2; b.row2 = r2;
-                        bs.push_back(b);
-                        r = r2;
-                        continue;
-                    }
-                }
                 for (int32_t pos = 0; pos < k; pos += 8) {
                     const int32_t m = std::min(8, k - pos);
                     bs.push_back(Batch{m, pos + m >= k, r, a + pos - e0});

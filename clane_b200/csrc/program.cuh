@@ -30,10 +30,7 @@ constexpr int kTaskHubShift = 10;
 constexpr int kDescLast = 1 << 4;
 constexpr int kDescPub = 1 << 5;
 constexpr int kDescRowShift = 6;      // 5 bits
-constexpr int kDescM2Shift = 11;      // 3 bits: neighbours of a second short row sharing the batch (0: none)
-constexpr int kDescRow2Shift = 14;    // 5 bits: its row, relative to the first row
 constexpr int kDescMetaShift = 19;    // 7 bits
-constexpr int kPairMax = 0;           // rows of <= kPairMax neighbours are paired (0: off -- measured no gain)
 
 constexpr int kMaxPeers = 15;                  // remote ranks of a row-partitioned run (one NVLink domain)
 constexpr int kLongBlocks = 128;               // hub rows of >= 1024 neighbours take the heavy chain kernel

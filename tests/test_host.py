@@ -349,31 +349,25 @@ def emulate_task(task, descs):
         return idesc
 
     def issue(idesc):       # what the loads of this batch fetch
-        m, mi, m2 = idesc & 15, (idesc >> 19) & 127, (idesc >> 11) & 7
-        assert 1 <= m <= 8 and m + m2 <= 8
+        m, mi = idesc & 15, (idesc >> 19) & 127
+        assert 1 <= m <= 8 and (idesc >> 11) & 0xff == 0
         u = meta[mi]
         assert u is not None and u % 128 == mi
-        for i in range(m + m2):
+        for i in range(m):
             assert meta[mi + i] == u + i, "(offset, w) ring does not hold the batch's edges"
         row = r0 + ((idesc >> 6) & 31) if idesc & 16 else None
-        if m2:              # a second short row in the same batch: both rows complete, both <= 4 neighbours
-            assert idesc & 16 and m <= 4 and m2 <= 4
-        return [e_first + u + i for i in range(m + m2)], row
+        return [e_first + u + i for i in range(m)], row
 
     def consume(idesc, loaded):
-        m, mi, m2 = idesc & 15, (idesc >> 19) & 127, (idesc >> 11) & 7
+        m, mi = idesc & 15, (idesc >> 19) & 127
         edges, row = loaded
-        for i in range(m + m2):     # the weights are read from the ring after the loads: it must still hold them
+        for i in range(m):          # the weights are read from the ring after the loads: it must still hold them
             assert e_first + meta[mi + i] == edges[i]
-        cur.extend(edges[:m])
+        cur.extend(edges)
         if idesc & 16:
             assert row is not None and row < r0 + nrows
             out.append((row, list(cur)))
             cur.clear()
-        if m2:
-            row2 = row + ((idesc >> 14) & 31)
-            assert row < row2 < r0 + nrows
-            out.append((row2, edges[m:]))
 
     out, cur = [], []
     for cb in range(nb):    # one batch per round: descriptor, loads, reduction
