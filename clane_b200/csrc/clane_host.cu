@@ -5,7 +5,11 @@
 //   graph.py:130-138  Graph.Z / set_Z                  -> clane_session_get_z / set_z
 //   embedder.py:71-108 Embedder.propagate              -> clane_session_propagate
 //   embedder.py:56-69  Embedder.iterate                -> clane_session_iterate
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +21,34 @@
 #include "plan.cuh"
 #include "program.cuh"
 
+namespace {
+
+// host threads this process may run on (its affinity mask), capped by the amount of work
+int host_threads(int64_t work_units) {
+    int n = 1;
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+#else
+    n = (int)std::thread::hardware_concurrency();
+#endif
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n, 64), work_units));
+}
+
+// fn(lo, hi) over [0, total) cut into one contiguous chunk per thread
+template <class F>
+void parallel_chunks(int64_t total, int nthreads, F&& fn) {
+    if (nthreads <= 1 || total < 2) { fn(0, total); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
+        if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+}  // namespace
+
 extern "C" {
 
 int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t e_raw, int64_t n, int32_t* h_rowptr,
@@ -24,28 +56,40 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
     if (e_raw < 0 || n < 0 || !h_rowptr || (e_raw > 0 && (!h_src || !h_dst || !h_col))) return CLANE_EINVAL;
     if (n > INT32_MAX || e_raw > INT32_MAX) return CLANE_ERANGE;
     try {
-        // counting sort by source, then sort + unique each row's destinations: the order
-        // torch's coalesce() produces (row-major, ascending column, duplicates merged).
-        std::vector<int64_t> start((size_t)n + 1, 0);
+        // counting sort by source, then sort + unique each row's destinations: the order torch's coalesce()
+        // produces (row-major, ascending column, duplicates merged).  The two edge passes are sequential (random
+        // per-row counters: atomics across threads measured slower than one thread); the row passes -- sort, unique,
+        // compaction -- run on all host threads over equal chunks of rows.
+        const int nt = host_threads(n / 65536 + 1);
+        std::vector<int32_t> start((size_t)n + 2, 0), fill, uniq((size_t)n + 1, 0);
+        std::vector<int32_t> tmp((size_t)std::max<int64_t>(e_raw, 1));
         for (int64_t e = 0; e < e_raw; ++e) {
             const int64_t s = h_src[e], t = h_dst[e];
             if (s < 0 || s >= n || t < 0 || t >= n) return CLANE_ERANGE;
             start[(size_t)s + 1]++;
         }
         for (int64_t v = 0; v < n; ++v) start[(size_t)v + 1] += start[(size_t)v];
-        std::vector<int64_t> fill(start.begin(), start.end() - 1);
-        std::vector<int32_t> tmp((size_t)std::max<int64_t>(e_raw, 1));
+        fill.assign(start.begin(), start.begin() + n + 1);
         for (int64_t e = 0; e < e_raw; ++e) tmp[(size_t)fill[(size_t)h_src[e]]++] = (int32_t)h_dst[e];
+        parallel_chunks(n, nt, [&](int64_t lo, int64_t hi) {
+            for (int64_t v = lo; v < hi; ++v) {
+                int32_t* a = tmp.data() + start[(size_t)v];
+                int32_t* b = tmp.data() + start[(size_t)v + 1];
+                if (b - a > 1) std::sort(a, b);
+                uniq[(size_t)v] = (int32_t)(std::unique(a, b) - a);
+            }
+        });
         int64_t out = 0;
         h_rowptr[0] = 0;
         for (int64_t v = 0; v < n; ++v) {
-            int32_t* a = tmp.data() + start[(size_t)v];
-            int32_t* b = tmp.data() + start[(size_t)v + 1];
-            if (b - a > 1) std::sort(a, b);
-            for (int32_t* p = a; p < b; ++p)
-                if (p == a || *p != *(p - 1)) h_col[out++] = *p;
+            out += uniq[(size_t)v];
             h_rowptr[v + 1] = (int32_t)out;
         }
+        parallel_chunks(n, nt, [&](int64_t lo, int64_t hi) {
+            for (int64_t v = lo; v < hi; ++v)
+                if (uniq[(size_t)v])
+                    memcpy(h_col + h_rowptr[v], tmp.data() + start[(size_t)v], (size_t)uniq[(size_t)v] * sizeof(int32_t));
+        });
         return out;
     } catch (const std::bad_alloc&) {
         return (int64_t)cudaErrorMemoryAllocation;
