@@ -35,15 +35,26 @@ int host_threads(int64_t work_units) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n, 64), work_units));
 }
 
-// fn(lo, hi) over [0, total) cut into one contiguous chunk per thread
+// fn(lo, hi, t) over [0, total) cut into one contiguous chunk per thread t (the cut depends only on total and nthreads)
 template <class F>
 void parallel_chunks(int64_t total, int nthreads, F&& fn) {
-    if (nthreads <= 1 || total < 2) { fn(0, total); return; }
+    if (nthreads <= 1 || total < 2) { fn((int64_t)0, total, 0); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) {
         const int64_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
-        if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+        th.emplace_back([&fn, lo, hi, t] { if (lo < hi) fn(lo, hi, t); });
     }
+    for (auto& x : th) x.join();
+}
+
+// fn(i) for every i in [0, total), items handed out dynamically (uneven items: buckets of a power-law graph)
+template <class F>
+void parallel_items(int64_t total, int nthreads, F&& fn) {
+    if (nthreads <= 1 || total < 2) { for (int64_t i = 0; i < total; ++i) fn(i); return; }
+    std::atomic<int64_t> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&] { for (int64_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < total;) fn(i); });
     for (auto& x : th) x.join();
 }
 
@@ -56,27 +67,68 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
     if (e_raw < 0 || n < 0 || !h_rowptr || (e_raw > 0 && (!h_src || !h_dst || !h_col))) return CLANE_EINVAL;
     if (n > INT32_MAX || e_raw > INT32_MAX) return CLANE_ERANGE;
     try {
-        // counting sort by source, then sort + unique each row's destinations: the order torch's coalesce()
-        // produces (row-major, ascending column, duplicates merged).  The two edge passes are sequential (random
-        // per-row counters: atomics across threads measured slower than one thread); the row passes -- sort, unique,
-        // compaction -- run on all host threads over equal chunks of rows.
-        const int nt = host_threads(n / 65536 + 1);
-        std::vector<int32_t> start((size_t)n + 2, 0), fill, uniq((size_t)n + 1, 0);
-        std::vector<int32_t> tmp((size_t)std::max<int64_t>(e_raw, 1));
-        for (int64_t e = 0; e < e_raw; ++e) {
-            const int64_t s = h_src[e], t = h_dst[e];
-            if (s < 0 || s >= n || t < 0 || t >= n) return CLANE_ERANGE;
-            start[(size_t)s + 1]++;
+        // The order torch's coalesce() produces: row-major, ascending column, duplicates merged.  Two-level counting
+        // sort on all host threads, no atomics and no random writes beyond a cache-sized window:
+        //   1. rows are grouped into buckets of 2^shift rows; every thread histograms its chunk of the edge list;
+        //   2. every thread scatters its chunk into per-(bucket, thread) regions (sequential writes per bucket);
+        //   3. every bucket (a few 10^4 edges: cache resident) is counting-sorted by row, each row's destinations
+        //      sorted and made unique; 4. a scan of the unique counts gives rowptr; 5. rows are compacted into col.
+        int shift = 0;
+        while ((n >> shift) > 4096) ++shift;
+        const int64_t nbuckets = (n >> shift) + 1;
+        const int nt = host_threads(std::max<int64_t>(e_raw, n) / 65536 + 1);
+        std::vector<int64_t> hist((size_t)nt * nbuckets, 0);          // [thread][bucket] -> counts, then write cursors
+        std::atomic<int> bad{0};
+        parallel_chunks(e_raw, nt, [&](int64_t lo, int64_t hi, int t) {
+            int64_t* h = hist.data() + (size_t)t * nbuckets;
+            for (int64_t e = lo; e < hi; ++e) {
+                const int64_t s = h_src[e], d = h_dst[e];
+                if (s < 0 || s >= n || d < 0 || d >= n) { bad.store(1, std::memory_order_relaxed); return; }
+                h[s >> shift]++;
+            }
+        });
+        if (bad.load()) return CLANE_ERANGE;
+        std::vector<int64_t> bstart((size_t)nbuckets + 1, 0);
+        {
+            int64_t run = 0;
+            for (int64_t b = 0; b < nbuckets; ++b) {
+                bstart[(size_t)b] = run;
+                for (int t = 0; t < nt; ++t) {
+                    const int64_t c = hist[(size_t)t * nbuckets + b];
+                    hist[(size_t)t * nbuckets + b] = run;              // this thread's write cursor inside the bucket
+                    run += c;
+                }
+            }
+            bstart[(size_t)nbuckets] = run;
         }
-        for (int64_t v = 0; v < n; ++v) start[(size_t)v + 1] += start[(size_t)v];
-        fill.assign(start.begin(), start.begin() + n + 1);
-        for (int64_t e = 0; e < e_raw; ++e) tmp[(size_t)fill[(size_t)h_src[e]]++] = (int32_t)h_dst[e];
-        parallel_chunks(n, nt, [&](int64_t lo, int64_t hi) {
-            for (int64_t v = lo; v < hi; ++v) {
-                int32_t* a = tmp.data() + start[(size_t)v];
-                int32_t* b = tmp.data() + start[(size_t)v + 1];
+        struct Pair { int32_t row, dst; };
+        std::vector<Pair> staged((size_t)std::max<int64_t>(e_raw, 1));
+        parallel_chunks(e_raw, nt, [&](int64_t lo, int64_t hi, int t) {
+            int64_t* cur = hist.data() + (size_t)t * nbuckets;
+            for (int64_t e = lo; e < hi; ++e) {
+                const int64_t s = h_src[e];
+                staged[(size_t)cur[s >> shift]++] = Pair{(int32_t)s, (int32_t)h_dst[e]};
+            }
+        });
+        std::vector<int32_t> tmp((size_t)std::max<int64_t>(e_raw, 1));   // destinations, row-major, each row sorted + unique at its front
+        std::vector<int32_t> start((size_t)n + 1, 0), uniq((size_t)n + 1, 0);
+        parallel_items(nbuckets, nt, [&](int64_t bk) {
+            const int64_t r0 = bk << shift, r1 = std::min<int64_t>(n, (bk + 1) << shift);
+            if (r0 >= r1) return;
+            const Pair* p = staged.data() + bstart[(size_t)bk];
+            const int64_t cnt = bstart[(size_t)bk + 1] - bstart[(size_t)bk];
+            std::vector<int32_t> c((size_t)(r1 - r0) + 1, 0);
+            for (int64_t i = 0; i < cnt; ++i) c[(size_t)(p[i].row - r0) + 1]++;
+            for (int64_t r = 0; r < r1 - r0; ++r) c[(size_t)r + 1] += c[(size_t)r];
+            const int64_t base = bstart[(size_t)bk];
+            for (int64_t r = 0; r < r1 - r0; ++r) start[(size_t)(r0 + r)] = (int32_t)(base + c[(size_t)r]);
+            std::vector<int32_t> cur(c.begin(), c.end() - 1);
+            for (int64_t i = 0; i < cnt; ++i) tmp[(size_t)(base + cur[(size_t)(p[i].row - r0)]++)] = p[i].dst;
+            for (int64_t r = 0; r < r1 - r0; ++r) {
+                int32_t* a = tmp.data() + base + c[(size_t)r];
+                int32_t* b = tmp.data() + base + c[(size_t)r + 1];
                 if (b - a > 1) std::sort(a, b);
-                uniq[(size_t)v] = (int32_t)(std::unique(a, b) - a);
+                uniq[(size_t)(r0 + r)] = (int32_t)(std::unique(a, b) - a);
             }
         });
         int64_t out = 0;
@@ -85,7 +137,7 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
             out += uniq[(size_t)v];
             h_rowptr[v + 1] = (int32_t)out;
         }
-        parallel_chunks(n, nt, [&](int64_t lo, int64_t hi) {
+        parallel_chunks(n, nt, [&](int64_t lo, int64_t hi, int) {
             for (int64_t v = lo; v < hi; ++v)
                 if (uniq[(size_t)v])
                     memcpy(h_col + h_rowptr[v], tmp.data() + start[(size_t)v], (size_t)uniq[(size_t)v] * sizeof(int32_t));
