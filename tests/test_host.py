@@ -520,3 +520,30 @@ def test_native_edge_ingest_missing_file(tmp_path):
     assert L.clane_edges_open(b"a\nb", 3, 2, str(tmp_path / "E").encode(), 0, ctypes.byref(h), ctypes.byref(n),
                               ctypes.byref(line), err, 256) == -5
     assert err.value.decode().endswith("/E")
+
+
+def test_csr_build_is_thread_count_independent():
+    """The two-level counting sort gives torch.coalesce()'s order whatever the number of host threads, on a skewed
+    multigraph with duplicates, self-loops, empty rows and more buckets than rows per bucket."""
+    import os
+    L = _lib.lib()
+    rng = np.random.default_rng(8)
+    n, e = 70001, 400000
+    src = (n * rng.random(e) ** 3).astype(np.int64)           # heavy head
+    dst = rng.integers(0, n, e)
+    src[:5000], dst[:5000] = src[5000:10000], dst[5000:10000]  # duplicates
+    dst[10000:10100] = src[10000:10100]                        # self-loops
+    key = np.unique(src * n + dst)
+    want_rp = np.searchsorted(key // n, np.arange(n + 1)).astype(np.int32)
+    want_col = (key % n).astype(np.int32)
+    have = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        for k in (1, 2, 3, len(have) if have else 1):
+            if have:
+                os.sched_setaffinity(0, set(sorted(have)[:k]))
+            rp, col = np.zeros(n + 1, np.int32), np.zeros(e, np.int32)
+            E = L.clane_csr_from_edges(src.ctypes.data, dst.ctypes.data, e, n, rp.ctypes.data, col.ctypes.data)
+            assert E == len(key) and np.array_equal(rp, want_rp) and np.array_equal(col[:E], want_col)
+    finally:
+        if have:
+            os.sched_setaffinity(0, have)
