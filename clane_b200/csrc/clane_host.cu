@@ -36,15 +36,23 @@ int host_threads(int64_t work_units) {
 }
 
 // fn(lo, hi, t) over [0, total) cut into one contiguous chunk per thread t (the cut depends only on total and nthreads)
+// Workers never let an exception escape their thread (that would be std::terminate across the C ABI): the first
+// failure is flagged and re-raised as bad_alloc on the calling thread after the join; a thread that cannot be
+// created leaves its share of the work to the caller.
 template <class F>
 void parallel_chunks(int64_t total, int nthreads, F&& fn) {
     if (nthreads <= 1 || total < 2) { fn((int64_t)0, total, 0); return; }
     std::vector<std::thread> th;
+    std::atomic<int> failed{0};
     for (int t = 0; t < nthreads; ++t) {
         const int64_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
-        th.emplace_back([&fn, lo, hi, t] { if (lo < hi) fn(lo, hi, t); });
+        auto job = [&fn, &failed, lo, hi, t] {
+            try { if (lo < hi) fn(lo, hi, t); } catch (...) { failed.store(1); }
+        };
+        try { th.emplace_back(job); } catch (...) { job(); }
     }
     for (auto& x : th) x.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 // fn(i) for every i in [0, total), items handed out dynamically (uneven items: buckets of a power-law graph)
@@ -52,10 +60,18 @@ template <class F>
 void parallel_items(int64_t total, int nthreads, F&& fn) {
     if (nthreads <= 1 || total < 2) { for (int64_t i = 0; i < total; ++i) fn(i); return; }
     std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
     std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t)
-        th.emplace_back([&] { for (int64_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < total;) fn(i); });
+    auto job = [&] {
+        try { for (int64_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < total;) fn(i); }
+        catch (...) { failed.store(1); }
+    };
+    for (int t = 0; t < nthreads; ++t) {
+        try { th.emplace_back(job); } catch (...) { break; }
+    }
+    job();   // the caller works too (and does everything if no thread could be created)
     for (auto& x : th) x.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 }  // namespace
@@ -143,8 +159,8 @@ int64_t clane_csr_from_edges(const int64_t* h_src, const int64_t* h_dst, int64_t
                     memcpy(h_col + h_rowptr[v], tmp.data() + start[(size_t)v], (size_t)uniq[(size_t)v] * sizeof(int32_t));
         });
         return out;
-    } catch (const std::bad_alloc&) {
-        return (int64_t)cudaErrorMemoryAllocation;
+    } catch (...) {
+        return (int64_t)CLANE_ENOMEM;   // negative, like every error of this call (a positive value is an edge count)
     }
 }
 
@@ -223,7 +239,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_tasks); cudaFree(plan->d_descs); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
-    cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubW); cudaFree(plan->d_hubT);
+    cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubT);
     cudaFree(plan->d_hub_cnt); cudaFree(plan->d_hub_done);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);
@@ -290,7 +306,7 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
                 emit_descriptors(bs, nbk * 8, descs);
                 tasks.push_back(t);
             }
-            blocks += (nblk + 1) & ~1;   // every row's scratch starts 16-byte aligned in hubW
+            blocks += (nblk + 1) & ~1;
         }
         *hub_blocks = blocks;
         for (int32_t i = 0; i < n_spans; ++i) {
@@ -435,7 +451,6 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
         PLAN_CUDA(cudaMemcpy(plan->d_hub_info, info.data(), n_hrows * sizeof(int4), cudaMemcpyHostToDevice));
         const size_t nb = (size_t)plan->hub_blocks;
         PLAN_CUDA(cudaMalloc(&plan->d_hubS, std::max<size_t>(nb * plan->nslab32b * 32, 1) * 16));
-        PLAN_CUDA(cudaMalloc(&plan->d_hubW, nb * 8));
         if (plan->ntail4 > 0) PLAN_CUDA(cudaMalloc(&plan->d_hubT, nb * 8 * plan->ntail4 * 16));
         const size_t chain_ctas = (size_t)n_hrows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
         PLAN_CUDA(cudaMalloc(&plan->d_hub_cnt, n_hrows * sizeof(int32_t)));

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -57,6 +58,21 @@ struct Failure {
     int code = CLANE_OK;
     std::string text;
 };
+
+
+// job(c) for every piece c, one thread each; an exception inside a worker (bad_alloc from a Failure's string) is
+// flagged and re-raised on the caller after the join, and a thread that cannot be created runs on the caller
+template <class F>
+void run_pieces(int npieces, F&& job) {
+    std::atomic<int> failed{0};
+    std::vector<std::thread> th;
+    auto guarded = [&](int c) { try { job(c); } catch (...) { failed.store(1); } };
+    for (int c = 0; c < npieces; ++c) {
+        try { th.emplace_back(guarded, c); } catch (...) { guarded(c); }
+    }
+    for (auto& t : th) t.join();
+    if (failed.load()) throw std::bad_alloc();
+}
 
 }  // namespace
 
@@ -133,26 +149,19 @@ int clane_edges_open(const char* v_ids, int64_t v_bytes, int64_t n_vertices, con
                 p = next;
             }
         };
-        {   // pass 1: count lines
-            std::vector<std::thread> th;
-            for (int c = 0; c < npieces; ++c)
-                th.emplace_back([&, c] {
-                    int64_t k = 0;
-                    for_lines(pieces[(size_t)c], [&](const char*, const char*) { ++k; });
-                    pieces[(size_t)c].lines = k;
-                });
-            for (auto& t : th) t.join();
-        }
+        run_pieces(npieces, [&](int c) {   // pass 1: count lines
+            int64_t k = 0;
+            for_lines(pieces[(size_t)c], [&](const char*, const char*) { ++k; });
+            pieces[(size_t)c].lines = k;
+        });
         int64_t total = 0;
         for (auto& pc : pieces) { pc.first = total; total += pc.lines; }
-        clane_edge_file* ef = new clane_edge_file();
+        std::unique_ptr<clane_edge_file> ef(new clane_edge_file());
         ef->src.resize((size_t)total);
         ef->dst.resize((size_t)total);
         std::vector<Failure> fails((size_t)npieces);
-        {   // pass 2: parse
-            std::vector<std::thread> th;
-            for (int c = 0; c < npieces; ++c)
-                th.emplace_back([&, c] {
+        run_pieces(npieces, [&](int c) {   // pass 2: parse
+                {
                     int64_t k = pieces[(size_t)c].first;
                     Failure& fl = fails[(size_t)c];
                     for_lines(pieces[(size_t)c], [&](const char* p, const char* stop) {
@@ -172,23 +181,20 @@ int clane_edges_open(const char* v_ids, int64_t v_bytes, int64_t n_vertices, con
                         ef->src[(size_t)line] = ia->second;
                         ef->dst[(size_t)line] = id->second;
                     });
-                });
-            for (auto& t : th) t.join();
-        }
+                }
+        });
         const Failure* worst = nullptr;
         for (const Failure& fl : fails)
             if (fl.code != CLANE_OK && (!worst || fl.line < worst->line)) worst = &fl;
         if (worst) {
             if (err_line) *err_line = worst->line;
             fail_text(worst->text);
-            const int code = worst->code;
-            delete ef;
-            return code;
+            return worst->code;
         }
         *e_raw = total;
-        *out = ef;
+        *out = ef.release();
         return CLANE_OK;
-    } catch (const std::bad_alloc&) {
+    } catch (...) {
         return CLANE_ENOMEM;
     }
 }

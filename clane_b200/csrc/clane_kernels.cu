@@ -104,8 +104,8 @@ __device__ __forceinline__ float sleef_expf_u10(float d) {
 // One warp per row.  Optional global divisor c = fl(sqrt(S1)) * fl(sqrt(S2)) (similarity.py:37).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_row_softmax(const float* __restrict__ scores, const float* __restrict__ norms2, int32_t row_lo, int32_t row_hi,
-              const int32_t* __restrict__ rowptr, float* __restrict__ w) {
+k_row_softmax(const float* scores, const float* __restrict__ norms2, int32_t row_lo, int32_t row_hi,
+              const int32_t* __restrict__ rowptr, float* w) {   // scores and w may be the same array (in place)
     const int row = row_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= row_hi) return;
@@ -308,7 +308,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.P0 = plan->d_P0;
     p.hub_info = static_cast<const int4*>(plan->d_hub_info); p.n_hub_rows = plan->n_hub_rows;
     p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
-    p.hubS = static_cast<float4*>(plan->d_hubS); p.hubW = static_cast<float2*>(plan->d_hubW);
+    p.hubS = static_cast<float4*>(plan->d_hubS);
     p.hubT = static_cast<float4*>(plan->d_hubT);
     p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
     p.chain_spin_ns = plan->chain_spin_ns;

@@ -28,7 +28,6 @@ struct clane_plan {
     unsigned long long chain_spin_ns = 400000;   // early chain pass time-out: ~2x the expected time of all segment tasks
     int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it
     void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
-    void* d_hubW = nullptr;            // float2[hub_blocks]      {w4, w6}
     void* d_hubT = nullptr;            // float4[hub_blocks * 8][ntail4]  raw z, sequential-regime columns
     int32_t* d_hub_cnt = nullptr;      // per hub row: segment warps done this sweep
     int32_t* d_hub_done = nullptr;     // per chain CTA: produced by the early (overlapped) chain pass

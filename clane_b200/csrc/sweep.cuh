@@ -61,7 +61,6 @@ struct SweepParams {
     int nslab32b;               // 32-column slabs below `limit`
     int sld;                    // 32 * nslab32b: columns per block in hubS
     float4* hubS;               // per hub row [32-column slab][block][32] {z6, z4, X, Y}
-    float2* hubW;               // [block] {w4, w6}
     float4* hubT;               // per hub row [sequential-regime column][neighbour] raw z (floats)
     int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
     int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
@@ -146,9 +145,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async16_sa(unsigned smem_addr, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8_sa(unsigned smem_addr, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async4_sa(unsigned smem_addr, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gsrc) : "memory");
@@ -463,7 +459,6 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     // sequential-regime scratch of the row: [column][8 * nblk_row] floats; this lane's first column, this segment
     float* tdst = reinterpret_cast<float*>(p.hubT) + B0 * 32 * p.ntail4 +
                   (size_t)(col_blocked ? 0 : cc - p.limit) * nblk_row * 8 + (size_t)b_first * 8;
-    float2* wdst = p.hubW + B0 + b_first;
     const int* __restrict__ offp = p.coloff + t0.z;
     const float* __restrict__ wp = p.w + t0.z;
     // a segment is at most 128 edges: the whole (offset, w) stream fits the ring
@@ -508,7 +503,6 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
                 *reinterpret_cast<float4*>(o + 3 * cp + 4) = make_float4(A[4].w, A[5].w, A[6].w, A[7].w);
             }
         }
-        if (slab == 0 && lane == 0) wdst[cb] = make_float2(w[4], w[6]);
     }
     // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
     __threadfence();
@@ -614,7 +608,9 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         // ---------------- producer ----------------
         if (blocked) {
             const float4* src = p.hubS + B0 * p.sld + (size_t)s * nblk * 32 + lane;   // contiguous 512 B per block
-            const float2* wsrc = p.hubW + B0;
+            // {w4, w6} of every block straight from w (constant during a sweep; no scratch copy that another SM's
+            // segment warp could be rewriting while this SM's L1 holds a stale sector of it)
+            const float* wsrc = p.w + a + 4;
             const unsigned ring_sa = smem_u32(ringS) + lane * 16;
             const unsigned wq_sa = smem_u32(wq) + (lane & 15) * 8;
             for (int g = 0; g < ngroups; ++g) {
@@ -625,7 +621,10 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
 #pragma unroll
                 for (int j = 0; j < kChainGroup; ++j)
                     if (b0 + j < nblk) cp_async16_sa(dst + j * 512, src + (size_t)(b0 + j) * 32);
-                if (lane < kChainGroup && b0 + lane < nblk) cp_async8_sa(wq_sa + (unsigned)st * (kChainGroup * 8), wsrc + b0 + lane);
+                if (lane < kChainGroup && b0 + lane < nblk) {
+                    cp_async4_sa(wq_sa + (unsigned)st * (kChainGroup * 8), wsrc + (size_t)(b0 + lane) * 8);
+                    cp_async4_sa(wq_sa + (unsigned)st * (kChainGroup * 8) + 4, wsrc + (size_t)(b0 + lane) * 8 + 2);
+                }
                 cp_async_arrive(full + st);
             }
         } else {

@@ -27,7 +27,7 @@ from torch.utils.data import Dataset
 
 from . import _lib
 
-HUB_THRESHOLD = 0      # 0 = library default (rows of degree > 1024 take the hub path)
+HUB_THRESHOLD = 0      # 0 = library default: rows longer than (edges of the plan / 4096), clamped to [256, 16384]
 
 
 class Vertex(object):
@@ -44,7 +44,12 @@ class Vertex(object):
 
     @property
     def z(self) -> torch.Tensor:
-        return self._graph.Z[self.idx]
+        return self._graph._row_of_Z(self.idx)
+
+    @z.setter
+    def z(self, value) -> None:
+        # the reference assigns rows in place (`v.z = ...`, embedder.py:92, graph.py:138)
+        self._graph._set_row_of_Z(self.idx, value)
 
     @property
     def outgoing_indices(self):
@@ -261,6 +266,25 @@ class Graph(Dataset):
         if self._dev is None:
             return self._Z_host if self._Z_host is not self.X else self.X.clone()
         return self.Z_device.cpu()
+
+    def _row_of_Z(self, idx: int) -> torch.Tensor:
+        """One row of the current embeddings on the host (a 4*d-byte copy, not the whole matrix)."""
+        if self._dev is None:
+            return self._Z_host[idx].clone() if self._Z_host is self.X else self._Z_host[idx]
+        S = self._dev
+        return S.Z[S.cur][idx, :S.d].cpu()
+
+    def _set_row_of_Z(self, idx: int, value) -> None:
+        value = torch.as_tensor(value)
+        if self._dev is None:
+            if self._Z_host is self.X:          # z stops aliasing x at the first write (graph.py:18-19)
+                self._Z_host = self.X.clone()
+            self._Z_host[idx] = value.to(self._Z_host.dtype)
+        else:
+            S = self._dev
+            row = value.to(device=S.device, dtype=torch.float32).reshape(S.d)
+            S.Z[0][idx, :S.d] = row             # both ping-pong buffers: sinks are never rewritten by a sweep
+            S.Z[1][idx, :S.d] = row
 
     def set_Z(self, Z: torch.Tensor) -> None:
         """Replace the embeddings (graph.py:136-138)."""

@@ -36,11 +36,34 @@ class CosineSimilarity(Similarity):
             v1 = v1.unsqueeze(0)
         if v2.dim() == 1:
             v2 = v2.unsqueeze(0)
-        if v1.shape != v2.shape or v1.dim() != 2:
+        if v1.dim() != 2 or v2.dim() != 2 or v1.shape[1] != v2.shape[1] or (
+                v1.shape[0] != v2.shape[0] and 1 not in (v1.shape[0], v2.shape[0])):
             raise RuntimeError(f"CosineSimilarity expects two [E, d] batches, got {tuple(v1.shape)} and {tuple(v2.shape)}")
-        dev = _lib.require_cuda()
+        _lib.require_cuda()
         L = _lib.lib()
         out_device = v1.device
+        e = max(int(v1.shape[0]), int(v2.shape[0]))
+        s = _lib.stream_handle()
+        if v1.shape[0] == v2.shape[0]:
+            out, norms2 = self._raw(v1, v2)
+        else:
+            # [1, d] against [E, d]: the reference's matmul broadcasts the single row (similarity.py:35-37) while each
+            # global norm runs over its tensor AS GIVEN -- dots of the expanded batch, the single row's norm counted once
+            out, nb = self._raw(v1.expand(e, -1), v2.expand(e, -1))
+            one = v1 if v1.shape[0] == 1 else v2
+            _, n1 = self._raw(one, one)
+            norms2 = torch.stack([n1[0], nb[1]]) if v1.shape[0] == 1 else torch.stack([nb[0], n1[0]])
+        _lib.check(L.clane_cosine_finalize(out.data_ptr(), norms2.data_ptr(), e, out.data_ptr(), s),
+                   "clane_cosine_finalize")
+        res = out[:e].to(out_device)
+        torch.cuda.current_stream().synchronize()
+        return res
+
+    @staticmethod
+    def _raw(v1: torch.Tensor, v2: torch.Tensor):
+        """(per-pair dots [E], the two global square sums [2]) on the device, in the reference's summation orders."""
+        dev = _lib.require_cuda()
+        L = _lib.lib()
         e, d = int(v1.shape[0]), int(v1.shape[1])
         ld = int(L.clane_padded_ld(d))
         # pair i is the edge  i -> e + i  of a bipartite helper graph over the stacked rows
@@ -52,14 +75,10 @@ class CosineSimilarity(Similarity):
         out = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
         norms2 = torch.empty(2, dtype=torch.float32, device=dev)
         plan = _lib.Plan(2 * e, e, d)          # scores-only plan: reduction scratch, no schedule
-        s = _lib.stream_handle()
         _lib.check(L.clane_scores_cosine(plan.handle, Z.data_ptr(), erow.data_ptr(), col.data_ptr(), 0, e,
-                                         out.data_ptr(), norms2.data_ptr(), s), "clane_scores_cosine")
-        _lib.check(L.clane_cosine_finalize(out.data_ptr(), norms2.data_ptr(), e, out.data_ptr(), s),
-                   "clane_cosine_finalize")
-        res = out[:e].to(out_device)
+                                         out.data_ptr(), norms2.data_ptr(), _lib.stream_handle()), "clane_scores_cosine")
         torch.cuda.current_stream().synchronize()   # the plan's scratch is freed when it goes out of scope
-        return res
+        return out, norms2
 
 
 class AsymmertricSimilarity(nn.Module, Similarity):

@@ -194,7 +194,26 @@ def prim_fixtures():
     print("prim fixtures written")
 
 
+def broadcast_fixtures():
+    """CosineSimilarity of the reference on a single row against a batch (similarity.py:35-37 broadcasts)."""
+    out = {}
+    cases = [(5, 8), (64, 128), (20, 500)]
+    sim = CosineSimilarity()
+    for i, (e, d) in enumerate(cases):
+        rng = np.random.default_rng(5000 + i)
+        a = rng.standard_normal((1, d)).astype(np.float32)
+        b = rng.standard_normal((e, d)).astype(np.float32)
+        out[f"ab_{e}_{d}"] = sim(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+        out[f"ba_{e}_{d}"] = sim(torch.from_numpy(b), torch.from_numpy(a)).numpy()
+    out["cases"] = np.array(cases, np.int64)
+    np.savez_compressed(HERE / "prim_cosine_broadcast.npz", **out)
+    print("broadcast fixtures written")
+
+
 def main():
+    if sys.argv[1:] == ["broadcast"]:
+        return broadcast_fixtures()
+    broadcast_fixtures()
     # the toy graph + config the reference's own tests use (tests/test_graph.py:13, tests/config.yaml)
     root = HERE.parent / "data_root"
     root.mkdir(exist_ok=True)

@@ -133,6 +133,36 @@ def test_cosine_plugin_batched_quirk_bit_exact(e, d):
     assert not got.is_cuda and np.array_equal(got.numpy(), want)
 
 
+def test_cosine_plugin_single_row_against_batch_matches_reference():
+    """[1, d] against [E, d] (the reference's matmul broadcasts, similarity.py:35-37): golden values of the real
+    reference, both argument orders."""
+    G = np.load(GOLD / "prim_cosine_broadcast.npz")
+    cos = similarity.CosineSimilarity()
+    for i, (e, d) in enumerate(G["cases"]):
+        rng = np.random.default_rng(5000 + i)
+        a = torch.from_numpy(rng.standard_normal((1, d)).astype(np.float32))
+        b = torch.from_numpy(rng.standard_normal((e, d)).astype(np.float32))
+        assert np.array_equal(cos(a, b).numpy(), G[f"ab_{e}_{d}"])
+        assert np.array_equal(cos(b, a).numpy(), G[f"ba_{e}_{d}"])
+        assert np.array_equal(cos(a[0], b).numpy(), G[f"ab_{e}_{d}"])          # 1-D input is unsqueezed first
+    with pytest.raises(RuntimeError):
+        cos(torch.rand(3, 8), torch.rand(4, 8))
+
+
+def test_vertex_z_assignment_writes_through():
+    """`v.z = ...` is how the reference updates a row (embedder.py:92, graph.py:138)."""
+    G = np.load(GOLD / "ref_cyclic100_d8.npz")
+    g = Graph.from_arrays(int(G["n"]), G["raw_src"], G["raw_dst"], G["X"])
+    g.V[3].z = torch.full([8], 2.5)                         # before the device state exists
+    assert torch.equal(g.Z[3], torch.full([8], 2.5)) and torch.equal(g.X[3], torch.from_numpy(G["X"][3]))
+    g._device_state()
+    g.V[5].z = torch.arange(8.0)
+    assert torch.equal(g.V[5].z, torch.arange(8.0)) and torch.equal(g.Z[3], torch.full([8], 2.5))
+    Z = g.Z
+    Z[3], Z[5] = g.X[3], g.X[5]
+    assert torch.equal(Z, g.X)
+
+
 # ---- sweep (embedder.py:84-94) ---------------------------------------------------------------------
 @pytest.mark.parametrize("case", REF_CASES)
 def test_first_sweep_bit_exact_with_reference(case):
@@ -346,6 +376,69 @@ def test_full_convergence_cora_shape_counts_match_oracle():
     rowptr, col = O.csr_from_edges(src, dst, n)
     Zo, spc, _ = O.iterate(X, rowptr, col, 0.76, 10)
     assert e.sweeps_per_call == spc.tolist()
+    assert np.array_equal(g.Z.numpy(), Zo)
+
+
+@pytest.mark.parametrize("shape", ["pubmed", "arxiv"])
+def test_full_convergence_counts_match_oracle_at_baseline_shapes(shape):
+    """Embedder.iterate() to convergence at BASELINE configs 3 and 4: per-call sweep counts, outer amounts and the
+    final embeddings against the oracle (the CPU port needs ~10-60 s for these)."""
+    n, src, dst, X = synth.make_graph(shape, seed=0)
+    g = Graph.from_arrays(n, src, dst, X)
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=10)
+    e.verbose = False
+    e.iterate()
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    Zo, spc, oam = O.iterate(X, rowptr, col, 0.76, 10)
+    assert e.sweeps_per_call == spc.tolist()
+    assert e.minimum_amount_updated_Z == oam.min()
+    Z = g.Z.numpy()
+    assert within_tolerance(Z, Zo) and np.array_equal(Z, Zo)
+
+
+def test_products_shape_full_size_against_oracle():
+    """BASELINE config 5 at full size on one GPU (2.45 M nodes / 61.9 M edges / d = 100): CSR, P, the L1 amounts of
+    two sweeps and Z, bit-exact against the oracle."""
+    n, src, dst, X = synth.make_graph("products", seed=0)
+    g = Graph.from_arrays(n, src, dst, X)
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    assert g._nnz == 61859140 and np.array_equal(g._rowptr, rowptr) and np.array_equal(g._col, col)
+    del src, dst
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=10)
+    e.verbose = False
+    e.propagate(max_sweeps=2)
+    S = g._device_state()
+    assert S.plan.n_hub_rows >= 1 and not S.plan.fused_l1
+    Zo, amounts, w = O.propagate(X, X, rowptr, col, 0.76, 10, max_sweeps=2)
+    assert np.array_equal(S.w[:S.e].cpu().numpy(), w)
+    assert np.array_equal(e.amounts_per_call[0], amounts)
+    Z = g.Z.numpy()
+    assert within_tolerance(Z, Zo) and np.array_equal(Z, Zo)
+
+
+def test_adjacent_hub_rows_across_build_p_calls(monkeypatch):
+    """Several short hub rows with consecutive ids (their chain scratch regions are neighbours), whole iterate():
+    every propagate() call rebuilds P, so weights parked for one call must never leak into the next."""
+    import clane_b200.graph as graph_module
+    monkeypatch.setattr(graph_module, "HUB_THRESHOLD", 16)
+    rng = np.random.default_rng(123)
+    n, d = 400, 64
+    src, dst = synth.make_edges(n, n * 3, "uniform", rng)
+    ks = [17, 18, 19, 25, 33, 41, 23, 17]
+    hub_src = np.concatenate([np.full(k, 100 + i) for i, k in enumerate(ks)])
+    hub_dst = np.concatenate([rng.permutation(n)[:k] for k in ks])
+    src, dst = np.concatenate([src, hub_src]), np.concatenate([dst, hub_dst])
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    g = Graph.from_arrays(n, src, dst, X)
+    e = Embedder(g, similarity.CosineSimilarity(), device=torch.device("cuda"), gamma=0.76, tolerence=2)
+    e.verbose = False
+    e.iterate()
+    assert g._device_state().plan.n_hub_rows >= len(ks)
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    Zo, spc, _ = O.iterate(X, rowptr, col, 0.76, 2)
+    assert e.sweeps_per_call == spc.tolist() and len(spc) >= 3
     assert np.array_equal(g.Z.numpy(), Zo)
 
 

@@ -98,6 +98,15 @@ def test_feature_file_precedence(tmp_path):
     assert np.array_equal(Graph(tmp_path, 99).X.numpy(), X + 1)
 
 
+def test_vertex_z_assignment_on_the_host(data_root):
+    """`v.z = ...` (embedder.py:92, graph.py:138) before any device state exists: z stops aliasing x."""
+    g = Graph(data_root=data_root, embedding_dim=4)
+    x3 = g.X[3].clone()
+    g.V[3].z = torch.full([4], 7.0)
+    assert torch.equal(g.V[3].z, torch.full([4], 7.0)) and torch.equal(g.V[3].x, x3)
+    assert torch.equal(g.Z[3], torch.full([4], 7.0)) and torch.equal(g.Z[4], g.X[4])
+
+
 def test_dataset_protocol(data_root):
     g = Graph(data_root=data_root, embedding_dim=4)
     assert g[5] == 5

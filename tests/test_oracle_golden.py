@@ -97,3 +97,18 @@ def test_oracle_threads_do_not_change_results():
         outs.append(O.iterate(G["X"], rowptr, col, float(G["gamma"]), int(G["tol"])))
     for Z, spc, oam in outs[1:]:
         assert np.array_equal(Z, outs[0][0]) and spc.tolist() == outs[0][1].tolist()
+
+
+def test_cosine_single_row_against_batch_matches_reference():
+    """The reference's matmul broadcasts a [1, d] argument (similarity.py:35-37): dots of the expanded batch in the
+    usual order, each global norm over its tensor as given.  Golden values of the real reference."""
+    G = np.load(GOLD / "prim_cosine_broadcast.npz")
+    for i, (e, d) in enumerate(G["cases"]):
+        rng = np.random.default_rng(5000 + i)
+        a = rng.standard_normal((1, d)).astype(np.float32)
+        b = rng.standard_normal((e, d)).astype(np.float32)
+        rowptr = np.concatenate([np.arange(e + 1), np.full(e, e)]).astype(np.int64)
+        dots, _, _ = O.scores_raw(np.concatenate([np.repeat(a, e, 0), b]), rowptr, np.arange(e, 2 * e, dtype=np.int32))
+        c = np.float32(np.sqrt(O.aten_sum(a * a), dtype=np.float32) * np.sqrt(O.aten_sum(b * b), dtype=np.float32))
+        want = (dots / c).astype(np.float32)
+        assert np.array_equal(want, G[f"ab_{e}_{d}"]) and np.array_equal(want, G[f"ba_{e}_{d}"])
