@@ -53,6 +53,15 @@ def workload_name(args) -> str:
     return "arxiv" if args.gpus == 1 else "products"
 
 
+def workload_config(name, n, e, d, scale):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    ws = 3 * n * d * 4 + 8 * e
+    return {"workload": f"{name}-shape synthetic", "nodes": n, "edges": e, "dim": d, "gamma": GAMMA,
+            "similarity": "CosineSimilarity", "scale": scale,
+            "l2": f"no flush: working set {ws / 1e6:.0f} MB exceeds the 126 MB L2" if ws > 126e6
+                  else "no flush: working set fits L2 (the steady state of the iteration; Cora/Pubmed shapes)"}
+
+
 def sweep_bytes(n, e, d):
     """Algorithmic bytes of one sweep: X, Z_cur read, Z_next written, col, w, rowptr."""
     return 12 * d * n + 8 * e + 4 * (n + 1)
@@ -138,7 +147,7 @@ class ClockSampler(threading.Thread):
 def cpu_sweeps(n, src, dst, X, budget_s: float, min_sweeps: int, max_sweeps: int, step_budget_s: float = 0.0):
     """Time CPU sweeps (row update + exact L1 change) of the oracle on the host threads.
 
-    Returns (edges per timed step, threads, times, sample description).  When a whole sweep is
+    Returns (edges per timed step, all edges, threads, times, sample description).  When a whole sweep is
     slower than step_budget_s (> 0), each timed step covers a contiguous row range holding about
     that much work -- a bounded sample of the same workload."""
     from oracle import oracle as O
@@ -175,7 +184,7 @@ def cpu_sweeps(n, src, dst, X, budget_s: float, min_sweeps: int, max_sweeps: int
         times.append(time.perf_counter() - t0)
         if hi == n:
             Z, Zn = Zn, Z
-    return edges, threads, times, what
+    return edges, int(rowptr[n]), threads, times, what
 
 
 def run_reference(args):
@@ -188,7 +197,7 @@ def run_reference(args):
     d = X.shape[1]
     # each step = one CPU sweep of the same workload (bounded: the whole run ends within minutes)
     total = args.warmup + args.steps
-    e, threads, times, what = cpu_sweeps(n, src, dst, X, budget_s=1e9, min_sweeps=total, max_sweeps=total,
+    e, e_all, threads, times, what = cpu_sweeps(n, src, dst, X, budget_s=1e9, min_sweeps=total, max_sweeps=total,
                                          step_budget_s=150.0 / total)
     timed = times[args.warmup:]
     ms = 1e3 * float(np.mean(timed))
@@ -197,8 +206,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}-shape synthetic", "nodes": n, "edges": e, "dim": d, "gamma": GAMMA,
-                   "similarity": "CosineSimilarity", "scale": args.scale},
+        "config": workload_config(name, n, e_all, d, args.scale),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{len(timed)} {what} (row update + exact L1) of the {name}-shape graph, "
                                    f"oracle C port of the reference's path, OpenMP over rows"},
@@ -207,6 +215,55 @@ def run_reference(args):
                 "and cannot run this shape; this arm times its bit-exact C restatement on all host threads",
     }
     print(json.dumps(line))
+
+
+
+def single_gpu_steps(torch, L, _lib, g, sim, steps, warmup=3):
+    """ms per sweep (exact L1 included) of graph `g` on THIS rank's GPU alone: the strong-scaling reference."""
+    S = g._device_state()
+    g.set_Z(g.X)
+    g._build_P_device(sim)
+    gamma = ctypes.c_float(float(np.float32(GAMMA)))
+    sh = S.stream.cuda_stream
+
+    def step(i):
+        a, b = S.Z[(S.cur + i) & 1], S.Z[(S.cur + i + 1) & 1]
+        _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), a.data_ptr(), b.data_ptr(), S.rowptr.data_ptr(),
+                                 S.col.data_ptr(), S.w.data_ptr(), gamma, S.amount.data_ptr(), 0, 0, 0, sh))
+    torch.cuda.synchronize()
+    for i in range(warmup):
+        step(i)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(S.stream)
+    for i in range(steps):
+        step(warmup + i)
+    ev1.record(S.stream)
+    torch.cuda.synchronize()
+    S.cur = (S.cur + warmup + steps) & 1
+    return ev0.elapsed_time(ev1) / steps
+
+
+def vectorised_cpu_sweeps(n, src, dst, X, budget_s=6.0):
+    """a best-effort VECTORISED torch-CPU restatement (CSR SpMM + axpy + L1 on all
+    host threads) -- timing only: its summation order is torch's, not the reference's, so counts may drift."""
+    import torch
+    from oracle import oracle as O
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    w = O.build_p(X, rowptr, col)
+    P = torch.sparse_csr_tensor(torch.from_numpy(rowptr), torch.from_numpy(col.astype(np.int64)), torch.from_numpy(w),
+                                size=(n, n))
+    Xt = torch.from_numpy(np.ascontiguousarray(X))
+    has = torch.from_numpy(np.diff(rowptr) > 0).unsqueeze(1)
+    Z = Xt.clone()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        Zn = torch.where(has, Xt + GAMMA * (P @ Z), Z)
+        amount = (Zn - Z).abs().sum().item()
+        times.append(time.perf_counter() - t0)
+        Z = Zn
+    return int(rowptr[n]), torch.get_num_threads(), times[1:], amount
 
 
 # ------------------------------------------------------------------------------------------------
@@ -323,6 +380,7 @@ def run_gpu(args):
     value = e / (ms_per_step * 1e-3)
     amount = float(S.amount.cpu()[0]) if runner is None else runner.last_amount()
 
+    PLAN = S.plan if runner is None else runner.plan
     peak, peak_src = measured_peak()
     kern_ms = float(kern[0])
     bytes_sweep = sweep_bytes(n, e, d)
@@ -331,23 +389,18 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}-shape synthetic", "nodes": n, "edges": e, "dim": d, "gamma": GAMMA,
-                   "similarity": "CosineSimilarity", "scale": args.scale,
-                   "parallelism": "single GPU" if world == 1 else
-                   f"rows partitioned by contiguous id over {world} GPUs; exchange: " +
-                   ("every finished row stored to all ranks' Z (NVLink peer memory) from inside the sweep kernel, "
-                    "one all-reduce of the L1 slots per sweep" + (" (multimem.st through the NVSwitch multicast mapping)"
-                                                                 if exch == "multicast" else "")
-                    if exch in ("p2p", "multicast")
-                    else "NCCL all-gather of Z per sweep"),
-                   "l2": f"no flush: working set {(3 * n * d * 4 + 8 * e) / 1e6:.0f} MB exceeds the 126 MB L2"
-                         if 3 * n * d * 4 + 8 * e > 126e6 else "working set fits L2 (steady state of the iteration)",
-                   "step": "row kernel (+ hub segments) with the hub chains beside it, exact L1 change (fused partials / "
-                           "cascade), device patience; P frozen",
-                   "plan": {"group_rows": (S.plan if runner is None else runner.plan).group_rows,
-                            "spans": (S.plan if runner is None else runner.plan).n_spans,
-                            "hub_rows": (S.plan if runner is None else runner.plan).n_hub_rows,
-                            "fused_l1": (S.plan if runner is None else runner.plan).fused_l1}},
+        "config": workload_config(name, n, e, d, args.scale),
+        "details": {"parallelism": "single GPU" if world == 1 else
+                    f"rows partitioned by contiguous id over {world} GPUs; exchange: " +
+                    ("every finished row stored to all ranks' Z (NVLink peer memory) from inside the sweep kernel, "
+                     "one all-reduce of the L1 slots per sweep" + (" (multimem.st through the NVSwitch multicast mapping)"
+                                                                  if exch == "multicast" else "")
+                     if exch in ("p2p", "multicast")
+                     else "NCCL all-gather of Z per sweep"),
+                    "step": "row kernel (+ hub segments) with the hub chains beside it, exact L1 change (fused partials / "
+                            "cascade), device patience; P frozen",
+                    "plan": {"group_rows": PLAN.group_rows, "spans": PLAN.n_spans, "hub_rows": PLAN.n_hub_rows,
+                             "fused_l1": PLAN.fused_l1}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(name), "kernel": "k_sweep_rows", "kernel_ms": kern_ms,
                      "sweep_ms_serialized": float(kern[1]), "l1_tail_ms": float(kern[2]), "hub_kernel_ms": float(kern[3]),
@@ -391,6 +444,41 @@ def run_gpu(args):
                                "wall clock, max over ranks; upload, plan build, build_P and the download are inside the "
                                "timed region and amortised over the steps of the call"}
         del r2
+        # ---- strong scaling on ONE workload: the same graph on rank 0's GPU alone, in this job ----
+        n1 = torch.zeros(1, device="cuda")
+        if rank == 0:
+            n1[0] = single_gpu_steps(torch, L, _lib, g, sim, min(args.steps, 50))
+        dist.broadcast(n1, 0)
+        n1_ms = float(n1.item())
+        n1_value = e / (n1_ms * 1e-3)
+        line["strong_scaling"] = {"workload": f"{name}-shape synthetic", "n1_ms_per_step": n1_ms, "n1_value": n1_value,
+                                  "efficiency": value / (world * n1_value),
+                                  "how": f"{min(args.steps, 50)} single-GPU sweeps of the same graph on rank 0, same job, CUDA "
+                                         "events; efficiency = value / (n_gpus * n1_value)"}
+        # ---- parity of the sharded path against the single-GPU path, outside every timed region ----
+        K = 3
+        rc_ = cdist.ShardedSweeper(g, sim, GAMMA, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
+        am = []
+        for i in range(K):
+            rc_.sweep(True)
+            am.append(rc_.last_amount())
+        Zs = rc_.Z[rc_.cur][:n]
+        Zb = torch.empty_like(Zs)
+        amb = torch.zeros(K, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            g.set_Z(g.X)
+            emb.sweeps_per_call, emb.amounts_per_call = [], []
+            emb.propagate(max_sweeps=K)
+            S1 = g._device_state()
+            Zb.copy_(S1.Z[S1.cur][:n])
+            amb.copy_(torch.from_numpy(np.asarray(emb.amounts_per_call[-1], np.float64)))
+        dist.broadcast(Zb, 0)
+        dist.broadcast(amb, 0)
+        same = torch.tensor([int(torch.equal(Zs, Zb) and am == amb.cpu().tolist())], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        line["parity_vs_single_gpu"] = bool(same.item())
+        line["parity_check"] = f"{K} sweeps from Z = X: every rank's full Z replica and the L1 amounts bit-identical to rank 0's single-GPU run"
+        del rc_, Zb
         if not args.no_converge:
             # time-to-converge of the sharded Embedder.iterate() (build_P calls + sweeps + patience on every rank)
             r3 = cdist.ShardedSweeper(g, sim, GAMMA, tol=10, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
@@ -404,6 +492,22 @@ def run_gpu(args):
             line["time_to_converge"] = {"seconds": float(dt.item()), "outer_iterations": len(spc), "sweeps": int(sum(spc)),
                                         "sweeps_per_call": spc, "tolerence": 10}
             del r3
+            box = [None]
+            if rank == 0:             # the same iterate() on one GPU: counts must agree
+                g.set_Z(g.X)
+                emb.sweeps_per_call, emb.amounts_per_call = [], []
+                emb.minimum_amount_updated_Z = float("inf")
+                emb.tolerences["global"].reset()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                emb.iterate()
+                torch.cuda.synchronize()
+                box[0] = (list(emb.sweeps_per_call), time.perf_counter() - t0)
+            dist.broadcast_object_list(box, 0)
+            line["time_to_converge"]["single_gpu_sweeps_per_call"] = box[0][0]
+            line["time_to_converge"]["single_gpu_seconds"] = box[0][1]
+            line["time_to_converge"]["counts_match_single_gpu"] = box[0][0] == list(spc)
+            line["parity_vs_single_gpu"] = line["parity_vs_single_gpu"] and box[0][0] == list(spc)
 
     if not args.no_converge and world == 1:
         g.set_Z(g.X)
@@ -415,8 +519,30 @@ def run_gpu(args):
                                     "sweeps": int(sum(emb.sweeps_per_call)), "sweeps_per_call": emb.sweeps_per_call,
                                     "tolerence": 10}
 
+    if world == 1 and name != "products" and args.workload is None and args.scale == 1.0 and not args.no_converge:
+        # the strong-scaling reference of the N > 1 lines, taken by the driver's own N = 1 run as well
+        n2, s2, d2, X2 = synth.make_graph("products", seed=0)
+        g2 = Graph.from_arrays(n2, s2, d2, X2)
+        del s2, d2
+        ms2 = single_gpu_steps(torch, L, _lib, g2, sim, 30)
+        line["products_n1"] = {"workload": "products-shape synthetic", "nodes": n2, "edges": g2._nnz, "dim": int(X2.shape[1]),
+                               "ms_per_step": ms2, "value": g2._nnz / (ms2 * 1e-3), "unit": UNIT,
+                               "whole_step_gbs": sweep_bytes(n2, g2._nnz, int(X2.shape[1])) / (ms2 * 1e-3) / 1e9,
+                               "note": "secondary: the workload of the N > 1 lines on one GPU (30 sweeps, CUDA events); "
+                                       "strong-scaling efficiency at N GPUs = value_N / (N * this value)"}
+        del g2, X2
+
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        ce, threads, times, what = cpu_sweeps(n, src, dst, X, budget_s=12.0, min_sweeps=3, max_sweeps=200,
+        ve, vthreads, vtimes, _ = vectorised_cpu_sweeps(n, src, dst, X)
+        line["cpu_baseline_vectorised"] = {
+            "value": ve / float(np.mean(vtimes)), "unit": UNIT, "cores": vthreads, "kind": "port",
+            "sample": f"{len(vtimes)} whole sweeps, torch-CPU sparse CSR SpMM + axpy + L1 on all host threads "
+                      "(BASELINE.md section 3 item iii; timing only -- torch's summation order, not the reference's)"}
+        line["cpu_baseline_reference_python"] = {
+            "value": None, "unit": UNIT,
+            "sample": "the unmodified reference (pure Python, O(N*E) per sweep; 210 edges/s measured at Cora shape in "
+                      "the build container, BASELINE.md) cannot run here: /root/reference does not exist on the GPU box"}
+        ce, _, threads, times, what = cpu_sweeps(n, src, dst, X, budget_s=12.0, min_sweeps=3, max_sweeps=200,
                                               step_budget_s=4.0)
         timed = times[1:]
         line["cpu_baseline"] = {"value": ce / float(np.mean(timed)), "unit": UNIT, "cores": threads, "kind": "port",
@@ -426,6 +552,8 @@ def run_gpu(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+        if line.get("parity_vs_single_gpu") is False:
+            raise SystemExit("sharded run differs from the single-GPU run")
 
 
 def e2e_session(L, g, X, n, e, d, steps):

@@ -43,7 +43,7 @@ SIGNATURES = {
     "clane_group_schedule": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp,
                                        c_i32p, c_vp, c_i32p, c_vp, c_i32p, c_i32p, c_i32p]),
     "clane_sweep_program": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_vp, C.c_int64,
-                                      c_vp, C.c_int64, c_i64p, c_i64p]),
+                                      c_i64p]),
     "clane_plan_create": (C.c_int, [C.POINTER(c_vp), C.c_int32, C.c_int64, C.c_int32, c_vp, C.c_int32, C.c_int32,
                                     C.c_int32]),
     "clane_plan_destroy": (C.c_int, [c_vp]),

@@ -238,7 +238,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_tasks); cudaFree(plan->d_descs); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_tasks); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubT);
     cudaFree(plan->d_hub_cnt); cudaFree(plan->d_hub_done);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
@@ -267,30 +267,11 @@ int clane_plan_destroy(clane_plan* plan) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct Batch { int m, last, row, u; };
-
-// Descriptors of a task's batches.  The kernel has one batch of loads in flight per warp;
-// the only other decision is when the next 32-edge (offset, w) window is published to the warp's 4-window
-// ring: windows 0 and 1 when the task opens, window q at the first batch that touches window q - 1 (it
-// replaces window q - 4; the reducer, one batch behind, is in window q - 2 or later).
-void emit_descriptors(const std::vector<Batch>& bs, int e_total, std::vector<int32_t>& out) {
-    using namespace clane;
-    int published = 2;
-    for (const Batch& b : bs) {
-        int pub = 0;
-        const int touched = (b.u + b.m - 1) / 32;
-        if (touched + 1 >= published && published * 32 < e_total) { pub = 1; ++published; }
-        out.push_back(b.m | (b.last ? kDescLast : 0) | (pub ? kDescPub : 0) | (b.row << kDescRowShift) |
-                      ((b.u & (kMetaRing - 1)) << kDescMetaShift));
-    }
-}
-
 // hub segments (16 full blocks each, longest rows first), then the spans by edge count, descending
 int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const int32_t* smeta, int32_t n_spans,
                   const int32_t* hrows, int32_t n_hrows, std::vector<clane::SweepTask>& tasks,
-                  std::vector<int32_t>& descs, std::vector<int32_t>& blk0, int64_t* hub_blocks) {
+                  std::vector<int32_t>& blk0, int64_t* hub_blocks) {
     using namespace clane;
-    std::vector<Batch> bs;
     try {
         blk0.assign((size_t)std::max(n_hrows, 1), 0);
         int64_t blocks = 0;
@@ -300,11 +281,8 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
             blk0[h] = (int32_t)blocks;
             for (int32_t b0 = 0; b0 < nblk; b0 += kSegEdges / 8) {
                 const int32_t nbk = std::min<int32_t>(kSegEdges / 8, nblk - b0);
-                bs.clear();
-                for (int32_t j = 0; j < nbk; ++j) bs.push_back(Batch{8, 0, 0, 8 * j});
-                SweepTask t{(int32_t)descs.size(), nbk, a + b0 * 8, nbk * 8, b0, kTaskSegment | (h << kTaskHubShift), (int32_t)blocks, nblk};
-                emit_descriptors(bs, nbk * 8, descs);
-                tasks.push_back(t);
+                tasks.push_back(SweepTask{a + b0 * 8, nbk * 8, b0, kTaskSegment | (h << kTaskHubShift), nbk, (int32_t)blocks,
+                                          nblk, 0});
             }
             blocks += (nblk + 1) & ~1;
         }
@@ -312,22 +290,10 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
         for (int32_t i = 0; i < n_spans; ++i) {
             const int32_t r0 = srow[i], nrows = smeta[i] & 0xff, direct = (smeta[i] >> 8) && fuse;
             const int32_t e0 = h_rowptr[r0];
-            bs.clear();
-            for (int32_t r = 0; r < nrows; ++r) {
-                const int32_t a = h_rowptr[r0 + r], k = h_rowptr[r0 + r + 1] - a;
-                for (int32_t pos = 0; pos < k; pos += 8) {
-                    const int32_t m = std::min(8, k - pos);
-                    bs.push_back(Batch{m, pos + m >= k, r, a + pos - e0});
-                }
-            }
-            SweepTask t{(int32_t)descs.size(), (int32_t)bs.size(), e0, h_rowptr[r0 + nrows] - e0, r0,
-                        nrows | (direct ? kTaskDirect : 0), 0, 0};
-            emit_descriptors(bs, t.e_total, descs);
-            tasks.push_back(t);
-            if (descs.size() > (size_t)INT32_MAX) return CLANE_ERANGE;
+            tasks.push_back(SweepTask{e0, h_rowptr[r0 + nrows] - e0, r0, nrows | (direct ? kTaskDirect : 0), 0, 0, 0, 0});
         }
     } catch (const std::bad_alloc&) {
-        return (int)cudaErrorMemoryAllocation;
+        return CLANE_ENOMEM;
     }
     return CLANE_OK;
 }
@@ -337,33 +303,26 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
 extern "C" {
 
 int clane_sweep_program(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
-                        int32_t hub_threshold, int32_t span_edges, int32_t* h_tasks, int64_t task_cap,
-                        int32_t* h_descs, int64_t desc_cap, int64_t* n_tasks, int64_t* n_descs) {
-    if (!h_rowptr || !n_tasks || !n_descs || n < 0 || row_lo < 0 || row_hi > n || row_lo > row_hi) return CLANE_EINVAL;
+                        int32_t hub_threshold, int32_t span_edges, int32_t* h_tasks, int64_t task_cap, int64_t* n_tasks) {
+    if (!h_rowptr || !n_tasks || n < 0 || row_lo < 0 || row_hi > n || row_lo > row_hi) return CLANE_EINVAL;
     const size_t cap = (size_t)(row_hi - row_lo) + 1;
     try {
-        std::vector<int32_t> srow(cap), smeta(cap), fix(cap), hrows(cap), blk0, descs;
+        std::vector<int32_t> srow(cap), smeta(cap), fix(cap), hrows(cap), blk0;
         std::vector<clane::SweepTask> tasks;
         int32_t n_spans = 0, n_fix = 0, n_hrows = 0, G = 0, fuse = 0;
         int rc = clane_group_schedule(h_rowptr, n, d, row_lo, row_hi, hub_threshold, span_edges, srow.data(), smeta.data(),
                                       &n_spans, fix.data(), &n_fix, hrows.data(), &n_hrows, &G, &fuse);
         if (rc != CLANE_OK) return rc;
         int64_t hub_blocks = 0;
-        rc = build_program(h_rowptr, fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, descs, blk0,
-                           &hub_blocks);
+        rc = build_program(h_rowptr, fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, blk0, &hub_blocks);
         if (rc != CLANE_OK) return rc;
         *n_tasks = (int64_t)tasks.size();
-        *n_descs = (int64_t)descs.size();
         if (h_tasks) {
             if (task_cap < (int64_t)tasks.size()) return CLANE_EWORKSPACE;
             memcpy(h_tasks, tasks.data(), tasks.size() * sizeof(clane::SweepTask));
         }
-        if (h_descs) {
-            if (desc_cap < (int64_t)descs.size()) return CLANE_EWORKSPACE;
-            memcpy(h_descs, descs.data(), descs.size() * sizeof(int32_t));
-        }
     } catch (const std::bad_alloc&) {
-        return (int)cudaErrorMemoryAllocation;
+        return CLANE_ENOMEM;
     }
     return CLANE_OK;
 }
@@ -424,22 +383,19 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
         if ((h_rowptr[hrows[h] + 1] - h_rowptr[hrows[h]]) / 8 >= kLongBlocks) plan->n_long_hub_rows = h + 1;
 
     std::vector<SweepTask> tasks;
-    std::vector<int32_t> descs, blk0;
-    rc = build_program(h_rowptr, plan->fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, descs, blk0,
+    std::vector<int32_t> blk0;
+    rc = build_program(h_rowptr, plan->fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, blk0,
                        &plan->hub_blocks);
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
     // the segments (8 neighbours per block, ~5 G neighbours/s while they are the only tasks running) come first in the
     // row kernel; a chain CTA that has waited twice that long gives up and leaves its row to the late pass
     plan->chain_spin_ns = std::min<unsigned long long>(5000000ull, 300000ull + (unsigned long long)(plan->hub_blocks * 8 * 0.4));
     plan->n_tasks = (int32_t)tasks.size();
-    plan->n_descs = (int64_t)descs.size();
     PLAN_CUDA(cudaMalloc(&plan->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(SweepTask)));
-    PLAN_CUDA(cudaMalloc(&plan->d_descs, std::max<size_t>(descs.size(), 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_info, std::max<size_t>(n_hrows, 1) * sizeof(int4)));
     if (!tasks.empty()) PLAN_CUDA(cudaMemcpy(plan->d_tasks, tasks.data(), tasks.size() * sizeof(SweepTask), cudaMemcpyHostToDevice));
-    if (!descs.empty()) PLAN_CUDA(cudaMemcpy(plan->d_descs, descs.data(), descs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_fix) PLAN_CUDA(cudaMemcpy(plan->d_fix_groups, fix.data(), n_fix * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (n_hrows) {
         PLAN_CUDA(cudaMemcpy(plan->d_hub_rows, hrows.data(), n_hrows * sizeof(int32_t), cudaMemcpyHostToDevice));

@@ -301,7 +301,7 @@ static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur
     p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
     p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
     p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
-    p.tasks = static_cast<const SweepTask*>(plan->d_tasks); p.descs = plan->d_descs; p.n_tasks = plan->n_tasks;
+    p.tasks = static_cast<const SweepTask*>(plan->d_tasks); p.n_tasks = plan->n_tasks;
     p.row_lo = plan->row_lo;
     p.G = plan->G; p.nslab = plan->nslab;
     p.fuse = (plan->fuse && want_l1) ? 1 : 0;

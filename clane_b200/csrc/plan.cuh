@@ -16,11 +16,9 @@ struct clane_plan {
     int32_t span_edges = 128;   // edge budget of a span
     int32_t n_spans = 0, n_fix_groups = 0, n_hub_rows = 0;
     int32_t n_long_hub_rows = 0;   // the first n_long_hub_rows hub rows (degree-descending) have >= kLongBlocks blocks
-    // the sweep's program (sweep.cuh): tasks sorted by work descending (hub segments first), batch descriptors
+    // the sweep's schedule (sweep.cuh): tasks sorted by work descending (hub segments first)
     void* d_tasks = nullptr;           // SweepTask[n_tasks]
-    int32_t* d_descs = nullptr;
     int32_t n_tasks = 0;
-    int64_t n_descs = 0;
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     void* d_hub_info = nullptr;        // int4 per hub row: {row, first edge, degree, first scratch block}

@@ -12,18 +12,17 @@
 // (one float4 of columns per lane) and rows, and memory-level parallelism comes from issuing
 // the (address-independent) gathers ahead of the in-order chains.
 //
-// The graph is static, so ALL control flow of the sweep is precomputed on the host (clane_plan_create,
-// "program"): the kernel only decodes 32-bit batch descriptors.
+// The graph is static, so the schedule of the sweep is made once per graph on the host (clane_plan_create):
 //
-//   task      : one warp per (task, 128-column slab).  A span task is a run of ordinary rows of one row
-//               group (<= span_edges edges); a segment task is 128 neighbours (16 blocks) of a hub row.
-//   batch     : up to 8 neighbours of one row (one 8-block, or the row's k mod 8 leftovers); a row's last
-//               batch also carries the row's X piece and (fused L1) its own Zcur piece.  Every piece is
-//               one 128-bit load per lane straight into registers -- lane L loads exactly the float4 it
-//               will reduce -- and batches are double-buffered: the loads of batch b + 1 are in flight
-//               while batch b is reduced (two 8 x float4 register buffers; no shared-memory staging, so
-//               each gathered byte crosses the SM's L1 / shared-memory data path once, not twice).
-//   descriptor: m | last | publish-meta-window | row | position in the (offset, w) ring.
+//   task      : one warp per (task, 128-column slab).  A span task is a run of consecutive ordinary rows of one
+//               row group (<= span_edges edges, or one longer row); a segment task is 128 neighbours (16 blocks)
+//               of a hub row.  Tasks are sorted by work, descending ("degree-sorted row blocks").
+//   span      : the warp stages the span's (offset, w) pairs in shared memory (one coalesced round trip), takes
+//               the degrees from rowptr, and walks the rows in order: per row the X piece, the row's own Zcur
+//               piece (fused L1) and <= 8 gathers are issued together as 128-bit loads straight into registers
+//               -- lane L loads exactly the float4 it will reduce, so a gathered byte crosses the SM's L1 data
+//               path once -- then reduced in the reference's order.  ~3 instructions per neighbour beside the
+//               arithmetic; one batch of loads in flight per warp, 32 resident warps per SM (64 registers).
 //   hub rows  : the reference's 8-neighbour block is  a = fma(w6,z6,a); a = fma(w4,z4,a); a += X; a += Y
 //               with X = fma(w5,z5,w7*z7), Y = fma(w0,z0,w2*z2) + fma(w1,z1,w3*z3) independent of the
 //               running sum.  Segment tasks (all SMs, inside k_sweep_rows) gather the neighbours and park
@@ -46,7 +45,6 @@ struct SweepParams {
     const float* w;
     float gamma;
     const SweepTask* tasks;     // sorted by work, descending (segments first)
-    const int32_t* descs;
     int n_tasks;
     int row_lo;
     int G;                      // rows per group (<= 32)
@@ -79,9 +77,10 @@ struct SweepParams {
 #endif
 constexpr int kRowWarps = CLANE_ROW_WARPS;     // row kernel: warps (= tasks) per CTA
 constexpr int kRowThreads = 32 * kRowWarps;
-// row kernel shared memory per warp: (offset, w) ring | 512-byte transpose scratch (fused L1) | 10 row-piece slots
-// (8 neighbours + X + own Zcur) of the batch that goes through cp.async
-constexpr size_t kRowWarpSmem = (size_t)(kMetaRing + 8) * sizeof(int2) + 512 + 10 * 512;
+constexpr int kRowWarpsPerSM = CLANE_ROW_WARPS_PER_SM;   // the register budget the row kernel is compiled for
+// row kernel shared memory per warp: (offset, w) window | two 512-byte transpose buffers (fused L1) | the row's X and
+// own Zcur pieces (cp.async) | stream position of a row longer than the window
+constexpr size_t kRowWarpSmem = (size_t)kMetaRing * sizeof(int2) + 2 * 512 + 2 * 512 + 16;
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 
 // hub chain kernel: one warp per CTA
@@ -183,41 +182,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Add one row's |delta| (lane L holds columns 4L..4L+3) to the chunk accumulator, in which lane m owns
-// cascade lane m: the row is d/32 consecutive cascade rows, taken in order.  The float4-per-lane layout is
-// transposed through 512 bytes of the warp's shared memory (one 128-bit store, d/32 32-bit loads).
-__device__ __forceinline__ float chunk_add_row(float chunk_acc, const float4& dl, int nseg, int lane, float* scratch) {
-    __syncwarp();                                              // every lane has read its X / own piece
-    reinterpret_cast<float4*>(scratch)[lane] = dl;
-    __syncwarp();
-#pragma unroll
-    for (int seg = 0; seg < 4; ++seg)
-        if (seg < nseg) chunk_acc = fadd(chunk_acc, scratch[seg * 32 + lane]);
-    return chunk_acc;
-}
-
-// L2 cache-policy hints (evict_last on the Zcur gathers, evict_first on X / Znext) were measured: the sector hit
-// rate stays at 44 % either way and the policy descriptors cost 8 % more instructions (R2UR / UMOV), so plain
-// accesses are used; Znext is written with the streaming (.cs) qualifier.
-// neighbour row piece of this lane: 16 bytes at float4 index `off16` of the lane's column base
-__device__ __forceinline__ float4 gather4(const float4* __restrict__ zb, int off16) {
-    return __ldg(zb + (unsigned)off16);
-}
-
-// Predicated loads in straight-line code.  Inside the pipelined loop every global load is one of these: loads
-// issued under divergent control flow (a switch on the batch length, an if on "last") make ptxas wait for the
-// outstanding loads at the next control-flow join -- which is the loop's back edge, exactly where the next
-// batch's loads must stay in flight.
-__device__ __forceinline__ void ldg4_if(float4& v, const float4* p, bool pred) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred));
-}
-__device__ __forceinline__ void ldg4_stream_if(float4& v, const float* p, bool pred) {   // X
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "@q ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred));
-}
+// Predicated loads in straight-line code (a load under a branch makes ptxas wait for it at the join).
 __device__ __forceinline__ void ldg_i32_if(int& v, const int* p, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
                  : "+r"(v) : "l"(p), "r"((int)pred));
@@ -225,6 +190,30 @@ __device__ __forceinline__ void ldg_i32_if(int& v, const int* p, bool pred) {
 __device__ __forceinline__ void ldg_f32_if(float& v, const float* p, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
                  : "+f"(v) : "l"(p), "r"((int)pred));
+}
+
+// L2 cache-policy hints (evict_last on the Zcur gathers, evict_first on X / Znext) were measured in round 1: the
+// sector hit rate stays at 44 % either way and the policy descriptors cost 8 % more instructions (R2UR / UMOV),
+// so plain accesses are used; Znext is written with the streaming (.cs) qualifier.
+// neighbour row piece of this lane: 16 bytes at float4 index `off16` of the lane's column base
+#ifndef CLANE_DEBUG_GATHER_MASK       // timing experiments only: fold every gather into a small table (wrong results)
+#define CLANE_DEBUG_GATHER_MASK 0xffffffffu
+#endif
+__device__ __forceinline__ float4 gather4(const float4* __restrict__ zb, int off16) {
+#ifdef CLANE_GATHER_NO_L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(zb + ((unsigned)off16 & CLANE_DEBUG_GATHER_MASK)));
+    return v;
+#else
+    return __ldg(zb + ((unsigned)off16 & CLANE_DEBUG_GATHER_MASK));
+#endif
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {   // X: read once per sweep, keep it out of L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 // the gathers of one batch: 128-bit loads straight into registers (lane L loads exactly the float4 of columns it
@@ -235,235 +224,174 @@ __device__ __forceinline__ void load_batch(float4 (&buf)[8], const int2* __restr
     for (int i = 0; i < M; ++i) buf[i] = gather4(zb, mp[i].x);
 }
 
-__device__ __forceinline__ void cp_async16_cg(unsigned smem_addr, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
-}
-// the gathers of one batch through cp.async: slot i of the warp's shared-memory slots <- neighbour i's row piece
+// <= 7 neighbours in the sequential order (a row shorter than 8, or the k mod 8 leftovers of a longer one):
+// (offset, w) pairs out of shared memory, M independent 128-bit gathers, then the fma chain
 template <int M>
-__device__ __forceinline__ void async_batch(unsigned slot_sa, const int2* __restrict__ mp, const float4* __restrict__ zb) {
+__device__ __forceinline__ void seq_batch(const int2* __restrict__ mp, const float4* __restrict__ zb, float4& acc) {
+    int2 m[M];
+    float4 z[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) cp_async16_cg(slot_sa + i * 512, zb + (unsigned)mp[i].x);
-}
-template <int M>
-__device__ __forceinline__ void slot_batch(float4 (&buf)[8], const float4* __restrict__ myslot) {
+    for (int i = 0; i < M; ++i) m[i] = mp[i];
 #pragma unroll
-    for (int i = 0; i < M; ++i) buf[i] = myslot[i * 32];
+    for (int i = 0; i < M; ++i) z[i] = gather4(zb, m[i].x);
+#pragma unroll
+    for (int i = 0; i < M; ++i) fma4(__int_as_float(m[i].y), z[i], acc);
 }
 
-template <int M>
-__device__ __forceinline__ void reduce_batch(const float4 (&z)[8], const int2* __restrict__ mp, float4& acc,
-                                             bool col_blocked) {
+// one full 8-block of a row with k >= 8.  kUniform: every lane of the warp is in the 8-block regime (d % 16 == 0),
+// so the choice is a uniform branch; otherwise lanes at or beyond `limit` run the sequential chain.
+__device__ __forceinline__ void block_batch(const int2* __restrict__ mp, const float4* __restrict__ zb, float4& acc,
+                                            bool all_blocked, bool col_blocked) {
+    int2 m[8];
+    float4 z[8];
     float w[8];
 #pragma unroll
-    for (int i = 0; i < M; ++i) w[i] = __int_as_float(mp[i].y);
-    if (M == 8 && col_blocked) {
+    for (int i = 0; i < 8; ++i) m[i] = mp[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = gather4(zb, m[i].x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __int_as_float(m[i].y);
+    if (all_blocked || col_blocked) {
         blocked8x4(acc, w, z);
     } else {
 #pragma unroll
-        for (int i = 0; i < M; ++i) fma4(w[i], z[i], acc);
+        for (int i = 0; i < 8; ++i) fma4(w[i], z[i], acc);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // row kernel: one warp per (task, 128-column slab)
 // ------------------------------------------------------------------------------------------
-// Per-warp state of the two streams a task reads: batch descriptors (a 32-entry window in registers, read
-// with a shuffle) and (offset, w) pairs (32-edge windows published to a 128-entry shared-memory ring).
-// Everything is an int offset from a kernel parameter (constant bank), not a pointer: registers are what
-// bounds the number of resident warps, and the resident warps are the memory-level parallelism.
-struct Streams {
-    int desc_first, e_first;
-    int nb, e_total;
-    int dwin, dnext;        // descriptor windows: current, prefetched
-    int pc;                 // the next (offset, w) window to publish, held in registers
-    float pw;
-    int win_q;              // (offset, w) windows published so far
-};
-
-__device__ __forceinline__ void publish_window(int q, int pc, float pw, int lane, int2* meta) {
-    const int base = (q & 3) * 32;
-    const int2 v = make_int2(pc, __float_as_int(pw));
-    meta[base + lane] = v;
-    if (base == 0 && lane < 8) meta[kMetaRing + lane] = v;   // mirror: a batch never wraps
-}
-
-// Open a task's streams: descriptor windows 0 and 1 in registers; (offset, w) windows 0 and 1 published
-// (one coalesced round trip for all of it), window 2 on its way.
-__device__ __forceinline__ void open_streams(const SweepParams& p, Streams& s, int lane, int2* meta) {
-    const int32_t* dp = p.descs + s.desc_first;
-    const int* offp = p.coloff + s.e_first;
-    const float* wp = p.w + s.e_first;
-    s.dwin = lane < s.nb ? __ldg(dp + lane) : 0;
-    int c0 = 0, c1 = 0;
-    float w0 = 0.0f, w1 = 0.0f;
-    if (lane < s.e_total) { c0 = __ldg(offp + lane); w0 = __ldg(wp + lane); }
-    if (32 + lane < s.e_total) { c1 = __ldg(offp + 32 + lane); w1 = __ldg(wp + 32 + lane); }
-    s.dnext = 32 + lane < s.nb ? __ldg(dp + 32 + lane) : 0;
-    s.pc = 0; s.pw = 0.0f;
-    if (64 + lane < s.e_total) { s.pc = __ldg(offp + 64 + lane); s.pw = __ldg(wp + 64 + lane); }
-    // the rest of the streams: one L2 prefetch per 128-byte line now, so that the window loads further
-    // down are L2 hits
-    for (int i = 96 + lane * 32; i < s.e_total; i += 32 * 32) { prefetch_l2(offp + i); prefetch_l2(wp + i); }
-    for (int i = 64 + lane * 32; i < s.nb; i += 32 * 32) prefetch_l2(dp + i);
-    publish_window(0, c0, w0, lane, meta);
-    publish_window(1, c1, w1, lane, meta);
+// (offset, w) pairs of up to kMetaRing consecutive edges of the task's stream, starting at edge `e0` (cnt left)
+// -> the warp's shared-memory window.  Four predicated, independent load pairs per lane: one round trip.
+__device__ __forceinline__ void stage_meta(const SweepParams& p, int e0, int cnt, int lane, int2* meta) {
+    const int* __restrict__ offp = p.coloff + e0;
+    const float* __restrict__ wp = p.w + e0;
+    int c[kMetaRing / 32];
+    float w[kMetaRing / 32];
+#pragma unroll
+    for (int q = 0; q < kMetaRing / 32; ++q) {
+        c[q] = 0; w[q] = 0.0f;
+        const int i = q * 32 + lane;
+        ldg_i32_if(c[q], offp + i, i < cnt);
+        ldg_f32_if(w[q], wp + i, i < cnt);
+    }
+#pragma unroll
+    for (int q = 0; q < kMetaRing / 32; ++q) meta[q * 32 + lane] = make_int2(c[q], __float_as_int(w[q]));
     __syncwarp();
-    s.win_q = 2;
+}
+// the next window of a row longer than kMetaRing (a span of its own): the stream position lives in shared memory,
+// not in registers the common path would have to carry
+__device__ __noinline__ void restage_meta(const SweepParams& p, int lane, int2* meta, int* state) {
+    __syncwarp();                              // every lane has read the old window
+    const int e0 = state[0] + kMetaRing, left = state[1] - kMetaRing;
+    __syncwarp();
+    if (lane == 0) { state[0] = e0; state[1] = left; }
+    stage_meta(p, e0, left, lane, meta);
 }
 
-// descriptor of batch ib; afterwards the (offset, w) ring holds the batch's edges
-// kMayRoll = false for odd batch indices: the 32-descriptor window only rolls over at multiples of 32
-template <bool kMayRoll>
-__device__ __forceinline__ int next_desc(const SweepParams& p, Streams& s, int ib, int lane, int2* meta) {
-    if (kMayRoll) {
-        const bool roll = (ib & 31) == 0 && ib > 0;
-        if (roll) { s.dwin = s.dnext; s.dnext = 0; }
-        ldg_i32_if(s.dnext, p.descs + (s.desc_first + ib + 32 + lane), roll && ib + 32 + lane < s.nb);   // int index first: one IMAD.WIDE
-    }
-    const int id = __shfl_sync(kFull, s.dwin, ib & 31);
-    const bool pub = (id & kDescPub) != 0;
-    if (pub) {
-        // This batch is the first to touch window win_q - 1: publish window win_q (fetched a whole window ago;
-        // it replaces window win_q - 4, which the previous batch has left) and fetch the next into the same
-        // registers.
-        publish_window(s.win_q, s.pc, s.pw, lane, meta);
-        __syncwarp();
-        ++s.win_q;
-    }
-    const int off = s.win_q * 32 + lane;
-    const bool fetch = pub && off < s.e_total;
-    const int eidx = s.e_first + off;
-    ldg_i32_if(s.pc, p.coloff + eidx, fetch);
-    ldg_f32_if(s.pw, p.w + eidx, fetch);
-    return id;
-}
-
-// span task: one batch per round -- descriptor, <= 10 loads straight into registers, reduction.  A warp has one
-// batch of loads in flight; the memory-level parallelism comes from the resident warps per SM (measured with
-// tools/l1pf_probe.cu: deeper per-warp pipelines or L1 / L2 prefetching do not beat more warps).
-__device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, const int4 t1, int slab, int lane,
-                                         int2* meta, float* scratch, float4* slots) {
+// Span task: a run of consecutive ordinary rows of one row group (a whole group when `direct`), one row at a time:
+// the row's X piece, its own Zcur piece (fused L1) and <= 8 gathers are issued together and reduced in the
+// reference's order -- one memory round trip per 8 neighbours.  No descriptors: the degrees come from rowptr (lane r
+// holds row r0 + r), the edges from the staged window.  The gathers are 128-bit loads straight into registers;
+// X and the own piece go through cp.async into 1 KB of the warp's shared memory, so that the 8 registers they
+// would occupy while the gathers are in flight are free: the kernel fits 64 registers = 32 resident warps per SM,
+// each with one batch of loads in flight (tools/l1pf_probe.cu: resident warps beat deeper per-warp pipelines on
+// this access pattern).
+__device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, int slab, int lane, int2* meta, float* scratch,
+                                         float4* rowbuf, int* state) {
+    const int r0 = t0.z, nrows = t0.w & 0xff;
+    const bool direct = (t0.w & kTaskDirect) != 0 && p.fuse != 0;
     const int c0 = slab * 128 + lane * 4;
     const bool active = c0 < p.ld;
-    const bool col_blocked = c0 < p.limit;
     const int cc = active ? c0 : 0;            // idle lanes shadow lane 0 (same sectors: no extra traffic)
-    const int r0 = t1.x;
-    const bool direct = (t1.y & kTaskDirect) != 0;   // runtime, not a template: one copy of the code in the instruction cache
-    Streams s;
-    s.desc_first = t0.x; s.nb = t0.y; s.e_first = t0.z; s.e_total = t0.w;
-    open_streams(p, s, lane, meta);
-
+    const bool col_blocked = cc < p.limit;
+    const bool all_blocked = p.limit == p.ld;  // uniform
+    const int rp = __ldg(p.rowptr + r0 + min(lane, nrows));
+    if (lane == 0) { state[0] = t0.x; state[1] = t0.y; }
+    stage_meta(p, t0.x, t0.y, lane, meta);
+    const int deg = __shfl_down_sync(kFull, rp, 1) - rp;
     const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
-    const unsigned slot_sa = smem_u32(slots) + lane * 16;      // this lane's 16 bytes of slot 0
-    const float4* myslot = slots + lane;
-    float4 A[8], xs, own;
-    xs = own = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned rowbuf_sa = smem_u32(rowbuf + lane);
+    const int nseg = p.d >> 5;
+    int mpos = 0;                              // position inside the window
     float chunk_acc = 0.0f;
-    const int nb = s.nb;
-
-    auto finish = [&](const float4& xv, const float4& ov, int row_off) {
-        const float4 out = finish_row(xv, acc, p.gamma);
+    for (int r = 0; r < nrows; ++r) {
+        int k = __shfl_sync(kFull, deg, r);
+        if (k == 0) continue;                  // a sink inside the span: never updated (embedder.py:88-89), |delta| = +0
+        {
+            const int row_off = (r0 + r) * p.ld + cc;      // n * ld < 2^31 (clane_plan_create)
+            cp_async16_sa(rowbuf_sa, p.X + row_off);
+            if (direct) cp_async16_sa(rowbuf_sa + 512, p.Zc + row_off);
+            cp_async_commit();
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; k >= 8; k -= 8) {
+            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; }
+            block_batch(meta + mpos, zb, acc, all_blocked, col_blocked);
+            mpos += 8;
+        }
+        if (k != 0) {
+            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; }
+            const int2* mp = meta + mpos;
+            switch (k) {
+                case 1: seq_batch<1>(mp, zb, acc); break;
+                case 2: seq_batch<2>(mp, zb, acc); break;
+                case 3: seq_batch<3>(mp, zb, acc); break;
+                case 4: seq_batch<4>(mp, zb, acc); break;
+                case 5: seq_batch<5>(mp, zb, acc); break;
+                case 6: seq_batch<6>(mp, zb, acc); break;
+                default: seq_batch<7>(mp, zb, acc); break;
+            }
+            mpos += k;
+        }
+        cp_async_wait<0>();                    // each lane reads back the 16 bytes it copied itself: no barrier
+        const float4 out = finish_row(rowbuf[lane], acc, p.gamma);
+        const int row_off = (r0 + r) * p.ld + cc;
         if (active) {
             st_stream4(p.Zn + row_off, out);
             if (p.mc != nullptr) multimem_st4(p.mc + row_off, out);
             for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
         }
         if (direct) {
-            const float4 dl = active ? absdiff4(out, ov) : make_float4(0.f, 0.f, 0.f, 0.f);
-            chunk_acc = chunk_add_row(chunk_acc, dl, p.d >> 5, lane, scratch);
-        }
-        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-
-    // Two batches in flight per warp, on two independent completion mechanisms: the odd batch goes through
-    // cp.async into the warp's 10 shared-memory slots (completion = async group), the even batch straight into
-    // registers (completion = scoreboard).  Both are issued before either is reduced; the reductions then run in
-    // order.  (Two register buffers would cost 32 more registers, i.e. a fifth of the resident warps; and ptxas
-    // tracks all 128-bit loads of a warp on one scoreboard, so waiting for the first would wait for both anyway.)
-    for (int cb = 0; cb < nb; cb += 2) {
-        const int idr = next_desc<true>(p, s, cb, lane, meta);
-        const bool has_s = cb + 1 < nb;
-        const int ids = has_s ? next_desc<false>(p, s, cb + 1, lane, meta) : 0;
-        // ---- odd batch: cp.async ----
-        const int2* mps = meta + ((ids >> kDescMetaShift) & 127);
-        const int row_off_s = (r0 + ((ids >> kDescRowShift) & 31)) * p.ld + cc;   // n * ld < 2^31 (clane_plan_create)
-        const bool last_s = (ids & kDescLast) != 0;
-        switch (ids & 15) {
-            case 8: async_batch<8>(slot_sa, mps, zb); break;
-            case 7: async_batch<7>(slot_sa, mps, zb); break;
-            case 6: async_batch<6>(slot_sa, mps, zb); break;
-            case 5: async_batch<5>(slot_sa, mps, zb); break;
-            case 4: async_batch<4>(slot_sa, mps, zb); break;
-            case 3: async_batch<3>(slot_sa, mps, zb); break;
-            case 2: async_batch<2>(slot_sa, mps, zb); break;
-            case 1: async_batch<1>(slot_sa, mps, zb); break;
-            default: break;
-        }
-        if (last_s) {
-            cp_async16_cg(slot_sa + 8 * 512, p.X + row_off_s);
-            if (direct) cp_async16_cg(slot_sa + 9 * 512, p.Zc + row_off_s);
-        }
-        cp_async_commit();
-        // ---- even batch: registers; loads and reduction in the same switch case ----
-        const int2* mp = meta + ((idr >> kDescMetaShift) & 127);
-        const bool last = (idr & kDescLast) != 0;
-        const int row_off = (r0 + ((idr >> kDescRowShift) & 31)) * p.ld + cc;
-        // the row's X and own Zcur pieces ride with its last batch (predicated, straight-line: a branch here
-        // would make ptxas wait for them at the join, before the gathers are even issued)
-        ldg4_stream_if(xs, p.X + row_off, last);
-        ldg4_if(own, reinterpret_cast<const float4*>(p.Zc + row_off), last && direct);
-        switch (idr & 15) {
-            case 8: load_batch<8>(A, mp, zb); reduce_batch<8>(A, mp, acc, col_blocked); break;
-            case 7: load_batch<7>(A, mp, zb); reduce_batch<7>(A, mp, acc, col_blocked); break;
-            case 6: load_batch<6>(A, mp, zb); reduce_batch<6>(A, mp, acc, col_blocked); break;
-            case 5: load_batch<5>(A, mp, zb); reduce_batch<5>(A, mp, acc, col_blocked); break;
-            case 4: load_batch<4>(A, mp, zb); reduce_batch<4>(A, mp, acc, col_blocked); break;
-            case 3: load_batch<3>(A, mp, zb); reduce_batch<3>(A, mp, acc, col_blocked); break;
-            case 2: load_batch<2>(A, mp, zb); reduce_batch<2>(A, mp, acc, col_blocked); break;
-            default: load_batch<1>(A, mp, zb); reduce_batch<1>(A, mp, acc, col_blocked); break;
-        }
-        if (last) finish(xs, own, row_off);
-        // ---- reduce the odd batch out of shared memory (each lane reads the 16 bytes it copied: no barrier) ----
-        cp_async_wait<0>();
-        if (has_s) {
-            switch (ids & 15) {
-                case 8: slot_batch<8>(A, myslot); reduce_batch<8>(A, mps, acc, col_blocked); break;
-                case 7: slot_batch<7>(A, myslot); reduce_batch<7>(A, mps, acc, col_blocked); break;
-                case 6: slot_batch<6>(A, myslot); reduce_batch<6>(A, mps, acc, col_blocked); break;
-                case 5: slot_batch<5>(A, myslot); reduce_batch<5>(A, mps, acc, col_blocked); break;
-                case 4: slot_batch<4>(A, myslot); reduce_batch<4>(A, mps, acc, col_blocked); break;
-                case 3: slot_batch<3>(A, myslot); reduce_batch<3>(A, mps, acc, col_blocked); break;
-                case 2: slot_batch<2>(A, myslot); reduce_batch<2>(A, mps, acc, col_blocked); break;
-                default: slot_batch<1>(A, myslot); reduce_batch<1>(A, mps, acc, col_blocked); break;
-            }
-            if (last_s) finish(myslot[8 * 32], myslot[9 * 32], row_off_s);
+            // the row is d / 32 consecutive cascade rows: transpose the float4-per-lane |delta| through 512 bytes of
+            // shared memory (two buffers, alternating: the next row's barrier orders this row's reads before the
+            // buffer's next use) and add them to the chunk accumulator in order
+            const float4 dl = active ? absdiff4(out, rowbuf[32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* sc = scratch + (r & 1) * 128;
+            reinterpret_cast<float4*>(sc)[lane] = dl;
+            __syncwarp();
+#pragma unroll
+            for (int seg = 0; seg < 4; ++seg)
+                if (seg < nseg) chunk_acc = fadd(chunk_acc, sc[seg * 32 + lane]);
         }
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
-    if (direct && p.fuse) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
+    if (direct) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
 }
 
 // hub segment task: up to 16 full 8-blocks of one hub row; park {z6, z4, X, Y} per (block, column), or the
 // raw z in the sequential regime, for k_hub_chain
 __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0, const int4 t1, int slab, int lane,
                                             int2* meta) {
+    // t0 = {first edge, edges, first 8-block within the hub row, flags}; t1 = {blocks, first scratch block of the row,
+    // 8-blocks of the row, -}
     const int c0 = slab * 128 + lane * 4;
     const bool active = c0 < p.ld, col_blocked = c0 < p.limit;
     const int cc = active ? c0 : 0;
     const float4* zb = reinterpret_cast<const float4*>(p.Zc + cc);
-    const int nb = t0.y, b_first = t1.x, nblk_row = t1.w;
-    const size_t B0 = (size_t)t1.z;
+    const int nb = t1.x, b_first = t0.z, nblk_row = t1.z;
+    const size_t B0 = (size_t)t1.y;
     // lane's four columns c0..c0+3 sit in 32-column slab c0 / 32 of the row's scratch: [slab][block][32]
     float4* sdst = p.hubS + B0 * p.sld + ((size_t)(cc >> 5) * nblk_row + b_first) * 32 + (cc & 31);
     // sequential-regime scratch of the row: [column][8 * nblk_row] floats; this lane's first column, this segment
     float* tdst = reinterpret_cast<float*>(p.hubT) + B0 * 32 * p.ntail4 +
                   (size_t)(col_blocked ? 0 : cc - p.limit) * nblk_row * 8 + (size_t)b_first * 8;
-    const int* __restrict__ offp = p.coloff + t0.z;
-    const float* __restrict__ wp = p.w + t0.z;
+    const int* __restrict__ offp = p.coloff + t0.x;
+    const float* __restrict__ wp = p.w + t0.x;
     // a segment is at most 128 edges: the whole (offset, w) stream fits the ring
     const int slab_bytes = min(128, p.ld - slab * 128) * 4;
-    for (int i = lane; i < t0.w; i += 32) {
+    for (int i = lane; i < t0.y; i += 32) {
         const int off16 = __ldg(offp + i);
         meta[i] = make_int2(off16, __float_as_int(__ldg(wp + i)));
         if (i >= 16) {   // the first two blocks are loaded right away
@@ -507,25 +435,25 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
     __threadfence();
     __syncwarp();
-    if (lane == 0) atomicAdd(p.hub_cnt + (t1.y >> kTaskHubShift), 1);
+    if (lane == 0) atomicAdd(p.hub_cnt + (t0.w >> kTaskHubShift), 1);
 }
 
-__global__ void __launch_bounds__(kRowThreads, CLANE_ROW_OCC * 4 / kRowWarps) k_sweep_rows(SweepParams p) {
+__global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
     if (p.st != nullptr && p.st->stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     int2* meta = reinterpret_cast<int2*>(mine);
-    float* scratch = reinterpret_cast<float*>(meta + kMetaRing + 8);
-    float4* slots = reinterpret_cast<float4*>(scratch + 128);
+    float* scratch = reinterpret_cast<float*>(meta + kMetaRing);
+    float4* rowbuf = reinterpret_cast<float4*>(scratch + 256);
+    int* state = reinterpret_cast<int*>(rowbuf + 64);
     const int wtask = blockIdx.x * kRowWarps + warp;
     int ti = wtask, slab = 0;
     if (p.nslab > 1) { ti = wtask / p.nslab; slab = wtask - ti * p.nslab; }
     if (ti >= p.n_tasks) return;
     const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
-    const int4 t1 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1);
-    if (t1.y & kTaskSegment) run_segment(p, t0, t1, slab, lane, meta);
-    else run_span(p, t0, t1, slab, lane, meta, scratch, slots);
+    if (t0.w & kTaskSegment) run_segment(p, t0, __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1), slab, lane, meta);
+    else run_span(p, t0, slab, lane, meta, scratch, rowbuf, state);
 }
 
 // ------------------------------------------------------------------------------------------

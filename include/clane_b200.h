@@ -105,8 +105,6 @@ int clane_edges_close(clane_edge_file* f);
  *   - the ordinary rows of a group are cut into spans of bounded edge count, sorted by edge
  *     count descending, one warp per (span, 128-column slab); groups of sinks only are dropped
  *     (embedder.py:88-89: such rows are never updated);
- *   - the control flow of the sweep kernel (batch sizes, row ends, window refills) is
- *     precomputed into 32-bit batch descriptors: see clane_sweep_program.
  * hub_threshold <= 0 selects the default: (edges of rows [row_lo, row_hi)) / 4096 rounded up to a
  * multiple of 8, clamped to [256, 16384] (a row is an in-order chain on one warp; this bounds it
  * to a few percent of a sweep).
@@ -125,18 +123,16 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
                          int32_t hub_threshold, int32_t span_edges, int32_t* h_span_row, int32_t* h_span_meta,
                          int32_t* n_spans, int32_t* h_fix_groups, int32_t* n_fix_groups, int32_t* h_hub_rows,
                          int32_t* n_hub_rows, int32_t* group_rows, int32_t* fused_l1);
-/* The sweep kernel's program for that schedule, on the host (what clane_plan_create uploads).
- *   h_tasks : 8 int32 per task {first descriptor, batches, first edge, edges, first row (span) or
- *             first 8-block within the hub row (segment), rows | direct << 8 | segment << 9,
- *             first scratch block of the hub row (segment), 8-blocks of the hub row (segment)};
- *             hub segments first (rows by degree, descending), then spans by edge count descending
- *   h_descs : one int32 per batch (<= 8 neighbours of one row):  m | last << 4 | publish the
- *             next 32-edge (offset, w) window first << 5 | row in span << 6 | (edge offset in
- *             the task's stream mod 128) << 19.
- * Either buffer may be NULL (sizes only); CLANE_EWORKSPACE if a capacity is too small. */
+/* The sweep kernel's task list for that schedule, on the host (what clane_plan_create uploads).
+ *   h_tasks : 8 int32 per task {first edge, edges, first row (span) or first 8-block within the hub row
+ *             (segment), rows | direct << 8 | segment << 9 | hub row index << 10, 8-blocks of the segment,
+ *             first scratch block of the hub row (segment), 8-blocks of the hub row (segment), 0};
+ *             hub segments first (rows by degree, descending), then spans by edge count descending.
+ *             A span's warp takes the row lengths from rowptr and walks the rows in order.
+ * h_tasks may be NULL (size only); CLANE_EWORKSPACE if task_cap is too small. */
 int clane_sweep_program(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi,
                         int32_t hub_threshold, int32_t span_edges, int32_t* h_tasks, int64_t task_cap,
-                        int32_t* h_descs, int64_t desc_cap, int64_t* n_tasks, int64_t* n_descs);
+                        int64_t* n_tasks);
 int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const int32_t* h_rowptr,
                       int32_t row_lo, int32_t row_hi, int32_t hub_threshold);
 int clane_plan_destroy(clane_plan* plan);

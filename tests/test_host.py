@@ -305,84 +305,61 @@ def test_cli_missing_config_and_unknown_method(tmp_path, data_root):
 
 
 # ---------------------------------------------------------------------------------------------
-# the sweep kernel's program: a host emulation of k_sweep_rows' control flow (sweep.cuh run_task)
+# the sweep kernel's task list: a host emulation of k_sweep_rows' control flow (run_span / run_segment in sweep.cuh)
 # ---------------------------------------------------------------------------------------------
 def sweep_program(rowptr, n, d, lo, hi, hub, span_edges=128):
     L = _lib.lib()
-    nt, nd = ctypes.c_int64(), ctypes.c_int64()
-    _lib.check(L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, 0, 0, 0, 0, ctypes.byref(nt),
-                                     ctypes.byref(nd)))
+    nt = ctypes.c_int64()
+    _lib.check(L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, 0, 0, ctypes.byref(nt)))
     tasks = np.zeros((max(nt.value, 1), 8), np.int32)
-    descs = np.zeros(max(nd.value, 1), np.int32)
     _lib.check(L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, tasks.ctypes.data, nt.value,
-                                     descs.ctypes.data, nd.value, ctypes.byref(nt), ctypes.byref(nd)))
+                                     ctypes.byref(nt)))
     assert L.clane_sweep_program(rowptr.ctypes.data, n, d, lo, hi, hub, span_edges, tasks.ctypes.data, nt.value - 1,
-                                 0, 0, ctypes.byref(nt), ctypes.byref(nd)) == (-3 if nt.value else 0)
-    return tasks[:nt.value], descs[:nd.value]
+                                 ctypes.byref(nt)) == (-3 if nt.value else 0)
+    return tasks[:nt.value]
 
 
-def emulate_task(task, descs):
-    """Walk one task exactly as a warp of k_sweep_rows does (run_span / run_segment in sweep.cuh), with edge ids
-    instead of data.  Returns (segment, direct, [(row or scratch block, [edge ids in reduction order])])."""
-    desc_first, nb, e_first, e_total, r0, flags, blk_base, nblk_row = (int(x) for x in task)
+def emulate_task(task, rowptr):
+    """Walk one task exactly as a warp of k_sweep_rows does, with edge ids instead of data.  Returns
+    (segment, direct, [(row or scratch block, [edge ids in reduction order])])."""
+    e_first, e_total, r0, flags, nb, blk_base, nblk_row, _ = (int(x) for x in task)
     segment, direct, nrows = bool(flags & 512), bool(flags & 256), flags & 0xff
-    dp = descs[desc_first:desc_first + nb]
-    if segment:        # whole (offset, w) stream in the ring, batches of 8 in order
+    if segment:        # whole (offset, w) stream in the window, batches of 8 in order
         assert e_total <= 128 and e_total == 8 * nb and r0 + nb <= nblk_row
         return True, False, [(blk_base + r0 + b, list(range(e_first + 8 * b, e_first + 8 * b + 8))) for b in range(nb)]
-    meta = [None] * (128 + 8)             # (offset, w) ring with 8 mirrored entries -> stream offset held
-    state = {"dwin": [int(dp[l]) if l < nb else 0 for l in range(32)],
-             "dnext": [int(dp[32 + l]) if 32 + l < nb else 0 for l in range(32)], "win_q": 0}
+    # span: degrees from rowptr (lane r holds row r0 + r), a 128-entry window of the edge stream, restaged when a
+    # batch starts at its end (only a single row longer than the window gets there)
+    assert 1 <= nrows <= 32 and e_first == rowptr[r0] and e_total == rowptr[r0 + nrows] - e_first
+    nonsink = sum(1 for r in range(nrows) if rowptr[r0 + r + 1] > rowptr[r0 + r])
+    assert e_total <= 128 or nonsink == 1          # a row longer than the window is the only row with edges in its span
+    state = [e_first, e_total]
+    window = list(range(e_first, e_first + min(e_total, 128)))
+    mpos, out = 0, []
 
-    def publish(q):
-        base = (q & 3) * 32
-        for lane in range(32):
-            meta[base + lane] = q * 32 + lane if q * 32 + lane < e_total else None
-            if base == 0 and lane < 8:
-                meta[128 + lane] = meta[base + lane]
+    def batch(m):
+        nonlocal mpos, window
+        if mpos == 128:
+            state[0] += 128
+            state[1] -= 128
+            assert state[1] > 0
+            window = list(range(state[0], state[0] + min(state[1], 128)))
+            mpos = 0
+        assert mpos + m <= len(window), "batch runs past the staged window"
+        got = window[mpos:mpos + m]
+        mpos += m
+        return got
 
-    publish(0)
-    publish(1)
-    state["win_q"] = 2
-
-    def next_desc(ib):
-        if ib % 32 == 0 and ib > 0:
-            state["dwin"] = state["dnext"]
-            state["dnext"] = [int(dp[ib + 32 + l]) if ib + 32 + l < nb else 0 for l in range(32)]
-        idesc = state["dwin"][ib & 31]
-        assert idesc == int(dp[ib])
-        if idesc & 32:
-            assert state["win_q"] * 32 < e_total, "published a window past the end of the stream"
-            publish(state["win_q"])
-            state["win_q"] += 1
-        return idesc
-
-    def issue(idesc):       # what the loads of this batch fetch
-        m, mi = idesc & 15, (idesc >> 19) & 127
-        assert 1 <= m <= 8 and (idesc >> 11) & 0xff == 0
-        u = meta[mi]
-        assert u is not None and u % 128 == mi
-        for i in range(m):
-            assert meta[mi + i] == u + i, "(offset, w) ring does not hold the batch's edges"
-        row = r0 + ((idesc >> 6) & 31) if idesc & 16 else None
-        return [e_first + u + i for i in range(m)], row
-
-    def consume(idesc, loaded):
-        m, mi = idesc & 15, (idesc >> 19) & 127
-        edges, row = loaded
-        for i in range(m):          # the weights are read from the ring after the loads: it must still hold them
-            assert e_first + meta[mi + i] == edges[i]
-        cur.extend(edges)
-        if idesc & 16:
-            assert row is not None and row < r0 + nrows
-            out.append((row, list(cur)))
-            cur.clear()
-
-    out, cur = [], []
-    for cb in range(nb):    # one batch per round: descriptor, loads, reduction
-        idesc = next_desc(cb)
-        consume(idesc, issue(idesc))
-    assert not cur
+    for r in range(nrows):
+        k = int(rowptr[r0 + r + 1] - rowptr[r0 + r])
+        if k == 0:
+            continue
+        cur = []
+        while k >= 8:
+            cur += batch(8)
+            k -= 8
+        if k:
+            cur += batch(k)
+        out.append((r0 + r, cur))
     return False, direct, out
 
 
@@ -401,20 +378,20 @@ def test_sweep_program_covers_every_edge_in_order(d, lo, hi, hub):
     g = Graph.from_arrays(n, src, dst, np.zeros((n, 4), np.float32))
     rowptr = g._rowptr
     k = np.diff(rowptr)
-    tasks, descs = sweep_program(rowptr, n, d, lo, hi, hub)
+    tasks = sweep_program(rowptr, n, d, lo, hi, hub)
     sr, sm, fx, hr, G, fused = group_schedule(rowptr, n, d, lo, hi, hub, 128)
     seen_rows, seen_blocks, n_seg = {}, {}, 0
     work = []
     for t in tasks:
-        segment, direct, out = emulate_task(t, descs)
-        work.append((not segment, -int(t[3])))
+        segment, direct, out = emulate_task(t, rowptr)
+        work.append((not segment, -int(t[1])))
         if segment:
             n_seg += 1
             for blk, edges in out:
                 assert blk not in seen_blocks
                 seen_blocks[blk] = edges
         else:
-            assert direct == (fused and any(int(r) == int(t[4]) and (m >> 8) for r, m in zip(sr, sm)))
+            assert direct == (fused and any(int(r) == int(t[2]) and (m >> 8) for r, m in zip(sr, sm)))
             for row, edges in out:
                 assert row not in seen_rows
                 seen_rows[row] = edges
