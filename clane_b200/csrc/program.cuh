@@ -4,7 +4,7 @@
 
 // resident warps per SM the row kernel is compiled for (register budget: 65536 / (32 * warps) per thread)
 #ifndef CLANE_ROW_WARPS_PER_SM
-#define CLANE_ROW_WARPS_PER_SM 32
+#define CLANE_ROW_WARPS_PER_SM 24
 #endif
 
 namespace clane {

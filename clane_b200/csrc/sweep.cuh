@@ -33,6 +33,10 @@
 #include "common.cuh"
 #include "program.cuh"
 
+#ifndef CLANE_DEBUG_GATHER_MASK       // timing experiments only: fold every gather into a small table (wrong results)
+#define CLANE_DEBUG_GATHER_MASK 0xffffffffu
+#endif
+
 namespace clane {
 
 struct SweepParams {
@@ -196,9 +200,6 @@ __device__ __forceinline__ void ldg_f32_if(float& v, const float* p, bool pred) 
 // sector hit rate stays at 44 % either way and the policy descriptors cost 8 % more instructions (R2UR / UMOV),
 // so plain accesses are used; Znext is written with the streaming (.cs) qualifier.
 // neighbour row piece of this lane: 16 bytes at float4 index `off16` of the lane's column base
-#ifndef CLANE_DEBUG_GATHER_MASK       // timing experiments only: fold every gather into a small table (wrong results)
-#define CLANE_DEBUG_GATHER_MASK 0xffffffffu
-#endif
 __device__ __forceinline__ float4 gather4(const float4* __restrict__ zb, int off16) {
 #ifdef CLANE_GATHER_NO_L1
     float4 v;
@@ -262,6 +263,28 @@ __device__ __forceinline__ void block_batch(const int2* __restrict__ mp, const f
 // ------------------------------------------------------------------------------------------
 // row kernel: one warp per (task, 128-column slab)
 // ------------------------------------------------------------------------------------------
+#ifndef CLANE_PF_AHEAD
+#define CLANE_PF_AHEAD 0       // window positions the L2 prefetch of neighbour rows runs ahead of the gathers (0: off)
+#endif
+#ifndef CLANE_PF_XOWN
+#define CLANE_PF_XOWN 1        // request the span's X / own Zcur lines when the span opens
+#endif
+// L2 prefetch of the neighbour rows of window entries [pf, pf + 8): lane L takes line L % 4 of entry pf + L / 4, so
+// one instruction covers the 8 x 512 bytes of a whole batch.  The kernel is bound by the latency of its gathers
+// (a batch waits for the slowest of <= 8 rows, and half of them miss the L2): a row requested one or two batches
+// early turns that DRAM round trip into an L2 hit.  No register, no scoreboard: fire and forget.
+__device__ __forceinline__ void prefetch_batch(const float* zslab, int slab_bytes, const int2* meta, int pf, int cnt, int lane) {
+    const int i = pf + (lane >> 2), line = (lane & 3) * 128;
+    if (i < cnt && line < slab_bytes) {
+        const char* a = reinterpret_cast<const char*>(zslab) + (size_t)((unsigned)meta[i].x & CLANE_DEBUG_GATHER_MASK) * 16 + line;
+#ifdef CLANE_PF_L1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#else
+        prefetch_l2(a);
+#endif
+    }
+}
+
 // (offset, w) pairs of up to kMetaRing consecutive edges of the task's stream, starting at edge `e0` (cnt left)
 // -> the warp's shared-memory window.  Four predicated, independent load pairs per lane: one round trip.
 __device__ __forceinline__ void stage_meta(const SweepParams& p, int e0, int cnt, int lane, int2* meta) {
@@ -316,23 +339,53 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, in
     const int nseg = p.d >> 5;
     int mpos = 0;                              // position inside the window
     float chunk_acc = 0.0f;
+    const float* zslab = p.Zc + slab * 128;
+    const int slab_bytes = min(128, p.ld - slab * 128) * 4;
+    int wcnt = min(t0.y, kMetaRing), pf = 0;   // entries in the window; entries whose rows are already requested
+    if (CLANE_PF_XOWN) {
+        // the rows' X and own Zcur pieces, known in advance: request the span's lines now
+        if (p.nslab == 1) {                    // consecutive rows are contiguous: one line per lane
+            const int bytes = nrows * p.ld * 4, o = lane * 128;
+            if (o < bytes) {
+                prefetch_l2(reinterpret_cast<const char*>(p.X + (size_t)r0 * p.ld) + o);
+                if (direct) prefetch_l2(reinterpret_cast<const char*>(p.Zc + (size_t)r0 * p.ld) + o);
+            }
+        } else if ((lane >> 2) < nrows && (lane & 3) * 128 < slab_bytes) {
+            const size_t o = ((size_t)(r0 + (lane >> 2)) * p.ld + slab * 128) * 4 + (lane & 3) * 128;
+            prefetch_l2(reinterpret_cast<const char*>(p.X) + o);
+        }
+    }
+    if (CLANE_PF_AHEAD > 0)
+        for (; pf < CLANE_PF_AHEAD && pf < wcnt; pf += 8) prefetch_batch(zslab, slab_bytes, meta, pf, wcnt, lane);
     for (int r = 0; r < nrows; ++r) {
         int k = __shfl_sync(kFull, deg, r);
         if (k == 0) continue;                  // a sink inside the span: never updated (embedder.py:88-89), |delta| = +0
         {
+#ifdef CLANE_DEBUG_ROW0          // timing experiments only: every row's X / own / Znext piece is row 0's (wrong results)
+            const int row_off = cc;
+#else
             const int row_off = (r0 + r) * p.ld + cc;      // n * ld < 2^31 (clane_plan_create)
+#endif
             cp_async16_sa(rowbuf_sa, p.X + row_off);
             if (direct) cp_async16_sa(rowbuf_sa + 512, p.Zc + row_off);
             cp_async_commit();
         }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (; k >= 8; k -= 8) {
-            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; }
+            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; pf = 0; wcnt = min(state[1], kMetaRing); }
+            if (CLANE_PF_AHEAD > 0 && pf < wcnt && pf < mpos + 8 + CLANE_PF_AHEAD) {
+                prefetch_batch(zslab, slab_bytes, meta, pf, wcnt, lane);
+                pf += 8;
+            }
             block_batch(meta + mpos, zb, acc, all_blocked, col_blocked);
             mpos += 8;
         }
         if (k != 0) {
-            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; }
+            if (mpos == kMetaRing) { restage_meta(p, lane, meta, state); mpos = 0; pf = 0; wcnt = min(state[1], kMetaRing); }
+            if (CLANE_PF_AHEAD > 0 && pf < wcnt && pf < mpos + 8 + CLANE_PF_AHEAD) {
+                prefetch_batch(zslab, slab_bytes, meta, pf, wcnt, lane);
+                pf += 8;
+            }
             const int2* mp = meta + mpos;
             switch (k) {
                 case 1: seq_batch<1>(mp, zb, acc); break;
@@ -347,7 +400,11 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, in
         }
         cp_async_wait<0>();                    // each lane reads back the 16 bytes it copied itself: no barrier
         const float4 out = finish_row(rowbuf[lane], acc, p.gamma);
+#ifdef CLANE_DEBUG_ROW0
+        const int row_off = cc;
+#else
         const int row_off = (r0 + r) * p.ld + cc;
+#endif
         if (active) {
             st_stream4(p.Zn + row_off, out);
             if (p.mc != nullptr) multimem_st4(p.mc + row_off, out);
