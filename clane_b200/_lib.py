@@ -25,6 +25,9 @@ class Patience(C.Structure):
                 ("max_sweeps", C.c_int32), ("stop", C.c_int32), ("last_amount", C.c_float), ("reserved", C.c_int32)]
 
 
+CLANE_EUNSUPPORTED = -9
+
+
 class ClaneError(RuntimeError):
     pass
 
@@ -55,6 +58,8 @@ SIGNATURES = {
     "clane_cosine_finalize": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
     "clane_build_p_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
+    "clane_sweeps": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, c_vp, c_vp, c_vp, C.c_float, C.c_int32, C.c_int32, c_vp, c_vp,
+                               C.c_int32, c_vp]),
     "clane_l1_diff": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_l1_partial": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
     "clane_l1_finish": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
@@ -62,6 +67,7 @@ SIGNATURES = {
     "clane_l1_finish_values": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
     "clane_plan_set_peers": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_vp]),
     "clane_plan_set_multicast": (C.c_int, [c_vp, C.c_uint64, C.c_uint64]),
+    "clane_plan_trace": (C.c_int, [c_vp, C.c_int, c_vp]),
     "clane_plan_profile": (C.c_int, [c_vp, C.c_int]),
     "clane_plan_profile_read": (C.c_int, [c_vp, c_f32p]),
     "clane_patience_reset": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp]),

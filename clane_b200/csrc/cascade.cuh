@@ -287,9 +287,9 @@ inline int cascade_launch_l01(const Elem& elem, int64_t n, int64_t node_lo, int6
 template <class Elem>
 inline int cascade_launch_finish(const Elem& elem, int64_t n, const float* p1, float* p2, float* out,
                                  clane_patience* st, float* log, int log_cap, unsigned* reset_counter,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, int threads = 1024) {
     CascadeShape sh = cascade_shape(n);
-    k_cascade_finish<Elem><<<1, 1024, 0, s>>>(elem, sh, p1, p2, out, st, log, log_cap, reset_counter);
+    k_cascade_finish<Elem><<<1, threads, 0, s>>>(elem, sh, p1, p2, out, st, log, log_cap, reset_counter);
     CLANE_LAUNCH_CHECK();
     return CLANE_OK;
 }

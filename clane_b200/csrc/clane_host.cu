@@ -240,15 +240,13 @@ int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
     cudaFree(plan->d_tasks); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubT);
-    cudaFree(plan->d_hub_cnt); cudaFree(plan->d_hub_done);
-    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
-    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
-    if (plan->ev_join2) cudaEventDestroy(plan->ev_join2);
+    for (cudaEvent_t ev : plan->evs) cudaEventDestroy(ev);
     if (plan->side) cudaStreamDestroy(plan->side);
     if (plan->side2) cudaStreamDestroy(plan->side2);
-    cudaFree(plan->d_P0); cudaFree(plan->d_coloff);
+    if (plan->tail) cudaStreamDestroy(plan->tail);
+    cudaFree(plan->d_P0); cudaFree(plan->d_coloff); cudaFree(plan->d_trace);
     for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    for (int i = 0; i < 6; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
+    for (int i = 0; i < 8; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
     cudaFree(plan->d_p1); cudaFree(plan->d_p2);
     delete plan;
     return CLANE_OK;
@@ -387,10 +385,8 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     rc = build_program(h_rowptr, plan->fuse, srow.data(), smeta.data(), n_spans, hrows.data(), n_hrows, tasks, blk0,
                        &plan->hub_blocks);
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
-    // the segments (8 neighbours per block, ~5 G neighbours/s while they are the only tasks running) come first in the
-    // row kernel; a chain CTA that has waited twice that long gives up and leaves its row to the late pass
-    plan->chain_spin_ns = std::min<unsigned long long>(5000000ull, 300000ull + (unsigned long long)(plan->hub_blocks * 8 * 0.4));
     plan->n_tasks = (int32_t)tasks.size();
+    plan->n_seg_tasks = plan->n_tasks - n_spans;
     PLAN_CUDA(cudaMalloc(&plan->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(SweepTask)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));
@@ -408,23 +404,18 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
         const size_t nb = (size_t)plan->hub_blocks;
         PLAN_CUDA(cudaMalloc(&plan->d_hubS, std::max<size_t>(nb * plan->nslab32b * 32, 1) * 16));
         if (plan->ntail4 > 0) PLAN_CUDA(cudaMalloc(&plan->d_hubT, nb * 8 * plan->ntail4 * 16));
-        const size_t chain_ctas = (size_t)n_hrows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
-        PLAN_CUDA(cudaMalloc(&plan->d_hub_cnt, n_hrows * sizeof(int32_t)));
-        PLAN_CUDA(cudaMalloc(&plan->d_hub_done, chain_ctas * sizeof(int32_t)));
-        PLAN_CUDA(cudaMemset(plan->d_hub_cnt, 0, n_hrows * sizeof(int32_t)));
-        PLAN_CUDA(cudaMemset(plan->d_hub_done, 0, chain_ctas * sizeof(int32_t)));
-        {   // the early chain pass runs beside the row kernel on its own stream, dispatched ahead of it
-            int lo = 0, hi = 0;
-            PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
-            PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side2, cudaStreamNonBlocking, hi));
-            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
-            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
-            PLAN_CUDA(cudaEventCreateWithFlags(&plan->ev_join2, cudaEventDisableTiming));
-        }
+    }
+    {   // the segments + chains run beside the span tasks on their own streams, dispatched ahead of them
+        int lo = 0, hi = 0;
+        PLAN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        plan->prio_hi = hi; plan->prio_lo = lo;
+        PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side, cudaStreamNonBlocking, hi));
+        PLAN_CUDA(cudaStreamCreateWithPriority(&plan->side2, cudaStreamNonBlocking, hi));
+        PLAN_CUDA(cudaStreamCreateWithPriority(&plan->tail, cudaStreamNonBlocking, hi));
     }
     if (plan->fuse) {
-        const size_t p0 = (size_t)(plan->n_groups + 1) * 32 * sizeof(float);
+        plan->p0_stride = (size_t)(plan->n_groups + 1) * 32;
+        const size_t p0 = 2 * plan->p0_stride * sizeof(float);
         PLAN_CUDA(cudaMalloc(&plan->d_P0, p0));
         PLAN_CUDA(cudaMemset(plan->d_P0, 0, p0));   // dropped (all-sink) groups contribute +0 forever
     }
@@ -440,11 +431,13 @@ int clane_plan_info(const clane_plan* plan, int32_t* group_rows, int32_t* n_span
     if (n_hub_rows) *n_hub_rows = plan->n_hub_rows;
     if (n_fix_groups) *n_fix_groups = plan->n_fix_groups;
     if (fused_l1) *fused_l1 = plan->fuse;
-    // row sweep, [early chain: long rows], [early chain: short rows], [late chain], [chunk fix-up], level-1, finish
+    // spans, [hub segments, chains of long rows, chains of short rows], then the exact L1: fused = [chunk fix-up],
+    // level 1, finish; otherwise level 0 + 1, finish
     if (launches_per_sweep) {
         const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
-        *launches_per_sweep = 3 + (n_long > 0 ? 1 : 0) + (n_short > 0 ? 1 : 0) + (plan->n_hub_rows > 0 ? 1 : 0) +
-                              ((plan->fuse && plan->n_fix_groups > 0) ? 1 : 0);
+        const int hub = plan->n_hub_rows > 0 ? 1 + (n_long > 0 ? 1 : 0) + (n_short > 0 ? 1 : 0) : 0;
+        const int l1 = plan->fuse ? 2 + (plan->n_fix_groups > 0 ? 1 : 0) : 2;
+        *launches_per_sweep = 1 + hub + l1;
     }
     return CLANE_OK;
 }
@@ -457,10 +450,10 @@ struct clane_session {
     int64_t e = 0;
     clane_plan* plan = nullptr;
     int32_t *rowptr = nullptr, *col = nullptr, *erow = nullptr;
-    float *X = nullptr, *Z[2] = {nullptr, nullptr}, *prev = nullptr, *w = nullptr, *norms2 = nullptr;
+    float *X = nullptr, *Z[3] = {nullptr, nullptr, nullptr}, *prev = nullptr, *w = nullptr, *norms2 = nullptr;
     float *amount = nullptr, *log = nullptr;
     clane_patience* state = nullptr;
-    int cur = 0;  // Z[cur] holds the current embeddings
+    int cur = 0;  // Z[cur] holds the current embeddings (three rotating buffers: clane_sweeps)
     int32_t log_cap = 0;
     cudaStream_t stream = nullptr;
     clane_patience* h_state = nullptr;  // pinned
@@ -489,7 +482,7 @@ int clane_session_destroy(clane_session* s) {
     if (!s) return CLANE_OK;
     clane_plan_destroy(s->plan);
     cudaFree(s->rowptr); cudaFree(s->col); cudaFree(s->erow);
-    cudaFree(s->X); cudaFree(s->Z[0]); cudaFree(s->Z[1]); cudaFree(s->prev); cudaFree(s->w); cudaFree(s->norms2);
+    cudaFree(s->X); cudaFree(s->Z[0]); cudaFree(s->Z[1]); cudaFree(s->Z[2]); cudaFree(s->prev); cudaFree(s->w); cudaFree(s->norms2);
     cudaFree(s->amount); cudaFree(s->log); cudaFree(s->state);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -521,6 +514,7 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
     SESSION_CUDA(cudaMalloc(&s->X, zbytes));
     SESSION_CUDA(cudaMalloc(&s->Z[0], zbytes));
     SESSION_CUDA(cudaMalloc(&s->Z[1], zbytes));
+    SESSION_CUDA(cudaMalloc(&s->Z[2], zbytes));
     SESSION_CUDA(cudaMalloc(&s->prev, zbytes));
     SESSION_CUDA(cudaMalloc(&s->w, ebytes));
     SESSION_CUDA(cudaMalloc(&s->norms2, 2 * sizeof(float)));
@@ -536,6 +530,7 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
         SESSION_TRY(copy_rows_h2d(s, s->X, h_X));
         SESSION_CUDA(cudaMemcpyAsync(s->Z[0], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
         SESSION_CUDA(cudaMemcpyAsync(s->Z[1], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
+        SESSION_CUDA(cudaMemcpyAsync(s->Z[2], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
     }
     SESSION_TRY(clane_edge_rows(s->rowptr, n, e, s->erow, s->stream));
     SESSION_CUDA(cudaStreamSynchronize(s->stream));  // the host vectors above go out of scope
@@ -548,6 +543,7 @@ int clane_session_set_z(clane_session* s, const float* h_Z) {
     int rc = copy_rows_h2d(s, s->Z[0], h_Z);
     if (rc != CLANE_OK) return rc;
     CLANE_CUDA(cudaMemcpyAsync(s->Z[1], s->Z[0], (size_t)s->n * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    CLANE_CUDA(cudaMemcpyAsync(s->Z[2], s->Z[0], (size_t)s->n * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
     s->cur = 0;
     s->p_valid = false;
     CLANE_CUDA(cudaStreamSynchronize(s->stream));
@@ -580,9 +576,10 @@ int clane_session_build_p(clane_session* s, float* h_w) {
 }
 
 static int session_sweep(clane_session* s, float gamma, bool with_state, float* d_amount) {
-    int rc = clane_sweep(s->plan, s->X, s->Z[s->cur], s->Z[s->cur ^ 1], s->rowptr, s->col, s->w, gamma, d_amount,
+    const int nxt = (s->cur + 1) % 3;
+    int rc = clane_sweep(s->plan, s->X, s->Z[s->cur], s->Z[nxt], s->rowptr, s->col, s->w, gamma, d_amount,
                          with_state ? s->state : nullptr, with_state ? s->log : nullptr, s->log_cap, s->stream);
-    s->cur ^= 1;
+    s->cur = nxt;
     return rc;
 }
 
@@ -594,26 +591,30 @@ int clane_session_propagate(clane_session* s, float gamma, int32_t tol, int32_t 
     rc = clane_patience_reset(s->state, tol, max_sweeps, s->stream);
     if (rc != CLANE_OK) return rc;
     const int start = s->cur;
-    int enq = 0;  // sweeps enqueued so far (the ones after the stop are device-side no-ops)
-    const int batch = std::max(1, std::min(tol, 8));
+    // one graph launch for the whole call (conditional WHILE over batches of sweeps); without conditional nodes:
+    // batches of 6 sweeps (two full buffer rotations), one host synchronisation per batch
+    rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 0, 1, s->state, s->log, s->log_cap, s->stream);
+    if (rc != CLANE_OK && rc != CLANE_EUNSUPPORTED) return rc;
+    const bool looped = rc == CLANE_OK;
     for (;;) {
-        for (int i = 0; i < batch; ++i, ++enq) {
-            rc = session_sweep(s, gamma, true, nullptr);
+        if (!looped) {
+            rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 6, 0, s->state, s->log, s->log_cap,
+                              s->stream);
             if (rc != CLANE_OK) return rc;
         }
         CLANE_CUDA(cudaMemcpyAsync(s->h_state, s->state, sizeof(clane_patience), cudaMemcpyDeviceToHost, s->stream));
         CLANE_CUDA(cudaStreamSynchronize(s->stream));
         if (s->h_state->stop) break;
+        if (looped) return CLANE_EINVAL;   // the loop ended without the stop flag: cannot happen
     }
     const int done = s->h_state->sweeps;
-    s->cur = (start + done) & 1;  // sweep i read Z[(start+i)&1] and wrote the other buffer
+    s->cur = (start + done) % 3;  // sweep i read Z[(start + i) % 3] and wrote the next buffer
     if (sweeps) *sweeps = done;
     if (h_amounts && cap > 0) {
         const int cnt = std::min(std::min(done, cap), s->log_cap);
         CLANE_CUDA(cudaMemcpyAsync(h_amounts, s->log, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
         CLANE_CUDA(cudaStreamSynchronize(s->stream));
     }
-    (void)enq;
     return CLANE_OK;
 }
 

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <algorithm>
 
 #include "cascade.cuh"
 #include "common.cuh"
@@ -190,7 +192,29 @@ __global__ void k_patience_reset(clane_patience* st, int tol, int max_sweeps) {
 
 }  // namespace clane
 
+namespace {
+
+// kernel launch with an explicit priority: the attribute stays on the kernel node when the launch is captured into a
+// graph (a captured node does not reliably inherit the priority of the stream it was captured from)
+template <class... KArgs, class... Args>
+cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+}  // namespace
+
 using namespace clane;
+
+constexpr int kSweepBatch = 6;     // sweeps per replayed graph of clane_sweeps (a multiple of the three Z buffers)
+// The L1 tail of sweep t runs while the span tasks of sweep t + 1 fill every SM (12 CTAs x 64 threads x 80 registers leave
+// 4096 registers per SM): 64-thread CTAs of <= 64 registers are what still fits beside them.
+constexpr int kTailThreads = 64;
 
 // =============================================================================================
 // C-ABI
@@ -210,6 +234,7 @@ const char* clane_error_string(int code) {
         case CLANE_EPARSE: return "clane: malformed edge line";
         case CLANE_EUNKNOWNID: return "clane: edge endpoint not in V";
         case CLANE_ENOMEM: return "clane: out of host memory";
+        case CLANE_EUNSUPPORTED: return "clane: not supported by this driver";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "clane: unknown error";
     }
 }
@@ -293,106 +318,288 @@ static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t st) {
     return cudaEventRecordWithFlags(ev, st, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
-static int sweep_enqueue(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext,
-                         const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma, float* d_amount,
-                         clane_patience* d_state, float* d_amounts_log, int32_t log_cap, cudaStream_t st) {
-    const bool want_l1 = d_amount != nullptr || d_state != nullptr;
-    SweepParams p;
-    p.X = d_X; p.Zc = d_Zcur; p.Zn = d_Znext;
-    p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
-    p.rowptr = d_rowptr; p.coloff = plan->d_coloff; p.w = d_w; p.gamma = gamma;
-    p.tasks = static_cast<const SweepTask*>(plan->d_tasks); p.n_tasks = plan->n_tasks;
-    p.row_lo = plan->row_lo;
-    p.G = plan->G; p.nslab = plan->nslab;
-    p.fuse = (plan->fuse && want_l1) ? 1 : 0;
-    p.P0 = plan->d_P0;
-    p.hub_info = static_cast<const int4*>(plan->d_hub_info); p.n_hub_rows = plan->n_hub_rows;
-    p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
-    p.hubS = static_cast<float4*>(plan->d_hubS);
-    p.hubT = static_cast<float4*>(plan->d_hubT);
-    p.hub_cnt = plan->d_hub_cnt; p.hub_done = plan->d_hub_done;
-    p.chain_spin_ns = plan->chain_spin_ns;
-    p.st = d_state;
-    p.n_remote = 0;
-    static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only
-    p.mc = nullptr;
-    for (int t = 0; t < 2 && plan->n_peers > 1 && !no_peer_stores; ++t)
-        if (plan->peers[t][plan->self_rank] == d_Znext) {
-            if (plan->mc[t] != nullptr) { p.mc = plan->mc[t]; continue; }   // one multicast store instead of n - 1 unicast ones
-            for (int r = 0; r < plan->n_peers; ++r)
-                if (r != plan->self_rank) p.peer[p.n_remote++] = plan->peers[t][r];
+namespace {
+
+struct SweepArgs {
+    const float* X;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* w;
+    float gamma;
+    float* amount;
+    clane_patience* state;
+    float* log;
+    int32_t log_cap;
+};
+
+// tell a conditional-WHILE graph whether to run its body (a batch of sweeps) once more
+__global__ void k_loop_condition(cudaGraphConditionalHandle handle, const clane_patience* st) {
+    cudaGraphSetConditional(handle, st->stop ? 0u : 1u);
+}
+
+}  // namespace
+
+// Enqueue `n_sweeps` consecutive sweeps.  Sweep t reads Z[(c0 + t) % nz] and writes Z[(c0 + t + 1) % nz].
+//
+// Streams of one sweep (all plan-owned except the caller's `st`; ordinary event dependencies, no flags):
+//   st    : span tasks (k_sweep_rows over the span part of the task list)
+//   side  : hub segment tasks (k_sweep_rows over the segment part), then the chains of the long hub rows
+//   side2 : the chains of the short hub rows (after the segments)
+//   tail  : the exact L1 change -- chunk fix-up, level 1, finish + patience
+// Between sweeps (nz == 3, three rotating Z buffers): the spans / segments of sweep t + 1 only need the rows and
+// chains of sweep t, so the whole L1 tail of sweep t runs beside sweep t + 1.  The patience flag a sweep sees is
+// therefore one sweep old: at most one speculative sweep runs after the stop, into a buffer that is not the result
+// (the result of the stopping sweep t is Z[(c0 + t + 1) % 3]; sweep t + 1 writes Z[(c0 + t + 2) % 3]; its tail is a
+// no-op, so the state, the log and the sweep count are exactly the reference's).  With nz == 2 every sweep waits for
+// the previous tail (its fix-up reads the buffer the next sweep overwrites).
+static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z, int nz, int c0, int n_sweeps, cudaStream_t st) {
+    const bool want_l1 = a.amount != nullptr || a.state != nullptr;
+    size_t ne = 0;
+    auto next_event = [&](cudaEvent_t* out) -> cudaError_t {
+        if (ne == plan->evs.size()) {
+            cudaEvent_t ev = nullptr;
+            cudaError_t rc = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (rc != cudaSuccess) return rc;
+            plan->evs.push_back(ev);
         }
-    // Hub rows: their segments are the first tasks of the row kernel; the chains follow on the same stream.
-    const int64_t chain_ctas = (int64_t)p.n_hub_rows * (plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0));
-    const int64_t row_ctas = ((int64_t)p.n_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
-    const bool prof = plan->profile;
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[0], st));
-    // The early chain passes only help if the device runs them beside the row kernel; with a single hardware work
-    // queue (CUDA_DEVICE_MAX_CONNECTIONS=1) kernels of different streams run in submission order and the early pass
-    // would just spin into its time-out before every row kernel.
-    static const bool overlap = [] {
-        if (getenv("CLANE_NO_CHAIN_OVERLAP") != nullptr) return false;
-        const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
-        return !(q != nullptr && atoi(q) == 1);
-    }();
+        *out = plan->evs[ne++];
+        return cudaSuccess;
+    };
+    auto mark = [&](cudaEvent_t* ev, cudaStream_t s) -> cudaError_t {       // *ev = a fresh event recorded on s
+        cudaError_t rc = next_event(ev);
+        return rc != cudaSuccess ? rc : cudaEventRecord(*ev, s);
+    };
+    static const bool no_peer_stores = getenv("CLANE_DEBUG_NO_PEER_STORES") != nullptr;   // timing experiments only
     const int per_row = plan->nslab32b + (plan->ntail4 > 0 ? 1 : 0);
     const int n_long = plan->n_long_hub_rows, n_short = plan->n_hub_rows - n_long;
-    if (chain_ctas > 0 && overlap) {   // early chain passes: beside the row kernel, waiting on its segment warps
-        CLANE_CUDA(cudaEventRecord(plan->ev_fork, st));
-        CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
-        if (n_long > 0) {
-            p.hub_first = 0;
-            k_hub_chain<true, false><<<(unsigned)(n_long * per_row), kChainThreads, kChainSmemBytes, plan->side>>>(p);
-            CLANE_LAUNCH_CHECK();
-        }
-        CLANE_CUDA(cudaEventRecord(plan->ev_join, plan->side));
-        if (n_short > 0) {             // its own stream: not behind the long rows' chains
-            CLANE_CUDA(cudaStreamWaitEvent(plan->side2, plan->ev_fork, 0));
-            p.hub_first = n_long;
-            k_hub_chain<true, true><<<(unsigned)(n_short * per_row), kChainThreads, chain_smem_bytes(kLightStages), plan->side2>>>(p);
-            CLANE_LAUNCH_CHECK();
-            CLANE_CUDA(cudaEventRecord(plan->ev_join2, plan->side2));
-        }
-    }
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[1], st));
-    if (row_ctas > 0) {
-        k_sweep_rows<<<(unsigned)row_ctas, kRowThreads, 0, st>>>(p);
-        CLANE_LAUNCH_CHECK();
-    }
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[2], st));
-    if (chain_ctas > 0 && overlap) {
-        CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
-        if (n_short > 0) CLANE_CUDA(cudaStreamWaitEvent(st, plan->ev_join2, 0));
-    }
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[4], st));
-    if (chain_ctas > 0) {              // late pass: whatever the early one left, and the reset of its flags
-        p.hub_first = 0;
-        k_hub_chain<false, true><<<(unsigned)chain_ctas, kChainThreads, chain_smem_bytes(kLightStages), st>>>(p);
-        CLANE_LAUNCH_CHECK();
-    }
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[5], st));
-    struct ProfTail {   // records the end-of-sweep event on every exit path below
-        clane_plan* pl; cudaStream_t s;
-        ~ProfTail() { if (pl->profile) prof_record(pl->ev_prof[3], s); }
-    } prof_tail{plan, st};
-    if (!want_l1) return CLANE_OK;
+    const bool hubs = plan->n_hub_rows > 0 && plan->n_seg_tasks > 0;
+    const int64_t seg_ctas = ((int64_t)plan->n_seg_tasks * plan->nslab + kRowWarps - 1) / kRowWarps;
+    const int64_t span_ctas = ((int64_t)(plan->n_tasks - plan->n_seg_tasks) * plan->nslab + kRowWarps - 1) / kRowWarps;
     const int64_t n_elems = (int64_t)plan->n * plan->d;
-    ElemAbsDiff el{d_Znext, d_Zcur, plan->d, plan->ld};
-    if (p.fuse) {
-        CascadeShape sh = cascade_shape(n_elems);
-        if (plan->n_fix_groups > 0) {
-            k_fix_chunks<<<(unsigned)(((int64_t)plan->n_fix_groups * 32 + 255) / 256), 256, 0, st>>>(
-                d_Znext, d_Zcur, plan->d, plan->n, plan->G, plan->d_fix_groups, plan->n_fix_groups, plan->d_P0, d_state);
-            CLANE_LAUNCH_CHECK();
+    const bool prof = plan->profile && n_sweeps == 1;
+    cudaEvent_t e_begin = nullptr;
+    CLANE_CUDA(mark(&e_begin, st));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[0], st));
+    std::vector<cudaEvent_t> eR((size_t)n_sweeps, nullptr), eC(eR), eC2(eR), eF(eR), eL(eR);
+    for (int t = 0; t < n_sweeps; ++t) {
+        const float* Zc = Z[(c0 + t) % nz];
+        float* Zn = Z[(c0 + t + 1) % nz];
+        SweepParams p;
+        p.X = a.X; p.Zc = Zc; p.Zn = Zn;
+        p.ld = plan->ld; p.d = plan->d; p.n = plan->n;
+        p.rowptr = a.rowptr; p.coloff = plan->d_coloff; p.w = a.w; p.gamma = a.gamma;
+        p.tasks = static_cast<const SweepTask*>(plan->d_tasks); p.n_tasks = plan->n_tasks; p.task_lo = 0;
+        p.row_lo = plan->row_lo;
+        p.G = plan->G; p.nslab = plan->nslab;
+        p.fuse = (plan->fuse && want_l1) ? 1 : 0;
+        p.P0 = plan->d_P0 + (size_t)(t & 1) * plan->p0_stride;
+        p.hub_info = static_cast<const int4*>(plan->d_hub_info); p.n_hub_rows = plan->n_hub_rows;
+        p.limit = plan->limit; p.ntail4 = plan->ntail4; p.nslab32b = plan->nslab32b; p.sld = plan->nslab32b * 32;
+        p.hubS = static_cast<float4*>(plan->d_hubS);
+        p.hubT = static_cast<float4*>(plan->d_hubT);
+        p.hub_first = 0;
+        p.st = a.state;
+        p.n_remote = 0;
+        p.mc = nullptr;
+        p.trace = nullptr;
+        unsigned long long* tr = (plan->d_trace != nullptr && t < kTraceSweeps) ? plan->d_trace + (size_t)t * kTraceSlots * 2 : nullptr;
+        for (int q = 0; q < 2 && plan->n_peers > 1 && !no_peer_stores; ++q)
+            if (plan->peers[q][plan->self_rank] == Zn) {
+                if (plan->mc[q] != nullptr) { p.mc = plan->mc[q]; continue; }   // one multicast store instead of n - 1 unicast ones
+                for (int r = 0; r < plan->n_peers; ++r)
+                    if (r != plan->self_rank) p.peer[p.n_remote++] = plan->peers[q][r];
+            }
+        // what the previous sweeps must have finished before this one may start
+        cudaEvent_t prev_tail = nullptr;       // the tail whose inputs this sweep overwrites / whose flag it reads
+        if (nz >= 3) { if (t >= 2) prev_tail = eL[t - 2]; }
+        else if (t >= 1) prev_tail = eL[t - 1];
+        // ---- side: hub segments, then the chains ----
+        cudaEvent_t eS_cur = nullptr;
+        if (hubs) {
+            CLANE_CUDA(cudaStreamWaitEvent(plan->side, t == 0 ? e_begin : eR[t - 1], 0));
+            if (t > 0 && eC2[t - 1]) CLANE_CUDA(cudaStreamWaitEvent(plan->side, eC2[t - 1], 0));
+            if (prev_tail) CLANE_CUDA(cudaStreamWaitEvent(plan->side, prev_tail, 0));
+            SweepParams ps = p;
+            ps.n_tasks = plan->n_seg_tasks;
+            ps.trace = tr;
+            CLANE_CUDA(launch_prio(k_sweep_rows, dim3((unsigned)seg_ctas), dim3(kRowThreads), 0, plan->side, plan->prio_hi, ps));
+            cudaEvent_t eS = nullptr;
+            CLANE_CUDA(mark(&eS, plan->side));
+            eS_cur = eS;
+            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[4], plan->side));
+            if (n_long > 0) {
+                p.trace = tr ? tr + 2 : nullptr;
+                CLANE_CUDA(launch_prio(k_hub_chain<false>, dim3((unsigned)(n_long * per_row)), dim3(kChainThreads), kHeavySmemBytes,
+                                       plan->side, plan->prio_hi, p));
+            }
+            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[5], plan->side));
+            CLANE_CUDA(mark(&eC[t], plan->side));
+            if (n_short > 0) {             // its own stream: not behind the long rows' chains
+                CLANE_CUDA(cudaStreamWaitEvent(plan->side2, eS, 0));
+                SweepParams pc = p;
+                pc.hub_first = n_long;
+                pc.trace = tr ? tr + 4 : nullptr;
+                CLANE_CUDA(launch_prio(k_hub_chain<true>, dim3((unsigned)(n_short * per_row)), dim3(kChainThreads), kLightSmemBytes,
+                                       plan->side2, plan->prio_hi, pc));
+                CLANE_CUDA(mark(&eC2[t], plan->side2));
+            }
         }
-        if (sh.n1_nodes > 0) {
-            k_level1_from_p0<<<(unsigned)((sh.n1_nodes * 32 + 255) / 256), 256, 0, st>>>(sh, plan->d_P0, plan->d_p1, d_state);
-            CLANE_LAUNCH_CHECK();
+        // ---- caller's stream: the span tasks ----
+        if (t > 0) {
+            if (eC[t - 1]) CLANE_CUDA(cudaStreamWaitEvent(st, eC[t - 1], 0));
+            if (eC2[t - 1]) CLANE_CUDA(cudaStreamWaitEvent(st, eC2[t - 1], 0));
         }
-        return cascade_launch_finish(el, n_elems, plan->d_p1, plan->d_p2, d_amount, d_state, d_amounts_log, log_cap,
-                                     nullptr, st);
+        if (prev_tail) CLANE_CUDA(cudaStreamWaitEvent(st, prev_tail, 0));
+        // (The segments and the light chains fit beside the span CTAs -- see sweep.cuh -- so the spans do not wait for
+        // them.  CLANE_DEBUG_SEG_WAIT=1 starts the spans behind the segments: a timing experiment.)
+        static const bool seg_wait = getenv("CLANE_DEBUG_SEG_WAIT") != nullptr;
+        if (eS_cur && seg_wait) CLANE_CUDA(cudaStreamWaitEvent(st, eS_cur, 0));
+        if (prof) CLANE_CUDA(prof_record(plan->ev_prof[1], st));
+        if (span_ctas > 0) {
+            SweepParams pr = p;
+            pr.task_lo = plan->n_seg_tasks;
+            pr.trace = tr ? tr + 6 : nullptr;
+            CLANE_CUDA(launch_prio(k_sweep_rows, dim3((unsigned)span_ctas), dim3(kRowThreads), 0, st, plan->prio_lo, pr));
+        }
+        if (prof) CLANE_CUDA(prof_record(plan->ev_prof[2], st));
+        CLANE_CUDA(mark(&eR[t], st));
+        // ---- tail: the exact L1 change of this sweep ----
+        if (want_l1) {
+            cudaStream_t tl = plan->tail;
+            CLANE_CUDA(cudaStreamWaitEvent(tl, eR[t], 0));
+            if (eC[t]) CLANE_CUDA(cudaStreamWaitEvent(tl, eC[t], 0));
+            if (eC2[t]) CLANE_CUDA(cudaStreamWaitEvent(tl, eC2[t], 0));
+            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[6], tl));
+            if (tr) k_trace_stamp<<<1, 1, 0, tl>>>(tr + 8, 0);
+            ElemAbsDiff el{Zn, Zc, plan->d, plan->ld};
+            int rc;
+            if (p.fuse) {
+                CascadeShape sh = cascade_shape(n_elems);
+                if (plan->n_fix_groups > 0) {
+                    CLANE_CUDA(launch_prio(k_fix_chunks, dim3((unsigned)(((int64_t)plan->n_fix_groups * 32 + kTailThreads - 1) / kTailThreads)),
+                                           dim3(kTailThreads), 0, tl, plan->prio_hi, (const float*)Zn, Zc, plan->d, plan->n, plan->G,
+                                           (const int32_t*)plan->d_fix_groups, plan->n_fix_groups, p.P0, (const clane_patience*)a.state));
+                }
+                CLANE_CUDA(mark(&eF[t], tl));
+                if (sh.n1_nodes > 0) {
+                    CLANE_CUDA(launch_prio(k_level1_from_p0, dim3((unsigned)((sh.n1_nodes * 32 + kTailThreads - 1) / kTailThreads)),
+                                           dim3(kTailThreads), 0, tl, plan->prio_hi, sh, (const float*)p.P0, plan->d_p1,
+                                           (const clane_patience*)a.state));
+                }
+                if (tr) k_trace_stamp<<<1, 1, 0, tl>>>(tr + 10, 0);
+                rc = cascade_launch_finish(el, n_elems, plan->d_p1, plan->d_p2, a.amount, a.state, a.log, a.log_cap, nullptr, tl,
+                                           n_sweeps > 1 ? kTailThreads : 1024);
+                if (tr) k_trace_stamp<<<1, 1, 0, tl>>>(tr + 10, 1);
+            } else {
+                rc = cascade_launch_l01(el, n_elems, 0, cascade_shape(n_elems).n1_nodes, plan->d_p1, a.state, tl);
+                CLANE_CUDA(mark(&eF[t], tl));      // Zn / Zc are not read after this point (the finish reads <= 31 tail elements:
+                if (rc == CLANE_OK)               // they belong to the last rows, which the waits below still protect -- see eL)
+                    rc = cascade_launch_finish(el, n_elems, plan->d_p1, plan->d_p2, a.amount, a.state, a.log, a.log_cap, nullptr, tl);
+            }
+            if (rc != CLANE_OK) return rc;
+            if (tr) k_trace_stamp<<<1, 1, 0, tl>>>(tr + 8, 1);
+            CLANE_CUDA(mark(&eL[t], tl));
+        }
     }
-    return cascade_launch(el, n_elems, plan->d_p1, plan->d_p2, d_amount, d_state, d_amounts_log, log_cap, st);
+    // join everything back into the caller's stream
+    const int last = n_sweeps - 1;
+    if (eC[last]) CLANE_CUDA(cudaStreamWaitEvent(st, eC[last], 0));
+    if (eC2[last]) CLANE_CUDA(cudaStreamWaitEvent(st, eC2[last], 0));
+    for (int t = std::max(0, n_sweeps - 2); t < n_sweeps; ++t)
+        if (eL[t]) CLANE_CUDA(cudaStreamWaitEvent(st, eL[t], 0));
+    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[3], st));
+    return CLANE_OK;
+}
+
+// enqueue through the CUDA-graph cache: capture once per argument set, replay afterwards.  loop != 0: the batch is the
+// body of a conditional WHILE node that repeats it until the patience state machine stops (one launch = one propagate()).
+static int launch_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z, int nz, int c0, int n_sweeps, int loop,
+                         cudaStream_t st) {
+    static const bool env_graphs = getenv("CLANE_NO_GRAPHS") == nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (!plan->use_graphs || !env_graphs || cap != cudaStreamCaptureStatusNone || st == nullptr) {
+        if (loop) return CLANE_EINVAL;   // the caller falls back to host-driven batches
+        return enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
+    }
+    const void* key[12] = {a.X, Z[0], Z[1], nz > 2 ? Z[2] : nullptr, a.rowptr, a.col, a.w, a.amount, a.state, a.log, st, nullptr};
+    clane_plan::SweepGraph* slot = nullptr;
+    for (auto& g : plan->graphs)
+        if (g.exec && g.gamma == a.gamma && g.log_cap == a.log_cap && g.n_sweeps == n_sweeps && g.nz == nz && g.c0 == c0 &&
+            g.loop == loop && memcmp(g.key, key, sizeof(key)) == 0)
+            slot = &g;
+    if (!slot) {
+        slot = &plan->graphs[0];
+        for (auto& g : plan->graphs)
+            if (g.last_use < slot->last_use) slot = &g;
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        int rc = CLANE_OK;
+        cudaError_t ce = cudaSuccess;
+        if (!loop) {
+            CLANE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
+            ce = cudaStreamEndCapture(st, &graph);
+        } else {
+            // graph = one conditional WHILE node; its body graph is filled by capturing the batch + the condition kernel
+            cudaGraphConditionalHandle handle;
+            cudaGraphNode_t node = nullptr;
+            ce = cudaGraphCreate(&graph, 0);
+            if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            if (ce == cudaSuccess) ce = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+            if (ce == cudaSuccess) {
+                cudaGraph_t body = np.conditional.phGraph_out[0];
+                ce = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+                if (ce == cudaSuccess) {
+                    rc = enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
+                    if (rc == CLANE_OK) {
+                        k_loop_condition<<<1, 1, 0, st>>>(handle, a.state);
+                        if (cudaGetLastError() != cudaSuccess) rc = CLANE_EINVAL;
+                    }
+                    cudaGraph_t same = nullptr;
+                    ce = cudaStreamEndCapture(st, &same);
+                }
+            }
+        }
+        if (rc != CLANE_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (loop) { plan->while_ok = false; return CLANE_EINVAL; }
+            if (rc != CLANE_OK) return rc;
+            plan->use_graphs = false;   // capture unsupported here: direct launches from now on
+            return enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
+        }
+        // per-node priorities (launch_prio): without this flag every node runs at the priority of the launching stream and
+        // the hub / tail kernels queue up behind the span tasks instead of running beside them
+        ce = cudaGraphInstantiateWithFlags(&slot->exec, graph, cudaGraphInstantiateFlagUseNodePriority);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            slot->exec = nullptr;
+            cudaGetLastError();
+            if (loop) { plan->while_ok = false; return CLANE_EINVAL; }
+            return (int)ce;
+        }
+        memcpy(slot->key, key, sizeof(key));
+        slot->gamma = a.gamma; slot->log_cap = a.log_cap; slot->n_sweeps = n_sweeps; slot->nz = nz; slot->c0 = c0;
+        slot->loop = loop;
+    }
+    slot->last_use = ++plan->graph_clock;
+    CLANE_CUDA(cudaGraphLaunch(slot->exec, st));
+    return CLANE_OK;
+}
+
+static int ensure_coloff(clane_plan* plan, const int32_t* d_col, cudaStream_t st) {
+    if (plan->e > 0 && plan->coloff_src != d_col) {   // first sweep with this column array
+        k_col_offsets<<<(unsigned)((plan->e + 255) / 256), 256, 0, st>>>(d_col, plan->e, plan->ld, plan->d_coloff);
+        CLANE_LAUNCH_CHECK();
+        plan->coloff_src = d_col;
+    }
+    return CLANE_OK;
 }
 
 int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* d_Znext, const int32_t* d_rowptr,
@@ -401,49 +608,39 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
     if (!plan || !plan->has_schedule || !d_X || !d_Zcur || !d_Znext || !d_rowptr) return CLANE_EINVAL;
     if (plan->e > 0 && (!d_col || !d_w)) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
-    if (plan->e > 0 && plan->coloff_src != d_col) {   // first sweep with this column array
-        k_col_offsets<<<(unsigned)((plan->e + 255) / 256), 256, 0, st>>>(d_col, plan->e, plan->ld, plan->d_coloff);
-        CLANE_LAUNCH_CHECK();
-        plan->coloff_src = d_col;
+    int rc = ensure_coloff(plan, d_col, st);
+    if (rc != CLANE_OK) return rc;
+    SweepArgs a{d_X, d_rowptr, d_col, d_w, gamma, d_amount, d_state, d_amounts_log, log_cap};
+    float* Z[2] = {const_cast<float*>(d_Zcur), d_Znext};
+    return launch_sweeps(plan, a, Z, 2, 0, 1, 0, st);
+}
+
+int clane_sweeps(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t cur, const int32_t* d_rowptr,
+                 const int32_t* d_col, const float* d_w, float gamma, int32_t n_sweeps, int32_t until_stop,
+                 clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_X || !d_Z3 || !d_Z3[0] || !d_Z3[1] || !d_Z3[2] || !d_rowptr || !d_state ||
+        cur < 0 || cur > 2 || n_sweeps < 0)
+        return CLANE_EINVAL;
+    if (plan->e > 0 && (!d_col || !d_w)) return CLANE_EINVAL;
+    cudaStream_t st = (cudaStream_t)s;
+    int rc = ensure_coloff(plan, d_col, st);
+    if (rc != CLANE_OK) return rc;
+    SweepArgs a{d_X, d_rowptr, d_col, d_w, gamma, nullptr, d_state, d_amounts_log, log_cap};
+    if (until_stop) {
+        if (!plan->while_ok) return CLANE_EUNSUPPORTED;
+        rc = launch_sweeps(plan, a, d_Z3, 3, cur, kSweepBatch, 1, st);
+        return rc == CLANE_EINVAL ? CLANE_EUNSUPPORTED : rc;
     }
-    static const bool env_graphs = getenv("CLANE_NO_GRAPHS") == nullptr;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    if (!plan->use_graphs || !env_graphs || cap != cudaStreamCaptureStatusNone || st == nullptr)
-        return sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state, d_amounts_log,
-                             log_cap, st);
-    // One sweep = up to five kernels on two streams.  Replay it as a CUDA graph: a propagate() call
-    // alternates between two argument sets (Zcur/Znext swapped), so each is captured once.
-    const void* key[10] = {d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, d_amount, d_state, d_amounts_log, st};
-    clane_plan::SweepGraph* slot = nullptr;
-    for (auto& g : plan->graphs)
-        if (g.exec && g.gamma == gamma && g.log_cap == log_cap && memcmp(g.key, key, sizeof(key)) == 0) slot = &g;
-    if (!slot) {
-        slot = plan->graphs[0].last_use <= plan->graphs[1].last_use ? &plan->graphs[0] : &plan->graphs[1];
-        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-        cudaGraph_t graph = nullptr;
-        CLANE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state,
-                               d_amounts_log, log_cap, st);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc != CLANE_OK || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            if (rc != CLANE_OK) return rc;
-            plan->use_graphs = false;   // capture unsupported here: direct launches from now on
-            return sweep_enqueue(plan, d_X, d_Zcur, d_Znext, d_rowptr, d_col, d_w, gamma, d_amount, d_state,
-                                 d_amounts_log, log_cap, st);
-        }
-        ce = cudaGraphInstantiate(&slot->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { slot->exec = nullptr; return (int)ce; }
-        memcpy(slot->key, key, sizeof(key));
-        slot->gamma = gamma;
-        slot->log_cap = log_cap;
+    // whole batches replay one cached graph per starting buffer (kSweepBatch is a multiple of 3: the rotation closes)
+    static const int batch = [] { const char* v = getenv("CLANE_SWEEP_BATCH"); return v ? std::max(1, atoi(v)) : kSweepBatch; }();
+    int done = 0;
+    while (n_sweeps - done >= batch) {
+        rc = launch_sweeps(plan, a, d_Z3, 3, (cur + done) % 3, batch, 0, st);
+        if (rc != CLANE_OK) return rc;
+        done += batch;
     }
-    slot->last_use = ++plan->graph_clock;
-    CLANE_CUDA(cudaGraphLaunch(slot->exec, st));
-    return CLANE_OK;
+    if (n_sweeps > done) rc = launch_sweeps(plan, a, d_Z3, 3, (cur + done) % 3, n_sweeps - done, 0, st);
+    return rc;
 }
 
 int clane_l1_diff(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_out, clane_stream_t s) {
@@ -509,10 +706,31 @@ int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, f
                                  log_cap, nullptr, (cudaStream_t)s);
 }
 
+int clane_plan_trace(clane_plan* plan, int enable, unsigned long long* h_out) {
+    if (!plan) return CLANE_EINVAL;
+    const size_t words = (size_t)kTraceSweeps * kTraceSlots * 2;
+    if (h_out && plan->d_trace) {      // read back what the last enqueue left
+        CLANE_CUDA(cudaDeviceSynchronize());
+        CLANE_CUDA(cudaMemcpy(h_out, plan->d_trace, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable) {
+        if (!plan->d_trace) CLANE_CUDA(cudaMalloc(&plan->d_trace, words * sizeof(unsigned long long)));
+        std::vector<unsigned long long> init(words);
+        for (size_t i = 0; i < words; ++i) init[i] = (i & 1) ? 0ull : ~0ull;   // {min start, max end}
+        CLANE_CUDA(cudaMemcpy(plan->d_trace, init.data(), words * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    } else if (plan->d_trace) {
+        cudaFree(plan->d_trace);
+        plan->d_trace = nullptr;
+    }
+    for (auto& g : plan->graphs)       // the stamps are arguments of the captured kernels: re-capture
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    return CLANE_OK;
+}
+
 int clane_plan_profile(clane_plan* plan, int enable) {
     if (!plan) return CLANE_EINVAL;
     if (enable && !plan->ev_prof[0])
-        for (int i = 0; i < 6; ++i) CLANE_CUDA(cudaEventCreate(&plan->ev_prof[i]));
+        for (int i = 0; i < 8; ++i) CLANE_CUDA(cudaEventCreate(&plan->ev_prof[i]));
     if (plan->profile != (enable != 0))   // the brackets are event-record nodes of the replayed sweep graphs: re-capture
         for (auto& g : plan->graphs)
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
@@ -525,8 +743,12 @@ int clane_plan_profile_read(clane_plan* plan, float* h_ms) {
     CLANE_CUDA(cudaEventSynchronize(plan->ev_prof[3]));
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[0], plan->ev_prof[1], plan->ev_prof[2]));   // row kernel
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[1], plan->ev_prof[0], plan->ev_prof[3]));   // whole sweep
-    CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[5], plan->ev_prof[3]));   // exact L1 tail
-    CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // hub chain kernel
+    h_ms[2] = h_ms[3] = 0.0f;
+    if (cudaEventQuery(plan->ev_prof[6]) == cudaSuccess)
+        CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[6], plan->ev_prof[3]));   // exact L1 tail
+    if (plan->n_long_hub_rows > 0 && cudaEventQuery(plan->ev_prof[5]) == cudaSuccess)
+        CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // chains of the long hub rows
+    cudaGetLastError();
     return CLANE_OK;
 }
 
@@ -541,7 +763,9 @@ int clane_patience_reset(clane_patience* d_state, int32_t tol, int32_t max_sweep
 int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
-    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeavySmemBytes));
+    if (const char* v = getenv("CLANE_ROW_CARVEOUT"))    // timing experiments: shared-memory carveout (percent) of the row kernel
+        CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

@@ -1,5 +1,7 @@
 // clane_plan: device-side schedule + scratch of one (graph shape, row range).  See clane_b200.h.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 struct clane_plan {
@@ -23,38 +25,44 @@ struct clane_plan {
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
     void* d_hub_info = nullptr;        // int4 per hub row: {row, first edge, degree, first scratch block}
     int64_t hub_blocks = 0;            // 8-neighbour blocks of all hub rows
-    unsigned long long chain_spin_ns = 400000;   // early chain pass time-out: ~2x the expected time of all segment tasks
     int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it
     void* d_hubS = nullptr;            // float4[hub_blocks][ld]  {z6, z4, X, Y}
     void* d_hubT = nullptr;            // float4[hub_blocks * 8][ntail4]  raw z, sequential-regime columns
-    int32_t* d_hub_cnt = nullptr;      // per hub row: segment warps done this sweep
-    int32_t* d_hub_done = nullptr;     // per chain CTA: produced by the early (overlapped) chain pass
-    cudaStream_t side = nullptr, side2 = nullptr;   // the early chain passes (long rows / short rows) run here,
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;   // forked from / joined to the caller's stream
+    int32_t n_seg_tasks = 0;           // the first n_seg_tasks tasks are hub segments (launched on `side`)
+    // plan-owned streams: hub segments + long-row chains | short-row chains | the exact-L1 tail of a sweep.  Forked from
+    // and joined to the caller's stream with events of `evs` (a pool: a multi-sweep enqueue needs a few per sweep)
+    cudaStream_t side = nullptr, side2 = nullptr, tail = nullptr;
+    int prio_hi = 0, prio_lo = 0;      // kernel priorities: hub / tail work beside the span tasks goes first
+    std::vector<cudaEvent_t> evs;
     // row-partitioned run: peer Znext buffers for the two Z ping-pong buffers (entry self = own buffer)
     int32_t n_peers = 0, self_rank = 0;
     float* peers[2][16] = {};
     float* mc[2] = {nullptr, nullptr};   // multicast (NVLS) addresses of the two buffers, or null
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
-    // CUDA-graph cache of whole sweeps (both streams, all kernels): a propagate() call ping-pongs between
-    // two argument sets, so two entries suffice; anything else falls back to direct launches.
+    // CUDA-graph cache of enqueued sweep batches (all streams, all kernels): a propagate() call cycles through a few
+    // argument sets (Z buffer rotation), so a handful of entries suffice; anything else evicts the oldest.
     struct SweepGraph {
-        const void* key[10] = {nullptr};
+        const void* key[12] = {nullptr};
         float gamma = 0.0f;
-        int log_cap = 0;
+        int log_cap = 0, n_sweeps = 0, nz = 0, c0 = 0, loop = 0;
         cudaGraphExec_t exec = nullptr;
         unsigned long long last_use = 0;
-    } graphs[2];
+    } graphs[6];
     unsigned long long graph_clock = 0;
     bool use_graphs = true;
+    bool while_ok = true;              // conditional-WHILE graphs available (cleared when their creation fails once)
     bool profile = false;              // record timing events around the kernels of each sweep
-    cudaEvent_t ev_prof[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* d_P0 = nullptr;      // [n_groups][32]   (fused only)
+    cudaEvent_t ev_prof[8] = {};
+    unsigned long long* d_trace = nullptr;   // measurement aid: [kTraceSweeps][kTraceSlots][2] globaltimer stamps
+    float* d_P0 = nullptr;      // [2][n_groups + 1][32]   (fused only; one copy per sweep parity)
+    size_t p0_stride = 0;       // floats per copy
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;
     float* d_p2 = nullptr;
     size_t p1_floats = 0, p2_floats = 0;
 };
+
+constexpr int kTraceSweeps = 64, kTraceSlots = 6;   // slots: segments, long chains, short chains, spans, L1 tail, -
 
 extern "C" int clane_internal_prepare_kernels(void);

@@ -28,7 +28,7 @@ constexpr int kTaskSegment = 1 << 9;
 constexpr int kTaskHubShift = 10;
 
 constexpr int kMaxPeers = 15;                  // remote ranks of a row-partitioned run (one NVLink domain)
-constexpr int kLongBlocks = 128;               // hub rows of >= 1024 neighbours take the heavy chain kernel
+constexpr int kLongBlocks = 2048;              // hub rows of >= 16384 neighbours take the heavy chain kernel
 constexpr int kSegEdges = 128;                 // neighbours per hub segment task (16 blocks)
 constexpr int kMetaRing = 128;                 // (offset, w) pairs of a warp's window
 

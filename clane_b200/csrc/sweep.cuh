@@ -64,17 +64,32 @@ struct SweepParams {
     int sld;                    // 32 * nslab32b: columns per block in hubS
     float4* hubS;               // per hub row [32-column slab][block][32] {z6, z4, X, Y}
     float4* hubT;               // per hub row [sequential-regime column][neighbour] raw z (floats)
-    int* hub_cnt;               // per hub row: segment warps that have parked their blocks (this sweep)
-    int* hub_done;              // per chain CTA: 1 once the early (overlapped) chain pass has produced the row piece
     int hub_first;              // first hub row of this chain launch
-    unsigned long long chain_spin_ns;   // early chain pass: give up waiting after this long (the late pass takes over)
+    int task_lo;                // first task of this row-kernel launch (segments and spans are launched separately)
     const clane_patience* st;
     // row-partitioned run: the other ranks' Znext buffers (peer memory over NVLink); every finished row is
     // stored to all of them from inside the kernel, so the exchange overlaps the sweep row by row
     float* peer[kMaxPeers];
     int n_remote;
     float* mc;                  // multicast (NVLS) address of Znext: one store reaches every rank; replaces peer[]
+    unsigned long long* trace;  // measurement aid (clane_plan_trace): {first CTA start, last CTA end} in ns, or null
 };
+
+// timeline stamps of a kernel: earliest start / latest end over its CTAs (globaltimer, ns)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(unsigned long long* tr) {
+    if (tr != nullptr && threadIdx.x == 0) atomicMin(tr, globaltimer_ns());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* tr) {
+    if (tr != nullptr && threadIdx.x == 0) atomicMax(tr + 1, globaltimer_ns());
+}
+__global__ void k_trace_stamp(unsigned long long* tr, int end) {
+    if (end) atomicMax(tr + 1, globaltimer_ns()); else atomicMin(tr, globaltimer_ns());
+}
 
 #ifndef CLANE_ROW_WARPS
 #define CLANE_ROW_WARPS 2
@@ -88,18 +103,23 @@ constexpr size_t kRowWarpSmem = (size_t)kMetaRing * sizeof(int2) + 2 * 512 + 2 *
 constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 
 // hub chain kernel: one warp per CTA
-constexpr int kChainGroup = 16;                // blocks per cp.async group (8 KB)
-constexpr int kChainGroups = 12;               // groups in flight (12 x 8 KB = 96 KB: two chain CTAs per SM)
-constexpr int kLightStages = 4;                // short hub rows
-__host__ __device__ constexpr size_t chain_smem_bytes(int stages) {
-    return (size_t)stages * kChainGroup * 32 * sizeof(float4) + (size_t)stages * kChainGroup * sizeof(float2);
+// Two variants.  Light (every hub row but the very longest): 8 blocks per cp.async group, 8 groups in flight (32 KB), no
+// register double buffer, compiled for 64 registers -- a CTA of 64 x 64 registers is exactly what an SM full of span
+// CTAs (12 x 64 threads x 80 registers) still has room for, so the chains run BESIDE the span tasks instead of waiting
+// for the machine to drain.  Heavy (rows of >= kLongBlocks blocks, where the chain itself bounds the sweep): 16 blocks
+// per group, 12 groups (96 KB), register double buffer -- the chain never waits for the ring.
+constexpr int kHeavyGroup = 16, kHeavyStages = 12;
+constexpr int kLightGroup = 8, kLightStages = 8;
+__host__ __device__ constexpr size_t chain_smem_bytes(int stages, int group) {
+    return (size_t)stages * group * 32 * sizeof(float4) + (size_t)stages * group * sizeof(float2);
 }
-constexpr size_t kChainSmemBytes = chain_smem_bytes(kChainGroups);
+constexpr size_t kHeavySmemBytes = chain_smem_bytes(kHeavyStages, kHeavyGroup);
+constexpr size_t kLightSmemBytes = chain_smem_bytes(kLightStages, kLightGroup);
 constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
 constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
 constexpr int kMaxStages = 128;                // mbarrier pairs per chain CTA
 constexpr int kChainThreads = 64;              // producer warp + chain warp
-static_assert(kChainGroups <= kMaxStages, "mbarriers");
+static_assert(kHeavyStages <= kMaxStages && kLightStages <= kMaxStages, "mbarriers");
 
 __device__ __forceinline__ void fma4(float wv, const float4& z, float4& acc) {
     acc.x = ffma(wv, z.x, acc.x); acc.y = ffma(wv, z.y, acc.y);
@@ -489,15 +509,12 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
             }
         }
     }
-    // tell the row's chain warps (k_hub_chain, running beside this kernel) that these blocks are parked
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicAdd(p.hub_cnt + (t0.w >> kTaskHubShift), 1);
 }
 
 __global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
     if (p.st != nullptr && p.st->stop) return;
+    trace_begin(p.trace);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem + (size_t)warp * kRowWarpSmem;
     int2* meta = reinterpret_cast<int2*>(mine);
@@ -507,10 +524,13 @@ __global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_swe
     const int wtask = blockIdx.x * kRowWarps + warp;
     int ti = wtask, slab = 0;
     if (p.nslab > 1) { ti = wtask / p.nslab; slab = wtask - ti * p.nslab; }
-    if (ti >= p.n_tasks) return;
-    const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
-    if (t0.w & kTaskSegment) run_segment(p, t0, __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1), slab, lane, meta);
-    else run_span(p, t0, slab, lane, meta, scratch, rowbuf, state);
+    ti += p.task_lo;
+    if (ti < p.n_tasks) {
+        const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
+        if (t0.w & kTaskSegment) run_segment(p, t0, __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1), slab, lane, meta);
+        else run_span(p, t0, slab, lane, meta, scratch, rowbuf, state);
+    }
+    if (p.trace != nullptr) { __syncthreads(); trace_end(p.trace); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -523,53 +543,26 @@ __global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_swe
 //   slab s < nslab32b : 32 columns in the 8-block order, lane = column;  per block {z6, z4, X, Y} + {w4, w6}
 //   slab s = nslab32b : the <= 16 sequential-regime columns, lane = column; per neighbour z (transposed by the
 //                       segment warps: every column's values are contiguous) + w
-// kEarly: launched on a side stream BEFORE k_sweep_rows and running beside it; every CTA waits (bounded) for
-//         its row's segment warps, then chains.  The hub rows' segments are the first tasks of the row kernel,
-//         so the chains finish long before the ordinary rows do and cost the sweep nothing.
-// !kEarly: launched after both; chains whatever the early pass did not (it timed out: kernels serialised by a
-//         profiler, or the device too busy to co-schedule), and resets the flags for the next sweep.
-// kLight: short rows -- 4-stage ring, no register double buffer: a CTA that costs an SM next to nothing while it
-//         waits.  !kLight: long rows (>= kLongBlocks blocks) -- 12 stages, the chain never waits for the ring.
-template <bool kEarly, bool kLight>
-__global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
-    constexpr int kStages = kLight ? kLightStages : kChainGroups;
+// Launched on the plan's side stream right after the segment tasks (a launch of k_sweep_rows over the segment part
+// of the task list, same stream): ordinary stream order, no flags, no waiting inside the kernel.  The span tasks
+// run on the caller's stream at the same time, so the chains cost the sweep nothing unless a hub row is long
+// enough to outlast all ordinary rows.
+// kLight: short rows -- 4-stage ring, no register double buffer.  !kLight: long rows (>= kLongBlocks blocks) --
+//         12 stages, the chain never waits for the ring.
+template <bool kLight>
+__global__ void __launch_bounds__(kChainThreads, kLight ? 16 : 1) k_hub_chain(SweepParams p) {
+    constexpr int kStages = kLight ? kLightStages : kHeavyStages;
+    constexpr int kChainGroup = kLight ? kLightGroup : kHeavyGroup;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
-    __shared__ int s_done;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = p.nslab32b + (p.ntail4 > 0 ? 1 : 0);
     const int hr = p.hub_first + blockIdx.x / per, s = blockIdx.x % per;
-    const int cta = hr * per + s;                      // index into hub_done
-    const bool stopped = p.st != nullptr && p.st->stop;
-    if (kEarly && stopped) return;
-    const int4 info = __ldg(p.hub_info + hr);          // one load: every access here queues behind the row kernel's
+    if (p.st != nullptr && p.st->stop) return;
+    trace_begin(p.trace);
+    const int4 info = __ldg(p.hub_info + hr);
     const int row = info.x, a = info.y, k = info.z;
     const int nblk = k >> 3;
-    if (kEarly) {
-        const int expect = ((nblk + kSegEdges / 8 - 1) / (kSegEdges / 8)) * p.nslab;
-        const volatile int* cnt = p.hub_cnt + hr;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        t1 = t0;
-        bool ready = false;
-        for (;;) {
-            if (*cnt >= expect) { ready = true; break; }
-            __nanosleep(200);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > p.chain_spin_ns) break;
-        }
-        ready = __syncthreads_and(ready);              // both warps agree
-        if (!ready) return;                            // the late pass does it
-        __threadfence();                               // acquire: the parked blocks of every segment warp
-    } else {
-        if (threadIdx.x == 0) {
-            s_done = p.hub_done[cta];
-            p.hub_done[cta] = 0;                       // also when stopped
-            if (s == 0) p.hub_cnt[hr] = 0;
-        }
-        __syncthreads();
-        if (s_done || stopped) return;
-    }
     const size_t B0 = (size_t)info.w;
     const int nleft = k - nblk * 8;
     if (threadIdx.x == 0) {
@@ -587,7 +580,7 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
     // sequential regime: stage = [ntc columns][kTailPitch] z | [32] w; as many stages as the shared memory holds
     float* zr = reinterpret_cast<float*>(smem);
     const int tstride = ntc * kTailPitch + kTailGroup;
-    const int tstages = min(kMaxStages, (int)(chain_smem_bytes(kStages) / sizeof(float)) / max(tstride, 1));
+    const int tstages = min(kMaxStages, (int)(chain_smem_bytes(kStages, kChainGroup) / sizeof(float)) / max(tstride, 1));
 
     if (warp == 1) {
         // ---------------- producer ----------------
@@ -748,7 +741,7 @@ __global__ void __launch_bounds__(kChainThreads) k_hub_chain(SweepParams p) {
         if (p.mc != nullptr) multimem_st1(p.mc + off, v);
         for (int j = 0; j < p.n_remote; ++j) p.peer[j][off] = v;
     }
-    if (kEarly && lane == 0) p.hub_done[cta] = 1;
+    trace_end(p.trace);
 }
 
 // Fused mode: the level-0 partial of every group that was not swept by a single warp (it holds

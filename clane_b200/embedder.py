@@ -2,10 +2,11 @@
 
 Same constructor, ``iterate()``, ``propagate()``, ``history`` and ``minimum_amount_updated_Z``;
 the per-vertex Python loop of embedder.py:85-92 becomes one ``clane_sweep`` C-ABI call per
-sweep (fused gather-SpMM + residual, exact L1 change, device-side patience state machine), and
-sweeps are enqueued in batches so the host synchronises once per batch instead of per sweep.
-The sweeps enqueued after the patience counter hit zero are device-side no-ops, so the result
-is exactly the reference's (same sweep count, same Z).
+sweep (fused gather-SpMM + residual, exact L1 change, device-side patience state machine); a
+whole ``propagate()`` is ONE ``clane_sweeps`` call -- a CUDA graph whose conditional WHILE node
+repeats batches of sweeps until the device-side patience counter reaches zero.  Work enqueued
+after that point is a device-side no-op, so the result is exactly the reference's (same sweep
+count, same Z).
 """
 from __future__ import annotations
 
@@ -179,30 +180,48 @@ class Embedder(object):
                    "clane_patience_reset")
         gamma = ctypes.c_float(float(np.float32(self.gamma)))
         history_Z = [] if self.save_history else None
-        batch = 1 if self.save_history else max(1, min(int(tol.initial_value), 8))
         start = S.cur
-        enqueued = 0
-        while True:
-            for _ in range(batch):
-                src, dst = S.Z[(start + enqueued) & 1], S.Z[(start + enqueued + 1) & 1]
-                _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), src.data_ptr(), dst.data_ptr(),
-                                         S.rowptr.data_ptr(), S.col.data_ptr(), S.w.data_ptr(), gamma,
-                                         0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream), "clane_sweep")
-                enqueued += 1
+
+        def read_state():
             with torch.cuda.stream(S.stream):
                 S.state_host.copy_(S.state, non_blocking=True)
             S.stream.synchronize()
-            st = _lib.Patience.from_buffer_copy(S.state_host.numpy().tobytes())
-            if history_Z is not None:
+            return _lib.Patience.from_buffer_copy(S.state_host.numpy().tobytes())
+
+        if history_Z is None:
+            # the whole call is ONE graph launch: a conditional WHILE node repeats batches of sweeps (the L1 / patience
+            # tail of every sweep beside the rows of the next one) until the device-side patience counter hits zero
+            rc = L.clane_sweeps(S.plan.handle, S.X.data_ptr(), S.Zptrs, start, S.rowptr.data_ptr(), S.col.data_ptr(),
+                                S.w.data_ptr(), gamma, 0, 1, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream)
+            if rc == _lib.CLANE_EUNSUPPORTED:      # no conditional graph nodes: host-driven batches, one sync per batch
+                st = None
+                while st is None or not st.stop:
+                    _lib.check(L.clane_sweeps(S.plan.handle, S.X.data_ptr(), S.Zptrs, start, S.rowptr.data_ptr(),
+                                              S.col.data_ptr(), S.w.data_ptr(), gamma, 6, 0, S.state.data_ptr(),
+                                              S.log.data_ptr(), S.log_cap, stream), "clane_sweeps")
+                    st = read_state()    # 6 sweeps = two full rotations: every batch starts at the same buffer
+            else:
+                _lib.check(rc, "clane_sweeps")
+                st = read_state()
+        else:
+            # save_history: one sweep per call, its Z copied out before the next one starts
+            k = 0
+            while True:
+                src, dst = S.Z[(start + k) % 3], S.Z[(start + k + 1) % 3]
+                _lib.check(L.clane_sweep(S.plan.handle, S.X.data_ptr(), src.data_ptr(), dst.data_ptr(),
+                                         S.rowptr.data_ptr(), S.col.data_ptr(), S.w.data_ptr(), gamma,
+                                         0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream), "clane_sweep")
+                k += 1
+                st = read_state()
                 if self._history_writer is not None:
                     history_Z.append(self._history_writer.put(dst[:S.n, :S.d], len(self.history['Z']), len(history_Z)))
                 else:
                     history_Z.append(dst[:S.n, :S.d].cpu())
-            if st.stop:
-                break
+                if st.stop:
+                    break
         done = int(st.sweeps)
         caller.wait_stream(S.stream)
-        S.cur = (start + done) & 1
+        S.cur = (start + done) % 3         # sweep i read Z[(start + i) % 3] and wrote the next buffer
         amounts = S.log[:min(done, S.log_cap)].cpu().numpy()
         self.sweeps_per_call.append(done)
         self.amounts_per_call.append(amounts)

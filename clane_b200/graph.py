@@ -7,7 +7,7 @@ constructor, attributes and methods (``Graph(data_root, embedding_dim)``, ``.d .
 on every access) and everything the iterative update touches lives in HBM:
 
     rowptr int32[N+1] | col int32[E] | erow int32[E] | w fp32[E]
-    X fp32[N, ld] | Z fp32[2][N, ld]   (ld = d rounded up to 4 floats: 16-byte aligned rows)
+    X fp32[N, ld] | Z fp32[3][N, ld]   (ld = d rounded up to 4 floats: 16-byte aligned rows; three rotating buffers)
     clane_plan: the degree-sorted row-block schedule (hub groups / row groups, sinks dropped)
 
 All arithmetic is done by libclane_b200.so through the C-ABI (clane_b200/_lib.py); torch
@@ -228,7 +228,8 @@ class Graph(Dataset):
             S.plan = _lib.Plan(n, e, d, self._rowptr, 0, n, HUB_THRESHOLD)   # module attribute: tests lower it
             S.X = torch.zeros([max(n, 1), ld], dtype=torch.float32, device=dev)
             S.X[:n, :d] = self.X.to(dev)
-            S.Z = [torch.zeros_like(S.X), torch.zeros_like(S.X)]
+            S.Z = [torch.zeros_like(S.X) for _ in range(3)]     # rotating: sweep t reads Z[(cur + t) % 3], writes the next
+            S.Zptrs = (ctypes.c_void_p * 3)(*[z.data_ptr() for z in S.Z])
             S.cur = 0
             S.w = torch.zeros(max(e, 1), dtype=torch.float32, device=dev)
             S.norms2 = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -251,6 +252,7 @@ class Graph(Dataset):
         S.Z[0].zero_()
         S.Z[0][:S.n, :S.d] = Z.to(device=S.device, dtype=torch.float32)
         S.Z[1].copy_(S.Z[0])
+        S.Z[2].copy_(S.Z[0])
         S.cur = 0
 
     @property
@@ -283,8 +285,8 @@ class Graph(Dataset):
         else:
             S = self._dev
             row = value.to(device=S.device, dtype=torch.float32).reshape(S.d)
-            S.Z[0][idx, :S.d] = row             # both ping-pong buffers: sinks are never rewritten by a sweep
-            S.Z[1][idx, :S.d] = row
+            for z in S.Z:                       # every buffer: rows without out-neighbours are never rewritten by a sweep
+                z[idx, :S.d] = row
 
     def set_Z(self, Z: torch.Tensor) -> None:
         """Replace the embeddings (graph.py:136-138)."""

@@ -44,6 +44,7 @@ extern "C" {
 #define CLANE_EPARSE (-6)      /* edge line without exactly one TAB */
 #define CLANE_EUNKNOWNID (-7)  /* edge endpoint that is not in V */
 #define CLANE_ENOMEM (-8)      /* host allocation failed */
+#define CLANE_EUNSUPPORTED (-9) /* not available with this driver (the caller has a fallback) */
 
 typedef void* clane_stream_t;  /* cudaStream_t */
 
@@ -187,6 +188,29 @@ int clane_sweep(clane_plan* plan, const float* d_X, const float* d_Zcur, float* 
                 const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma,
                 float* d_amount, clane_patience* d_state, float* d_amounts_log, int32_t log_cap,
                 clane_stream_t s);
+
+/* Several sweeps of one Embedder.propagate call (/root/reference/clane/embedder.py:83-108) enqueued at once, with
+ * the patience state machine on the device.  d_Z3 = three [n, ld] buffers (host array of three device pointers);
+ * sweep t reads d_Z3[(cur + t) % 3] and writes d_Z3[(cur + t + 1) % 3] (rows without out-neighbours are never
+ * written: all three buffers must hold their value).  With three buffers the exact L1 change + patience update of
+ * sweep t runs beside the rows of sweep t + 1; a sweep therefore sees a patience flag that is one sweep old, and at
+ * most ONE speculative sweep runs after the stop -- into a buffer that is not the result -- while its own L1 / patience
+ * step is a no-op: d_state->sweeps, the amounts log and the result d_Z3[(cur + d_state->sweeps) % 3] are exactly the
+ * reference's.
+ *   until_stop == 0: exactly n_sweeps sweeps are enqueued (no-ops once d_state->stop is set).
+ *   until_stop != 0: ONE graph launch whose conditional WHILE node repeats batches of sweeps until d_state->stop
+ *                    (bound the number with clane_patience_reset's max_sweeps); CLANE_EUNSUPPORTED if conditional
+ *                    graph nodes are not available -- call again with until_stop == 0 and poll d_state.
+ * Returns as soon as the work is enqueued on stream s. */
+int clane_sweeps(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t cur, const int32_t* d_rowptr,
+                 const int32_t* d_col, const float* d_w, float gamma, int32_t n_sweeps, int32_t until_stop,
+                 clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
+
+/* Measurement aid: a timeline of the kernels of the next enqueued batch of sweeps.  enable != 0 arms it (and resets the
+ * stamps); h_out (may be NULL) first receives the stamps of the previous batch: [64 sweeps][6 slots][2] unsigned 64-bit
+ * globaltimer nanoseconds {first CTA start, last CTA end}; slots: hub segments, long-row chains, short-row chains, span
+ * tasks, exact-L1 tail, unused.  Untouched slots read {2^64 - 1, 0}. */
+int clane_plan_trace(clane_plan* plan, int enable, unsigned long long* h_out);
 
 /* (Za - Zb).abs().sum() over the flattened [n*d] array in ATen cascade order
  * (/root/reference/clane/embedder.py:60).  Result in d_out[0]. */
