@@ -436,6 +436,20 @@ def run_gpu(args):
         line["sharded_phase_ms_all_ranks"] = allp
 
     if world == 1:
+        # Graph.build_P (scores + global norms + row softmax), once per propagate() call: its own small roofline
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        g._build_P_device(sim)
+        torch.cuda.synchronize()
+        evs[0].record()
+        for _ in range(10):
+            g._build_P_device(sim)
+        evs[1].record()
+        torch.cuda.synchronize()
+        bp_ms = evs[0].elapsed_time(evs[1]) / 10
+        bp_bytes = 4 * d * n + 16 * e + 4 * (n + 1)
+        line["build_p"] = {"ms": bp_ms, "algorithmic_bytes": bp_bytes, "achieved_gbs": bp_bytes / (bp_ms * 1e-3) / 1e9,
+                           "frac": bp_bytes / (bp_ms * 1e-3) / 1e9 / peak,
+                           "kernels": "k_dots (warp per 32 edges, tiled) + cascade level 0/1 + finish + row softmax"}
         if rank == 0:
             line["e2e"] = e2e_session(L, g, X, n, e, d, args.steps)
     else:

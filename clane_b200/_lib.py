@@ -54,7 +54,10 @@ SIGNATURES = {
     "clane_cascade_shape": (C.c_int, [C.c_int64, c_i64p, c_i64p]),
     "clane_edge_rows": (C.c_int, [c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "clane_scores_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp, c_vp]),
+    "clane_norms_partial": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "clane_norms_finish": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_row_softmax": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
+    "clane_plan_softmax": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_cosine_finalize": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
     "clane_build_p_cosine": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp, C.c_int32, c_vp]),

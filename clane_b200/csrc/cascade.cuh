@@ -41,6 +41,22 @@ struct ElemAbsDiff {  // |a[t] - b[t]| over an [n, d] matrix stored with leading
         }
         v[0] = fabsf(fsub(__ldg(a + idx), __ldg(b + idx)));
     }
+    // streaming form for the level-0 loop: element t, then t + 32, t + 64, ... without a division per element
+    struct Iter { size_t idx; int j; };
+    __device__ __forceinline__ Iter iter(int64_t t) const {
+        Iter it;
+        if (d == ld) { it.idx = (size_t)t; it.j = 0; }
+        else { const int64_t r = t / d; it.j = (int)(t - r * d); it.idx = (size_t)r * ld + it.j; }
+        return it;
+    }
+    __device__ __forceinline__ void next(Iter& it, float* v) const {
+        v[0] = fabsf(fsub(__ldg(a + it.idx), __ldg(b + it.idx)));
+        it.idx += 32;
+        if (d != ld) {
+            it.j += 32;
+            while (it.j >= d) { it.j -= d; it.idx += (size_t)(ld - d); }
+        }
+    }
 };
 
 struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + j
@@ -49,6 +65,7 @@ struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + 
     const int32_t* erow;
     const int32_t* col;
     int d, ld;
+    int64_t e_count;      // edges (the streaming form never reads an index past the last one)
     struct Base { int64_t e0; uint32_t j0; };
     __device__ __forceinline__ Base prepare(int64_t t0) const {
         Base bs;
@@ -64,6 +81,29 @@ struct ElemGatherSq2 {  // (Z[erow[e]][j]^2, Z[col[e]][j]^2) for flat t = e*d + 
         v[0] = fmul(x, x);
         v[1] = fmul(y, y);
     }
+    // streaming form: the edge's two row pointers are fetched once per edge, not once per element
+    struct Iter { int64_t e; int j; const float* pa; const float* pb; };
+    __device__ __forceinline__ Iter iter(int64_t t) const {
+        Iter it;
+        it.e = t / d;
+        it.j = (int)(t - it.e * d);
+        it.pa = Z + (size_t)__ldg(erow + it.e) * ld;
+        it.pb = Z + (size_t)__ldg(col + it.e) * ld;
+        return it;
+    }
+    __device__ __forceinline__ void next(Iter& it, float* v) const {
+        const float x = __ldg(it.pa + it.j), y = __ldg(it.pb + it.j);
+        v[0] = fmul(x, x);
+        v[1] = fmul(y, y);
+        it.j += 32;
+        if (it.j >= d) {
+            do { it.j -= d; ++it.e; } while (it.j >= d);
+            // (the last element of the array may step one edge past the end: clamp the index loads, the pointers are unused)
+            const int64_t ec = it.e < e_count ? it.e : e_count - 1;
+            it.pa = Z + (size_t)__ldg(erow + ec) * ld;
+            it.pb = Z + (size_t)__ldg(col + ec) * ld;
+        }
+    }
 };
 
 // The <= 31 elements the finish kernel reads itself (everything past the last complete cascade row; the whole
@@ -75,6 +115,9 @@ struct ElemValues {
     struct Base { int dummy; };
     __device__ __forceinline__ Base prepare(int64_t) const { return Base{0}; }
     __device__ __forceinline__ void load(const Base&, uint32_t off, float* v) const { v[0] = vals[off]; }
+    struct Iter { uint32_t off; };
+    __device__ __forceinline__ Iter iter(int64_t t) const { return Iter{(uint32_t)t}; }
+    __device__ __forceinline__ void next(Iter& it, float* v) const { v[0] = vals[it.off & 31]; it.off += 32; }
 };
 
 template <class Elem>
@@ -112,14 +155,14 @@ k_cascade_l01(Elem elem, CascadeShape sh, float* __restrict__ ws, int64_t node_l
 
     for (int ch = warp; ch < nchunks; ch += kCascadeWarps) {
         const int64_t t0 = (row0 + (int64_t)ch * step) * 32;
-        typename Elem::Base bs = elem.prepare(t0);
+        typename Elem::Iter it = elem.iter(t0 + lane);
         float acc[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[q] = 0.0f;
         for (int r = 0; r < step; r += 8) {
             float v[8][NQ];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) elem.load(bs, (uint32_t)((r + u) * 32 + lane), v[u]);
+            for (int u = 0; u < 8; ++u) elem.next(it, v[u]);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -131,13 +174,13 @@ k_cascade_l01(Elem elem, CascadeShape sh, float* __restrict__ ws, int64_t node_l
     if (!full && sh.r_rem > 0 && warp == (int)(sh.c_rem % kCascadeWarps)) {
         // leftover rows of the last, incomplete chunk: they stay in acc[0] to the end
         const int64_t t0 = (row0 + sh.c_rem * step) * 32;
-        typename Elem::Base bs = elem.prepare(t0);
+        typename Elem::Iter it = elem.iter(t0 + lane);
         float acc[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[q] = 0.0f;
         for (int r = 0; r < (int)sh.r_rem; ++r) {
             float v[NQ];
-            elem.load(bs, (uint32_t)(r * 32 + lane), v);
+            elem.next(it, v);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) acc[q] = fadd(acc[q], v[q]);
         }

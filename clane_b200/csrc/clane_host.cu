@@ -238,7 +238,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
 
 int clane_plan_destroy(clane_plan* plan) {
     if (!plan) return CLANE_OK;
-    cudaFree(plan->d_tasks); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
+    cudaFree(plan->d_tasks); cudaFree(plan->d_long_rows); cudaFree(plan->d_fix_groups); cudaFree(plan->d_hub_rows);
     cudaFree(plan->d_hub_info); cudaFree(plan->d_hubS); cudaFree(plan->d_hubT);
     for (cudaEvent_t ev : plan->evs) cudaEventDestroy(ev);
     if (plan->side) cudaStreamDestroy(plan->side);
@@ -387,6 +387,16 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     if (rc != CLANE_OK) { clane_plan_destroy(plan); return rc; }
     plan->n_tasks = (int32_t)tasks.size();
     plan->n_seg_tasks = plan->n_tasks - n_spans;
+    {   // rows the row softmax of build_P gives a whole CTA (>= 64 neighbours)
+        std::vector<int32_t> longr;
+        for (int32_t v = row_lo; v < row_hi; ++v)
+            if (h_rowptr[v + 1] - h_rowptr[v] >= 64) longr.push_back(v);
+        plan->n_long_rows = (int32_t)longr.size();
+        if (!longr.empty()) {
+            PLAN_CUDA(cudaMalloc(&plan->d_long_rows, longr.size() * sizeof(int32_t)));
+            PLAN_CUDA(cudaMemcpy(plan->d_long_rows, longr.data(), longr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+    }
     PLAN_CUDA(cudaMalloc(&plan->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(SweepTask)));
     PLAN_CUDA(cudaMalloc(&plan->d_fix_groups, std::max<size_t>(n_fix, 1) * sizeof(int32_t)));
     PLAN_CUDA(cudaMalloc(&plan->d_hub_rows, std::max<size_t>(n_hrows, 1) * sizeof(int32_t)));

@@ -39,38 +39,86 @@ __global__ void k_edge_rows(const int32_t* __restrict__ rowptr, int32_t n, int64
 // per-edge dot, sequential over the feature index (similarity.py:35-37)
 //   d < 400 : ATen native bmm loop  acc = fl(acc + fl(a*b))
 //   d >= 400: oneMKL                acc = fma(a, b, acc)
+// The chain over the d features of one edge is inherently serial (one thread), the gathers want a whole warp per
+// row.  So a warp takes 32 consecutive edges: phase A reads both rows of every edge with coalesced 128-bit loads
+// (lane = float4 of columns, 128 columns at a time) and parks the products -- or, for the fma order, both operands --
+// in a shared-memory tile; phase B gives every lane one edge, which it sums in feature order out of the tile (row
+// pitch 132 floats: the 128-bit reads of a quarter warp cover all 32 banks).  The running sums stay in registers
+// across the 128-column blocks, so any d works.
 // ------------------------------------------------------------------------------------------
+constexpr int kDotCols = 128, kDotPitch = kDotCols + 4;
+template <bool kFma> __host__ __device__ constexpr int dot_warps() { return kFma ? 2 : 4; }
+template <bool kFma> __host__ __device__ constexpr size_t dot_smem() { return (size_t)dot_warps<kFma>() * 32 * kDotPitch * sizeof(float) * (kFma ? 2 : 1); }
+
 template <bool kFma>
-__global__ void __launch_bounds__(256)
-k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ erow,
-       const int32_t* __restrict__ col, int64_t e_lo, int64_t e_hi, float* __restrict__ dots) {
-    const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e_hi) return;
-    const float* a = Z + (size_t)__ldg(erow + e) * ld;
-    const float* b = Z + (size_t)__ldg(col + e) * ld;
-    float acc = 0.0f;
-    const int d4 = d & ~3;
-    int j = 0;
-    for (; j + 16 <= d4; j += 16) {
-        float4 x[4], y[4];
+__global__ void __launch_bounds__(32 * dot_warps<kFma>())
+k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ erow, const int32_t* __restrict__ col,
+       int64_t e_lo, int64_t e_hi, float* __restrict__ dots) {
+    extern __shared__ __align__(16) float dot_tile[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ta = dot_tile + (size_t)warp * 32 * kDotPitch * (kFma ? 2 : 1);
+    float* tb = ta + 32 * kDotPitch;                     // kFma only
+    const int64_t ntiles = (e_hi - e_lo + 31) / 32;
+    for (int64_t tile = (int64_t)blockIdx.x * dot_warps<kFma>() + warp; tile < ntiles; tile += (int64_t)gridDim.x * dot_warps<kFma>()) {
+        const int64_t e0 = e_lo + tile * 32;
+        const int cnt = (int)min((int64_t)32, e_hi - e0);
+        int ra = 0, rb = 0;                              // lane i: the two rows of edge e0 + i (float4 units)
+        if (lane < cnt) { ra = __ldg(erow + e0 + lane) * (ld >> 2); rb = __ldg(col + e0 + lane) * (ld >> 2); }
+        float acc = 0.0f;
+        for (int c0 = 0; c0 < d; c0 += kDotCols) {
+            const int c = c0 + 4 * lane;
+            const bool in = c < ld;                      // rows are padded to a multiple of 4 floats: whole float4s are readable
+            const float4* zc = reinterpret_cast<const float4*>(Z) + (in ? c >> 2 : 0);
+            // ---- phase A: 8 edges per round, 16 independent 128-bit loads in flight ----
+            // (consecutive edges mostly share their source row -- CSR order: its piece is loaded once per run)
+            int prev = -1;
+            float4 xprev = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < cnt; i += 8) {
+                float4 x[8], y[8];
+                int oa[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { x[u] = ldg4(a + j + 4 * u); y[u] = ldg4(b + j + 4 * u); }
+                for (int u = 0; u < 8; ++u) {
+                    oa[u] = __shfl_sync(kFull, ra, (i + u) & 31);
+                    const int ob = __shfl_sync(kFull, rb, (i + u) & 31);
+                    y[u] = __ldg(zc + ob);
+                    if (oa[u] != (u == 0 ? prev : oa[u - 1])) x[u] = __ldg(zc + oa[u]);     // uniform branch
+                }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (kFma) {
-                acc = ffma(x[u].x, y[u].x, acc); acc = ffma(x[u].y, y[u].y, acc);
-                acc = ffma(x[u].z, y[u].z, acc); acc = ffma(x[u].w, y[u].w, acc);
-            } else {
-                acc = fadd(acc, fmul(x[u].x, y[u].x)); acc = fadd(acc, fmul(x[u].y, y[u].y));
-                acc = fadd(acc, fmul(x[u].z, y[u].z)); acc = fadd(acc, fmul(x[u].w, y[u].w));
+                for (int u = 0; u < 8; ++u)
+                    if (oa[u] == (u == 0 ? prev : oa[u - 1])) x[u] = u == 0 ? xprev : x[u - 1];
+                prev = oa[7];
+                xprev = x[7];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (kFma) {
+                        *reinterpret_cast<float4*>(ta + (i + u) * kDotPitch + 4 * lane) = x[u];
+                        *reinterpret_cast<float4*>(tb + (i + u) * kDotPitch + 4 * lane) = y[u];
+                    } else {
+                        *reinterpret_cast<float4*>(ta + (i + u) * kDotPitch + 4 * lane) =
+                            make_float4(fmul(x[u].x, y[u].x), fmul(x[u].y, y[u].y), fmul(x[u].z, y[u].z), fmul(x[u].w, y[u].w));
+                    }
+                }
             }
+            __syncwarp();
+            // ---- phase B: lane i sums edge i over this block's columns, in order ----
+            const int ncol = min(kDotCols, d - c0);
+            const float* pa = ta + lane * kDotPitch;
+            const float* pb = tb + lane * kDotPitch;
+            int j = 0;
+            for (; j + 4 <= ncol; j += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(pa + j);
+                if (kFma) {
+                    const float4 q = *reinterpret_cast<const float4*>(pb + j);
+                    acc = ffma(p.x, q.x, acc); acc = ffma(p.y, q.y, acc); acc = ffma(p.z, q.z, acc); acc = ffma(p.w, q.w, acc);
+                } else {
+                    acc = fadd(acc, p.x); acc = fadd(acc, p.y); acc = fadd(acc, p.z); acc = fadd(acc, p.w);
+                }
+            }
+            for (; j < ncol; ++j) acc = kFma ? ffma(pa[j], pb[j], acc) : fadd(acc, pa[j]);
+            __syncwarp();
         }
+        if (lane < cnt) dots[e0 + lane] = acc;
     }
-    for (; j < d; ++j) {
-        const float x = __ldg(a + j), y = __ldg(b + j);
-        acc = kFma ? ffma(x, y, acc) : fadd(acc, fmul(x, y));
-    }
-    dots[e] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -105,64 +153,121 @@ __device__ __forceinline__ float sleef_expf_u10(float d) {
 //   rows shorter than 16), p_i = e_i * (1 / sum).
 // One warp per row.  Optional global divisor c = fl(sqrt(S1)) * fl(sqrt(S2)) (similarity.py:37).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_row_softmax(const float* scores, const float* __restrict__ norms2, int32_t row_lo, int32_t row_hi,
-              const int32_t* __restrict__ rowptr, float* w) {   // scores and w may be the same array (in place)
-    const int row = row_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+constexpr int kSoftmaxShort = 64;   // rows shorter than this: one thread per row; the others: one warp per row
+
+// Short rows (the bulk of a power-law graph: mean degree ~7): one THREAD per row.  The reference's order for k < 16 is a
+// plain sequential sum -- exactly a one-thread loop; for 16 <= k < 64 the thread keeps the 16 lane accumulators of
+// vec::reduce_all in registers and folds them with the xor-8/4/2/1 butterfly (only the nodes lane 0's result needs).
+__global__ void __launch_bounds__(128)
+k_row_softmax_short(const float* scores, const float* __restrict__ norms2, int32_t row_lo, int32_t row_hi,
+                    const int32_t* __restrict__ rowptr, float* w) {   // scores and w may be the same array (in place)
+    const int row = row_lo + (int)((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (row >= row_hi) return;
     const int a = __ldg(rowptr + row), k = __ldg(rowptr + row + 1) - a;
-    if (k == 0) return;
+    if (k == 0 || k >= kSoftmaxShort) return;
     const bool div = norms2 != nullptr;
     float c = 1.0f;
     if (div) c = fmul(__fsqrt_rn(__ldg(norms2)), __fsqrt_rn(__ldg(norms2 + 1)));
-
     float m = -CUDART_INF_F;
-    for (int i = lane; i < k; i += 32) {
+    for (int i = 0; i < k; ++i) {
+        float s = scores[a + i];
+        if (div) s = __fdiv_rn(s, c);
+        m = fmaxf(m, s);
+    }
+    float sum;
+    if (k < 16) {
+        sum = 0.0f;
+        for (int i = 0; i < k; ++i) {
+            float s = scores[a + i];
+            if (div) s = __fdiv_rn(s, c);
+            const float e = sleef_expf_u10(fsub(s, m));
+            w[a + i] = e;                       // position i is never read again as a score
+            sum = i == 0 ? e : fadd(sum, e);
+        }
+    } else {
+        float acc[16];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+        // lane l accumulates e_l, e_{l+16}, ... over the full 16-vectors, then the k mod 16 leftovers go to lanes 0..
+        for (int base = 0; base < k; base += 16) {
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+                if (base + l < k) {
+                    float s = scores[a + base + l];
+                    if (div) s = __fdiv_rn(s, c);
+                    const float e = sleef_expf_u10(fsub(s, m));
+                    w[a + base + l] = e;
+                    acc[l] = base == 0 ? e : fadd(acc[l], e);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 8; h >= 1; h >>= 1)
+#pragma unroll
+            for (int l = 0; l < h; ++l) acc[l] = fadd(acc[l], acc[l + h]);
+        sum = acc[0];
+    }
+    const float inv = __fdiv_rn(1.0f, sum);
+    for (int i = 0; i < k; ++i) w[a + i] = fmul(w[a + i], inv);
+}
+
+// Long rows: one CTA per row.  Only the 16-lane accumulation is serial (k / 16 dependent adds per lane: microseconds
+// even for a row of 10^5 neighbours); the maximum and the exponentials -- the expensive part -- are spread over the CTA.
+// rows: a list of row ids (rows of >= kSoftmaxShort neighbours, from the plan), or null = row_lo + blockIdx.x.
+constexpr int kSoftmaxLongThreads = 256;
+__global__ void __launch_bounds__(kSoftmaxLongThreads)
+k_row_softmax_long(const float* scores, const float* __restrict__ norms2, const int32_t* __restrict__ rows, int32_t row_lo,
+                   const int32_t* __restrict__ rowptr, float* w) {   // scores and w may be the same array (in place)
+    __shared__ float red[kSoftmaxLongThreads / 32];
+    __shared__ float s_sum;
+    const int row = rows != nullptr ? __ldg(rows + blockIdx.x) : row_lo + (int)blockIdx.x;
+    const int a = __ldg(rowptr + row), k = __ldg(rowptr + row + 1) - a;
+    if (k < kSoftmaxShort) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool div = norms2 != nullptr;
+    float c = 1.0f;
+    if (div) c = fmul(__fsqrt_rn(__ldg(norms2)), __fsqrt_rn(__ldg(norms2 + 1)));
+    float m = -CUDART_INF_F;
+    for (int i = tid; i < k; i += kSoftmaxLongThreads) {
         float s = scores[a + i];
         if (div) s = __fdiv_rn(s, c);
         m = fmaxf(m, s);
     }
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, h));
-
-    float sum;
-    float e_reg = 0.0f;  // rows of <= 32 edges keep e in a register
-    if (k < 16) {
-        if (lane < k) {
-            float s = scores[a + lane];
-            if (div) s = __fdiv_rn(s, c);
-            e_reg = sleef_expf_u10(fsub(s, m));
-        }
-        sum = __shfl_sync(kFull, e_reg, 0);
-        for (int i = 1; i < k; ++i) sum = fadd(sum, __shfl_sync(kFull, e_reg, i));
-    } else {
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int q = 1; q < kSoftmaxLongThreads / 32; ++q) m = fmaxf(m, red[q]);
+    // every exponential, in parallel (element i is read as a score and written as e_i by the same thread)
+    for (int i = tid; i < k; i += kSoftmaxLongThreads) {
+        float s = scores[a + i];
+        if (div) s = __fdiv_rn(s, c);
+        w[a + i] = sleef_expf_u10(fsub(s, m));
+    }
+    __syncthreads();
+    // lane l < 16 of warp 0: e_l, e_{l+16}, ... in order (the k mod 16 leftovers land in lanes 0..), then the butterfly
+    if (warp == 0) {
         float acc = 0.0f;
-        for (int base = 0; base < k; base += 32) {
-            const int i = base + lane;
-            float e = 0.0f;
-            if (i < k) {
-                float s = scores[a + i];
-                if (div) s = __fdiv_rn(s, c);
-                e = sleef_expf_u10(fsub(s, m));
-                if (k > 32) w[a + i] = e;
+        if (lane < 16) {
+            int i = lane;
+            for (; i + 7 * 16 < k; i += 8 * 16) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = w[a + i + 16 * u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = (i == lane && u == 0) ? v[0] : fadd(acc, v[u]);
             }
-            e_reg = e;
-            const float hi = __shfl_down_sync(kFull, e, 16);
-            // lane l < 16 accumulates e_l, e_{l+16}, e_{l+32}, ... in order (missing = +0)
-            acc = fadd(acc, e);
-            acc = fadd(acc, hi);
+            for (; i < k; i += 16) acc = i == lane ? w[a + i] : fadd(acc, w[a + i]);
         }
 #pragma unroll
         for (int h = 8; h >= 1; h >>= 1) acc = fadd(acc, __shfl_xor_sync(kFull, acc, h));
-        sum = __shfl_sync(kFull, acc, 0);
+        if (lane == 0) s_sum = acc;
     }
-    const float inv = __fdiv_rn(1.0f, sum);
-    if (k <= 32) {
-        if (lane < k) w[a + lane] = fmul(e_reg, inv);
-    } else {
-        for (int i = lane; i < k; i += 32) w[a + i] = fmul(w[a + i], inv);
-    }
+    __syncthreads();
+    const float inv = __fdiv_rn(1.0f, s_sum);
+    for (int i = tid; i < k; i += kSoftmaxLongThreads) w[a + i] = fmul(w[a + i], inv);
 }
 
 // col[e] * ld / 4: the float4 index the sweep gathers from (one multiply per edge, once per graph)
@@ -270,26 +375,68 @@ int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_er
 
 int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col,
                         int64_t edge_lo, int64_t edge_hi, float* d_dots, float* d_norms2, clane_stream_t s) {
-    if (!plan || !d_Z || !d_erow || !d_col || !d_dots || !d_norms2) return CLANE_EINVAL;
+    if (!plan || !d_Z || !d_erow || !d_col || !d_dots) return CLANE_EINVAL;
     if (edge_lo < 0 || edge_hi > plan->e || edge_lo > edge_hi) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
     if (edge_hi > edge_lo) {
-        const unsigned grid = (unsigned)((edge_hi - edge_lo + 255) / 256);
-        if (plan->d < 400) k_dots<false><<<grid, 256, 0, st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
-        else k_dots<true><<<grid, 256, 0, st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+        const int64_t ntiles = (edge_hi - edge_lo + 31) / 32;
+        if (plan->d < 400) {
+            const unsigned grid = (unsigned)std::min<int64_t>((ntiles + dot_warps<false>() - 1) / dot_warps<false>(), 148 * 24);
+            k_dots<false><<<grid, 32 * dot_warps<false>(), dot_smem<false>(), st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+        } else {
+            const unsigned grid = (unsigned)std::min<int64_t>((ntiles + dot_warps<true>() - 1) / dot_warps<true>(), 148 * 24);
+            k_dots<true><<<grid, 32 * dot_warps<true>(), dot_smem<true>(), st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+        }
         CLANE_LAUNCH_CHECK();
     }
-    ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld};
+    if (!d_norms2) return CLANE_OK;       // dots only: a rank of a row-partitioned run reduces the norms by node range
+    ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld, plan->e};
     return cascade_launch(el, plan->e * (int64_t)plan->d, plan->d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, st);
+}
+
+int clane_norms_partial(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col, int64_t node_lo,
+                        int64_t node_hi, float* d_p1, clane_stream_t s) {
+    if (!plan || !d_Z || !d_erow || !d_col || !d_p1) return CLANE_EINVAL;
+    ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld, plan->e};
+    return cascade_launch_l01(el, plan->e * (int64_t)plan->d, node_lo, node_hi, d_p1, nullptr, (cudaStream_t)s);
+}
+
+int clane_norms_finish(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col, const float* d_p1,
+                       float* d_norms2, clane_stream_t s) {
+    if (!plan || !d_Z || !d_erow || !d_col || !d_p1 || !d_norms2) return CLANE_EINVAL;
+    ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld, plan->e};
+    return cascade_launch_finish(el, plan->e * (int64_t)plan->d, d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, nullptr,
+                                 (cudaStream_t)s);
 }
 
 int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t row_lo, int32_t row_hi,
                       const int32_t* d_rowptr, float* d_w, clane_stream_t s) {
     if (!d_scores || !d_rowptr || !d_w || row_lo < 0 || row_hi < row_lo) return CLANE_EINVAL;
     if (row_hi == row_lo) return CLANE_OK;
-    const unsigned grid = (unsigned)(((int64_t)(row_hi - row_lo) * 32 + 255) / 256);
-    k_row_softmax<<<grid, 256, 0, (cudaStream_t)s>>>(d_scores, d_norms2, row_lo, row_hi, d_rowptr, d_w);
+    // rows shorter than kSoftmaxShort: a thread each; the rest: a CTA each (without a plan's list of long rows the CTAs of
+    // short rows exit at once)
+    k_row_softmax_short<<<(unsigned)((row_hi - row_lo + 127) / 128), 128, 0, (cudaStream_t)s>>>(d_scores, d_norms2, row_lo, row_hi,
+                                                                                             d_rowptr, d_w);
     CLANE_LAUNCH_CHECK();
+    k_row_softmax_long<<<(unsigned)(row_hi - row_lo), kSoftmaxLongThreads, 0, (cudaStream_t)s>>>(d_scores, d_norms2, nullptr, row_lo,
+                                                                                             d_rowptr, d_w);
+    CLANE_LAUNCH_CHECK();
+    return CLANE_OK;
+}
+
+int clane_plan_softmax(clane_plan* plan, const float* d_scores, const float* d_norms2, const int32_t* d_rowptr, float* d_w,
+                       clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_scores || !d_rowptr || !d_w) return CLANE_EINVAL;
+    const int32_t rows = plan->row_hi - plan->row_lo;
+    if (rows <= 0) return CLANE_OK;
+    k_row_softmax_short<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)s>>>(d_scores, d_norms2, plan->row_lo, plan->row_hi,
+                                                                                   d_rowptr, d_w);
+    CLANE_LAUNCH_CHECK();
+    if (plan->n_long_rows > 0) {
+        k_row_softmax_long<<<(unsigned)plan->n_long_rows, kSoftmaxLongThreads, 0, (cudaStream_t)s>>>(d_scores, d_norms2, plan->d_long_rows,
+                                                                                                 plan->row_lo, d_rowptr, d_w);
+        CLANE_LAUNCH_CHECK();
+    }
     return CLANE_OK;
 }
 
@@ -307,7 +454,7 @@ int clane_build_p_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ro
     // rows [row_lo, row_hi) own the contiguous edge range [rowptr[row_lo], rowptr[row_hi])
     int rc = clane_scores_cosine(plan, d_Z, d_erow, d_col, plan->edge_lo, plan->edge_hi, d_w, d_norms2, s);
     if (rc != CLANE_OK) return rc;
-    return clane_row_softmax(d_w, d_norms2, plan->row_lo, plan->row_hi, d_rowptr, d_w, s);
+    return clane_plan_softmax(plan, d_w, d_norms2, d_rowptr, d_w, s);
 }
 
 // timing bracket: an ordinary record, or -- while the sweep is being captured -- an external event-record node of
@@ -764,6 +911,8 @@ int clane_internal_prepare_kernels(void) {
     static bool done = false;
     if (done) return CLANE_OK;
     CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeavySmemBytes));
+    CLANE_CUDA(cudaFuncSetAttribute(k_dots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<false>()));
+    CLANE_CUDA(cudaFuncSetAttribute(k_dots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<true>()));
     if (const char* v = getenv("CLANE_ROW_CARVEOUT"))    // timing experiments: shared-memory carveout (percent) of the row kernel
         CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)

@@ -23,6 +23,8 @@ struct clane_plan {
     int32_t n_tasks = 0;
     int32_t* d_fix_groups = nullptr;   // fused mode: groups whose chunk partial is recomputed from memory
     int32_t* d_hub_rows = nullptr;     // rows of degree > hub_threshold, degree-descending
+    int32_t* d_long_rows = nullptr;    // rows of >= 64 neighbours (row softmax: one CTA each)
+    int32_t n_long_rows = 0;
     void* d_hub_info = nullptr;        // int4 per hub row: {row, first edge, degree, first scratch block}
     int64_t hub_blocks = 0;            // 8-neighbour blocks of all hub rows
     int32_t limit = 0, ntail4 = 0, nslab32b = 0;   // 16*floor(d/16); float4 pieces beyond it; 32-column slabs below it

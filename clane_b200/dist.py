@@ -19,9 +19,10 @@ per sweep instead.  The three global scalars stay bit-identical on every rank:
     stores of Znext have landed.  Patience is replicated, never broadcast.  When the shape
     cannot be cut that way (d odd, tiny n) the ranks first synchronise, then reduce balanced
     node ranges of the full array.
-  * the two Frobenius norms of build_P (similarity.py:37) are computed redundantly by every rank
-    over all E*d gathered elements (each rank holds the full Z and CSR); dots and softmax only for
-    the rank's own rows.
+  * the two Frobenius norms of build_P (similarity.py:37) are cascade sums over the flattened [E*d] gathered
+    arrays: each rank reduces a balanced, contiguous range of the cascade's level-1 nodes (it holds the full Z and
+    CSR, so any node range is local work), the ranks all-reduce the node slots exactly as for the L1 change, and every
+    rank finishes the fixed-order combine itself; dots and softmax only for the rank's own rows.
 
 The helpers at the top are pure host logic (tested under gloo on CPU); ShardedSweeper needs CUDA.
 """
@@ -137,6 +138,11 @@ class ShardedSweeper:
             self.nlo, self.nhi = node_range(self.n1, self.world, self.rank)
         # level-1 slots [n1 + 2][32] + the trailing element values [32]: one all-reduce
         self.p1 = torch.zeros((self.n1 + 3) * 32, dtype=torch.float32, device=dev)
+        # the norms of build_P: level-1 nodes of the cascade over [E*d], two quantities per node
+        _lib.check(L.clane_cascade_shape(e * d, ctypes.byref(nodes), None))
+        self.nn = int(nodes.value)
+        self.nn_lo, self.nn_hi = node_range(self.nn, self.world, self.rank)
+        self.pn = torch.zeros((self.nn + 2) * 64, dtype=torch.float32, device=dev)
         self.sync_token = torch.zeros(1, dtype=torch.float32, device=dev)
         s = _lib.stream_handle()
         _lib.check(L.clane_edge_rows(self.rowptr.data_ptr(), n, e, self.erow.data_ptr(), s))
@@ -178,10 +184,30 @@ class ShardedSweeper:
         return "nccl" if self.world > 1 else "none"
 
     def build_p(self) -> None:
+        """Graph.build_P for this rank's rows: dots of the own edges, the two global norms reduced by level-1 node
+        range (each rank its share of the nodes of the cascade over [E*d], one all-reduce of the slots -- every slot is
+        written by exactly one rank, so the sum is exact and identical everywhere), softmax of the own rows."""
         L = _lib.lib()
-        _lib.check(L.clane_build_p_cosine(self.plan.handle, self.Z[self.cur].data_ptr(), self.rowptr.data_ptr(),
-                                          self.erow.data_ptr(), self.col.data_ptr(), self.w.data_ptr(),
-                                          self.norms2.data_ptr(), _lib.stream_handle()), "clane_build_p_cosine")
+        s = _lib.stream_handle()
+        z = self.Z[self.cur].data_ptr()
+        if self.e == 0:
+            return
+        if self.world == 1:
+            _lib.check(L.clane_build_p_cosine(self.plan.handle, z, self.rowptr.data_ptr(), self.erow.data_ptr(),
+                                              self.col.data_ptr(), self.w.data_ptr(), self.norms2.data_ptr(), s),
+                       "clane_build_p_cosine")
+            return
+        elo, ehi = int(self.g._rowptr[self.lo]), int(self.g._rowptr[self.hi])
+        _lib.check(L.clane_scores_cosine(self.plan.handle, z, self.erow.data_ptr(), self.col.data_ptr(), elo, ehi,
+                                         self.w.data_ptr(), 0, s), "clane_scores_cosine")
+        self.pn.zero_()
+        _lib.check(L.clane_norms_partial(self.plan.handle, z, self.erow.data_ptr(), self.col.data_ptr(), self.nn_lo,
+                                         self.nn_hi, self.pn.data_ptr(), s), "clane_norms_partial")
+        dist.all_reduce(self.pn, op=dist.ReduceOp.SUM)
+        _lib.check(L.clane_norms_finish(self.plan.handle, z, self.erow.data_ptr(), self.col.data_ptr(), self.pn.data_ptr(),
+                                        self.norms2.data_ptr(), s), "clane_norms_finish")
+        _lib.check(L.clane_plan_softmax(self.plan.handle, self.w.data_ptr(), self.norms2.data_ptr(), self.rowptr.data_ptr(),
+                                        self.w.data_ptr(), s), "clane_plan_softmax")
 
     def sweep(self, with_l1: bool = True) -> int:
         """One sweep: own rows (stored to every rank's Znext when the exchange is fused), exact L1 +

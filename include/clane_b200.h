@@ -155,9 +155,19 @@ int clane_edge_rows(const int32_t* d_rowptr, int32_t n, int64_t e, int32_t* d_er
  *                 d < 400, fma for d >= 400 -- the ATen / MKL switch), for edges
  *                 [edge_lo, edge_hi);
  *   d_norms2[0] = sum(Z[src]^2), d_norms2[1] = sum(Z[dst]^2) over the flattened [E*d]
- *                 gathered arrays in ATen cascade-sum order (all E edges). */
+ *                 gathered arrays in ATen cascade-sum order (all E edges); NULL: dots only. */
 int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col,
                         int64_t edge_lo, int64_t edge_hi, float* d_dots, float* d_norms2, clane_stream_t s);
+
+/* The two global norms of similarity.py:37 split for a row-partitioned (multi-GPU) run, like clane_l1_partial: the
+ * level-1 nodes of the cascade over the flattened [E*d] gathered arrays are independent, so each rank reduces nodes
+ * [node_lo, node_hi) (of clane_cascade_shape(E*d)) into d_p1 -- layout [n1_nodes + 2][2][32] floats, zero elsewhere --
+ * the ranks all-reduce(SUM) the slots (each is written by exactly one rank: exact), and clane_norms_finish combines
+ * them in the one fixed order on every rank: d_norms2[0..1]. */
+int clane_norms_partial(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col, int64_t node_lo,
+                        int64_t node_hi, float* d_p1, clane_stream_t s);
+int clane_norms_finish(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col, const float* d_p1,
+                       float* d_norms2, clane_stream_t s);
 
 /* The per-source softmax of Graph.build_P (/root/reference/clane/graph.py:122-123) for rows
  * [row_lo, row_hi).  If d_norms2 != NULL each score is first divided by
@@ -165,6 +175,11 @@ int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ero
  * produced by a user plugin.  d_w may alias d_scores. */
 int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t row_lo, int32_t row_hi,
                       const int32_t* d_rowptr, float* d_w, clane_stream_t s);
+
+/* The same softmax for the plan's rows, with the plan's list of long rows (one CTA per row of >= 64 neighbours, one
+ * thread per shorter row). */
+int clane_plan_softmax(clane_plan* plan, const float* d_scores, const float* d_norms2, const int32_t* d_rowptr, float* d_w,
+                       clane_stream_t s);
 
 /* The final division of CosineSimilarity.__call__ (similarity.py:37) for standalone plugin
  * calls: d_out[i] = d_dots[i] / fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))).  May alias. */
