@@ -343,6 +343,9 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     const int64_t auto_thr = std::min<int64_t>(16384, std::max<int64_t>(256, (e_local / 4096 + 7) / 8 * 8));
     plan->hub_threshold = hub_threshold > 0 ? std::min(std::max(hub_threshold, 8), 1 << 20) : (int32_t)auto_thr;
     plan->span_edges = 128;
+    // measured at arxiv shape: a propagate() of 20 sweeps is 1.2 ms faster enqueued directly (no graph to build), but a
+    // host-driven loop stalls the device at every state read; so direct enqueue stays an opt-in
+    plan->prefer_direct = getenv("CLANE_PREFER_DIRECT") != nullptr;
     // tuning aids (benchmark sweeps only)
     if (const char* v = getenv("CLANE_HUB_THRESHOLD")) plan->hub_threshold = std::max(atoi(v), 8);
     if (const char* v = getenv("CLANE_SPAN_EDGES")) plan->span_edges = std::max(atoi(v), 8);
@@ -465,6 +468,7 @@ struct clane_session {
     clane_patience* state = nullptr;
     int cur = 0;  // Z[cur] holds the current embeddings (three rotating buffers: clane_sweeps)
     int32_t log_cap = 0;
+    void* pool = nullptr;               // one device allocation behind all of the pointers above (prev excepted)
     cudaStream_t stream = nullptr;
     clane_patience* h_state = nullptr;  // pinned
     float* h_stage = nullptr;           // pinned staging for padded rows
@@ -491,9 +495,7 @@ static int copy_rows_d2h(clane_session* s, float* h_dst, const float* d_src) {
 int clane_session_destroy(clane_session* s) {
     if (!s) return CLANE_OK;
     clane_plan_destroy(s->plan);
-    cudaFree(s->rowptr); cudaFree(s->col); cudaFree(s->erow);
-    cudaFree(s->X); cudaFree(s->Z[0]); cudaFree(s->Z[1]); cudaFree(s->Z[2]); cudaFree(s->prev); cudaFree(s->w); cudaFree(s->norms2);
-    cudaFree(s->amount); cudaFree(s->log); cudaFree(s->state);
+    cudaFree(s->pool); cudaFree(s->prev);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -518,22 +520,24 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
     const size_t zbytes = std::max<size_t>((size_t)n * s->ld * sizeof(float), 16);
     const size_t ebytes = std::max<size_t>((size_t)e * sizeof(int32_t), 16);
     SESSION_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    SESSION_CUDA(cudaMalloc(&s->rowptr, (size_t)(n + 1) * sizeof(int32_t)));
-    SESSION_CUDA(cudaMalloc(&s->col, ebytes));
-    SESSION_CUDA(cudaMalloc(&s->erow, ebytes));
-    SESSION_CUDA(cudaMalloc(&s->X, zbytes));
-    SESSION_CUDA(cudaMalloc(&s->Z[0], zbytes));
-    SESSION_CUDA(cudaMalloc(&s->Z[1], zbytes));
-    SESSION_CUDA(cudaMalloc(&s->Z[2], zbytes));
-    SESSION_CUDA(cudaMalloc(&s->prev, zbytes));
-    SESSION_CUDA(cudaMalloc(&s->w, ebytes));
-    SESSION_CUDA(cudaMalloc(&s->norms2, 2 * sizeof(float)));
-    SESSION_CUDA(cudaMalloc(&s->amount, sizeof(float)));
-    SESSION_CUDA(cudaMalloc(&s->log, (size_t)s->log_cap * sizeof(float)));
-    SESSION_CUDA(cudaMalloc(&s->state, sizeof(clane_patience)));
-    SESSION_TRY(clane_plan_create(&s->plan, n, e, d, h_rowptr, 0, n, hub_threshold));
+    // ONE device allocation for everything the session owns (a dozen separate cudaMallocs cost milliseconds), carved
+    // at 256-byte boundaries; `prev` (only iterate() needs it) is allocated on first use.
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t sizes[] = {up((size_t)(n + 1) * sizeof(int32_t)), up(ebytes), up(ebytes), up(zbytes), up(zbytes), up(zbytes),
+                            up(zbytes), up(ebytes), 256, 256, up((size_t)s->log_cap * sizeof(float)), 256};
+    size_t total = 0;
+    for (size_t b : sizes) total += b;
+    SESSION_CUDA(cudaMalloc(&s->pool, total));
+    {
+        char* p = static_cast<char*>(s->pool);
+        auto take = [&](int i) { char* q = p; p += sizes[i]; return q; };
+        s->rowptr = (int32_t*)take(0); s->col = (int32_t*)take(1); s->erow = (int32_t*)take(2);
+        s->X = (float*)take(3); s->Z[0] = (float*)take(4); s->Z[1] = (float*)take(5); s->Z[2] = (float*)take(6);
+        s->w = (float*)take(7); s->norms2 = (float*)take(8); s->amount = (float*)take(9); s->log = (float*)take(10);
+        s->state = (clane_patience*)take(11);
+    }
     SESSION_CUDA(cudaMallocHost(&s->h_state, sizeof(clane_patience)));
-
+    // uploads first (asynchronous from pinned buffers), so that the host-side schedule build below overlaps them
     SESSION_CUDA(cudaMemcpyAsync(s->rowptr, h_rowptr, (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (e > 0) SESSION_CUDA(cudaMemcpyAsync(s->col, h_col, (size_t)e * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     if (n > 0) {
@@ -542,6 +546,7 @@ int clane_session_create(clane_session** out, int32_t n, int64_t e, int32_t d, c
         SESSION_CUDA(cudaMemcpyAsync(s->Z[1], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
         SESSION_CUDA(cudaMemcpyAsync(s->Z[2], s->X, zbytes, cudaMemcpyDeviceToDevice, s->stream));
     }
+    SESSION_TRY(clane_plan_create(&s->plan, n, e, d, h_rowptr, 0, n, hub_threshold));
     SESSION_TRY(clane_edge_rows(s->rowptr, n, e, s->erow, s->stream));
     SESSION_CUDA(cudaStreamSynchronize(s->stream));  // the host vectors above go out of scope
     *out = s;
@@ -602,13 +607,13 @@ int clane_session_propagate(clane_session* s, float gamma, int32_t tol, int32_t 
     if (rc != CLANE_OK) return rc;
     const int start = s->cur;
     // one graph launch for the whole call (conditional WHILE over batches of sweeps); without conditional nodes:
-    // batches of 6 sweeps (two full buffer rotations), one host synchronisation per batch
+    // batches of 12 sweeps (whole buffer rotations), one host synchronisation per batch
     rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 0, 1, s->state, s->log, s->log_cap, s->stream);
     if (rc != CLANE_OK && rc != CLANE_EUNSUPPORTED) return rc;
     const bool looped = rc == CLANE_OK;
     for (;;) {
         if (!looped) {
-            rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 6, 0, s->state, s->log, s->log_cap,
+            rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 12, 0, s->state, s->log, s->log_cap,
                               s->stream);
             if (rc != CLANE_OK) return rc;
         }
@@ -633,6 +638,7 @@ int clane_session_iterate(clane_session* s, float gamma, int32_t tol, int32_t ma
     if (!s || tol < 1 || !min_amount) return CLANE_EINVAL;
     int patience = tol, calls = 0;
     const size_t zbytes = (size_t)s->n * s->ld * sizeof(float);
+    if (!s->prev) CLANE_CUDA(cudaMalloc(&s->prev, std::max<size_t>(zbytes, 16)));
     for (;;) {
         CLANE_CUDA(cudaMemcpyAsync(s->prev, s->Z[s->cur], zbytes, cudaMemcpyDeviceToDevice, s->stream));
         int sweeps = 0;

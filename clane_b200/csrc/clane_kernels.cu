@@ -467,6 +467,11 @@ static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t st) {
 
 namespace {
 
+cudaError_t prof_mark(clane_plan* plan, int i, cudaStream_t st) {
+    plan->prof_mask |= 1u << i;
+    return prof_record(plan->ev_prof[i], st);
+}
+
 struct SweepArgs {
     const float* X;
     const int32_t* rowptr;
@@ -524,9 +529,10 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
     const int64_t span_ctas = ((int64_t)(plan->n_tasks - plan->n_seg_tasks) * plan->nslab + kRowWarps - 1) / kRowWarps;
     const int64_t n_elems = (int64_t)plan->n * plan->d;
     const bool prof = plan->profile && n_sweeps == 1;
+    if (prof) plan->prof_mask = 0;
     cudaEvent_t e_begin = nullptr;
     CLANE_CUDA(mark(&e_begin, st));
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[0], st));
+    if (prof) CLANE_CUDA(prof_mark(plan, 0, st));
     std::vector<cudaEvent_t> eR((size_t)n_sweeps, nullptr), eC(eR), eC2(eR), eF(eR), eL(eR);
     for (int t = 0; t < n_sweeps; ++t) {
         const float* Zc = Z[(c0 + t) % nz];
@@ -573,13 +579,13 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             cudaEvent_t eS = nullptr;
             CLANE_CUDA(mark(&eS, plan->side));
             eS_cur = eS;
-            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[4], plan->side));
+            if (prof) CLANE_CUDA(prof_mark(plan, 4, plan->side));
             if (n_long > 0) {
                 p.trace = tr ? tr + 2 : nullptr;
                 CLANE_CUDA(launch_prio(k_hub_chain<false>, dim3((unsigned)(n_long * per_row)), dim3(kChainThreads), kHeavySmemBytes,
                                        plan->side, plan->prio_hi, p));
             }
-            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[5], plan->side));
+            if (prof) CLANE_CUDA(prof_mark(plan, 5, plan->side));
             CLANE_CUDA(mark(&eC[t], plan->side));
             if (n_short > 0) {             // its own stream: not behind the long rows' chains
                 CLANE_CUDA(cudaStreamWaitEvent(plan->side2, eS, 0));
@@ -601,14 +607,14 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
         // them.  CLANE_DEBUG_SEG_WAIT=1 starts the spans behind the segments: a timing experiment.)
         static const bool seg_wait = getenv("CLANE_DEBUG_SEG_WAIT") != nullptr;
         if (eS_cur && seg_wait) CLANE_CUDA(cudaStreamWaitEvent(st, eS_cur, 0));
-        if (prof) CLANE_CUDA(prof_record(plan->ev_prof[1], st));
+        if (prof) CLANE_CUDA(prof_mark(plan, 1, st));
         if (span_ctas > 0) {
             SweepParams pr = p;
             pr.task_lo = plan->n_seg_tasks;
             pr.trace = tr ? tr + 6 : nullptr;
             CLANE_CUDA(launch_prio(k_sweep_rows, dim3((unsigned)span_ctas), dim3(kRowThreads), 0, st, plan->prio_lo, pr));
         }
-        if (prof) CLANE_CUDA(prof_record(plan->ev_prof[2], st));
+        if (prof) CLANE_CUDA(prof_mark(plan, 2, st));
         CLANE_CUDA(mark(&eR[t], st));
         // ---- tail: the exact L1 change of this sweep ----
         if (want_l1) {
@@ -616,7 +622,7 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             CLANE_CUDA(cudaStreamWaitEvent(tl, eR[t], 0));
             if (eC[t]) CLANE_CUDA(cudaStreamWaitEvent(tl, eC[t], 0));
             if (eC2[t]) CLANE_CUDA(cudaStreamWaitEvent(tl, eC2[t], 0));
-            if (prof) CLANE_CUDA(prof_record(plan->ev_prof[6], tl));
+            if (prof) CLANE_CUDA(prof_mark(plan, 6, tl));
             if (tr) k_trace_stamp<<<1, 1, 0, tl>>>(tr + 8, 0);
             ElemAbsDiff el{Zn, Zc, plan->d, plan->ld};
             int rc;
@@ -654,7 +660,7 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
     if (eC2[last]) CLANE_CUDA(cudaStreamWaitEvent(st, eC2[last], 0));
     for (int t = std::max(0, n_sweeps - 2); t < n_sweeps; ++t)
         if (eL[t]) CLANE_CUDA(cudaStreamWaitEvent(st, eL[t], 0));
-    if (prof) CLANE_CUDA(prof_record(plan->ev_prof[3], st));
+    if (prof) CLANE_CUDA(prof_mark(plan, 3, st));
     return CLANE_OK;
 }
 
@@ -665,7 +671,9 @@ static int launch_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z, 
     static const bool env_graphs = getenv("CLANE_NO_GRAPHS") == nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    if (!plan->use_graphs || !env_graphs || cap != cudaStreamCaptureStatusNone || st == nullptr) {
+    static const bool env_force = getenv("CLANE_FORCE_GRAPHS") != nullptr;   // measurement aid
+    if (!plan->use_graphs || !env_graphs || cap != cudaStreamCaptureStatusNone || st == nullptr ||
+        (plan->prefer_direct && !env_force)) {
         if (loop) return CLANE_EINVAL;   // the caller falls back to host-driven batches
         return enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
     }
@@ -774,7 +782,8 @@ int clane_sweeps(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t
     if (rc != CLANE_OK) return rc;
     SweepArgs a{d_X, d_rowptr, d_col, d_w, gamma, nullptr, d_state, d_amounts_log, log_cap};
     if (until_stop) {
-        if (!plan->while_ok) return CLANE_EUNSUPPORTED;
+        static const bool env_force = getenv("CLANE_FORCE_GRAPHS") != nullptr;
+        if (!plan->while_ok || (plan->prefer_direct && !env_force)) return CLANE_EUNSUPPORTED;
         rc = launch_sweeps(plan, a, d_Z3, 3, cur, kSweepBatch, 1, st);
         return rc == CLANE_EINVAL ? CLANE_EUNSUPPORTED : rc;
     }
@@ -891,11 +900,12 @@ int clane_plan_profile_read(clane_plan* plan, float* h_ms) {
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[0], plan->ev_prof[1], plan->ev_prof[2]));   // row kernel
     CLANE_CUDA(cudaEventElapsedTime(&h_ms[1], plan->ev_prof[0], plan->ev_prof[3]));   // whole sweep
     h_ms[2] = h_ms[3] = 0.0f;
-    if (cudaEventQuery(plan->ev_prof[6]) == cudaSuccess)
+    if (plan->prof_mask & (1u << 6))
         CLANE_CUDA(cudaEventElapsedTime(&h_ms[2], plan->ev_prof[6], plan->ev_prof[3]));   // exact L1 tail
-    if (plan->n_long_hub_rows > 0 && cudaEventQuery(plan->ev_prof[5]) == cudaSuccess)
+    if ((plan->prof_mask & (3u << 4)) == (3u << 4)) {
+        CLANE_CUDA(cudaEventSynchronize(plan->ev_prof[5]));
         CLANE_CUDA(cudaEventElapsedTime(&h_ms[3], plan->ev_prof[4], plan->ev_prof[5]));   // chains of the long hub rows
-    cudaGetLastError();
+    }
     return CLANE_OK;
 }
 

@@ -53,9 +53,11 @@ struct clane_plan {
     } graphs[6];
     unsigned long long graph_clock = 0;
     bool use_graphs = true;
+    bool prefer_direct = false;        // enqueue sweeps directly instead of replaying graphs (CLANE_PREFER_DIRECT: measurement aid)
     bool while_ok = true;              // conditional-WHILE graphs available (cleared when their creation fails once)
     bool profile = false;              // record timing events around the kernels of each sweep
     cudaEvent_t ev_prof[8] = {};
+    unsigned prof_mask = 0;            // which of them the last profiled sweep recorded
     unsigned long long* d_trace = nullptr;   // measurement aid: [kTraceSweeps][kTraceSlots][2] globaltimer stamps
     float* d_P0 = nullptr;      // [2][n_groups + 1][32]   (fused only; one copy per sweep parity)
     size_t p0_stride = 0;       // floats per copy

@@ -193,13 +193,13 @@ class Embedder(object):
             # tail of every sweep beside the rows of the next one) until the device-side patience counter hits zero
             rc = L.clane_sweeps(S.plan.handle, S.X.data_ptr(), S.Zptrs, start, S.rowptr.data_ptr(), S.col.data_ptr(),
                                 S.w.data_ptr(), gamma, 0, 1, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, stream)
-            if rc == _lib.CLANE_EUNSUPPORTED:      # no conditional graph nodes: host-driven batches, one sync per batch
+            if rc == _lib.CLANE_EUNSUPPORTED:      # long sweeps (enqueued directly) or no conditional nodes: batches, one sync each
                 st = None
                 while st is None or not st.stop:
                     _lib.check(L.clane_sweeps(S.plan.handle, S.X.data_ptr(), S.Zptrs, start, S.rowptr.data_ptr(),
-                                              S.col.data_ptr(), S.w.data_ptr(), gamma, 6, 0, S.state.data_ptr(),
+                                              S.col.data_ptr(), S.w.data_ptr(), gamma, 12, 0, S.state.data_ptr(),
                                               S.log.data_ptr(), S.log_cap, stream), "clane_sweeps")
-                    st = read_state()    # 6 sweeps = two full rotations: every batch starts at the same buffer
+                    st = read_state()    # 12 sweeps = whole rotations: every batch starts at the same buffer
             else:
                 _lib.check(rc, "clane_sweeps")
                 st = read_state()
