@@ -413,7 +413,9 @@ def run_gpu(args):
                      "one all-reduce of the L1 slots per sweep" + (" (multimem.st through the NVSwitch multicast mapping)"
                                                                   if exch == "multicast" else "")
                      if exch in ("p2p", "multicast")
-                     else "NCCL all-gather of Z per sweep"),
+                     else "rows swept in chunks, every finished chunk copied to all ranks' Z by the copy engines (peer-to-peer "
+                          "cudaMemcpyAsync over NVLink) while the next chunk is swept; one all-reduce of the L1 slots per sweep"
+                     if exch == "ce" else "NCCL all-gather of Z per sweep"),
                      "step": "span tasks with the hub segments + chains beside them, exact L1 change (fused partials / cascade) "
                             "and device patience of every sweep beside the next sweep's rows (three rotating Z buffers, "
                             "replayed graphs of 6 sweeps); P frozen",
@@ -462,19 +464,20 @@ def run_gpu(args):
         r2 = cdist.ShardedSweeper(g, sim, GAMMA, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
         for i in range(args.steps):
             r2.sweep(True)
-        Zh = r2.Z_host()
+        Zh = r2.Z_host_slice()           # every rank downloads its own rows: together they are Z
         amount2 = r2.last_amount()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         secs = float(dt.item())
-        h2d = n * d * 4 + 4 * (n + 1) + 4 * e
-        d2h = Zh.numel() * 4 + 4
-        line["e2e"] = {"value": e * args.steps / secs, "unit": UNIT, "h2d_bytes_per_step": world * h2d / args.steps,
-                       "d2h_bytes_per_step": world * d2h / args.steps, "seconds": secs, "steps": args.steps,
+        h2d = n * d * 4 + world * (4 * (n + 1) + 4 * e)          # X once (a slice per rank), the CSR on every rank
+        d2h = n * d * 4 + 4 * world
+        line["e2e"] = {"value": e * args.steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                       "d2h_bytes_per_step": d2h / args.steps, "seconds": secs, "steps": args.steps,
                        "last_amount": amount2,
-                       "note": "ShardedSweeper(graph from host arrays) + steps x sweep(exact L1) + Z_host() on every rank, "
-                               "wall clock, max over ranks; upload, plan build, build_P and the download are inside the "
-                               "timed region and amortised over the steps of the call"}
+                       "note": "ShardedSweeper(graph from host arrays) + steps x sweep(exact L1) + Z_host_slice() on every rank, "
+                               "wall clock, max over ranks; every rank uploads the CSR and its own rows of X (the other rows "
+                               "arrive over NVLink) and downloads its own rows of Z; upload, plan build, build_P and the "
+                               "download are inside the timed region and amortised over the steps of the call"}
         del r2
         # ---- strong scaling on ONE workload: the same graph on rank 0's GPU alone, in this job ----
         n1 = torch.zeros(1, device="cuda")

@@ -348,7 +348,7 @@ int clane_plan_create(clane_plan** out, int32_t n, int64_t e, int32_t d, const i
     plan->prefer_direct = getenv("CLANE_PREFER_DIRECT") != nullptr;
     // tuning aids (benchmark sweeps only)
     if (const char* v = getenv("CLANE_HUB_THRESHOLD")) plan->hub_threshold = std::max(atoi(v), 8);
-    if (const char* v = getenv("CLANE_SPAN_EDGES")) plan->span_edges = std::max(atoi(v), 8);
+    if (const char* v = getenv("CLANE_SPAN_EDGES")) plan->span_edges = std::min(std::max(atoi(v), 8), clane::kMetaRing);
     plan->nslab = (plan->ld + 127) / 128;
     plan->limit = (d / 16) * 16;
     plan->ntail4 = (plan->ld - plan->limit) / 4;

@@ -603,9 +603,11 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             if (eC2[t - 1]) CLANE_CUDA(cudaStreamWaitEvent(st, eC2[t - 1], 0));
         }
         if (prev_tail) CLANE_CUDA(cudaStreamWaitEvent(st, prev_tail, 0));
-        // (The segments and the light chains fit beside the span CTAs -- see sweep.cuh -- so the spans do not wait for
-        // them.  CLANE_DEBUG_SEG_WAIT=1 starts the spans behind the segments: a timing experiment.)
-        static const bool seg_wait = getenv("CLANE_DEBUG_SEG_WAIT") != nullptr;
+        // The segments and the light chains fit beside the span CTAs (sweep.cuh), so normally the spans do not wait for
+        // them.  Heavy chains want an SM each: with long hub rows the spans start behind the segments, together with the
+        // heavy chains, which the higher priority places first (the segments are microseconds of a millisecond sweep).
+        static const char* seg_wait_env = getenv("CLANE_SEG_WAIT");     // 0 / 1: measurement aid
+        const bool seg_wait = seg_wait_env ? atoi(seg_wait_env) != 0 : n_long > 0;
         if (eS_cur && seg_wait) CLANE_CUDA(cudaStreamWaitEvent(st, eS_cur, 0));
         if (prof) CLANE_CUDA(prof_mark(plan, 1, st));
         if (span_ctas > 0) {

@@ -107,16 +107,19 @@ constexpr size_t kRowSmemBytes = (size_t)kRowWarps * kRowWarpSmem;
 // register double buffer, compiled for 64 registers -- a CTA of 64 x 64 registers is exactly what an SM full of span
 // CTAs (12 x 64 threads x 80 registers) still has room for, so the chains run BESIDE the span tasks instead of waiting
 // for the machine to drain.  Heavy (rows of >= kLongBlocks blocks, where the chain itself bounds the sweep): 16 blocks
-// per group, 12 groups (96 KB), register double buffer -- the chain never waits for the ring.
-constexpr int kHeavyGroup = 16, kHeavyStages = 12;
+// per group, register double buffer, and a ring of 26 groups = 216 KB: nothing else fits on the SM, which is the point --
+// beside 24 span warps a chain warp wins an issue slot only every ~12 cycles instead of every 4 (measured: 9 ns per
+// dependent operation), so the few chains that bound a sweep get an SM each to themselves.
+constexpr int kHeavyGroup = 16, kHeavyStages = 26;
 constexpr int kLightGroup = 8, kLightStages = 8;
 __host__ __device__ constexpr size_t chain_smem_bytes(int stages, int group) {
     return (size_t)stages * group * 32 * sizeof(float4) + (size_t)stages * group * sizeof(float2);
 }
 constexpr size_t kHeavySmemBytes = chain_smem_bytes(kHeavyStages, kHeavyGroup);
 constexpr size_t kLightSmemBytes = chain_smem_bytes(kLightStages, kLightGroup);
-constexpr int kTailGroup = 32;                 // neighbours per stage of the sequential-regime chain
-constexpr int kTailPitch = 36;                 // floats per (stage, column): 32 + 4, so that the 16 columns' 128-bit loads spread over the banks
+// sequential-regime chain: neighbours per ring stage (light / heavy) and floats per (stage, column): + 4, so that the
+// columns' 128-bit loads spread over the banks.  The heavy chain pays its mbarrier round trip once per 128 neighbours.
+constexpr int kLightTailGroup = 32, kHeavyTailGroup = 128;
 constexpr int kMaxStages = 128;                // mbarrier pairs per chain CTA
 constexpr int kChainThreads = 64;              // producer warp + chain warp
 static_assert(kHeavyStages <= kMaxStages && kLightStages <= kMaxStages, "mbarriers");
@@ -553,6 +556,8 @@ template <bool kLight>
 __global__ void __launch_bounds__(kChainThreads, kLight ? 16 : 1) k_hub_chain(SweepParams p) {
     constexpr int kStages = kLight ? kLightStages : kHeavyStages;
     constexpr int kChainGroup = kLight ? kLightGroup : kHeavyGroup;
+    constexpr int kTailGroup = kLight ? kLightTailGroup : kHeavyTailGroup;
+    constexpr int kTailPitch = kTailGroup + 4;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -612,14 +617,15 @@ __global__ void __launch_bounds__(kChainThreads, kLight ? 16 : 1) k_hub_chain(Sw
                 if (g >= tstages) mbar_wait(empty + st, (unsigned)(g / tstages - 1) & 1u);
                 const int i0 = g * kTailGroup;
                 const int cnt = min(kTailGroup, nnb - i0);            // multiple of 8
-                // 16-byte pieces: column q / 8, neighbours 4 * (q % 8) .. + 3
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int q = lane + 32 * t, c = q >> 3, pc = (q & 7) * 4;
-                    if (c < ntc && pc < cnt)
+                // 16-byte pieces: column q / (kTailGroup / 4), neighbours 4 * (q % (kTailGroup / 4)) .. + 3
+                constexpr int kPieces = kTailGroup / 4;
+                for (int q = lane; q < ntc * kPieces; q += 32) {
+                    const int c = q / kPieces, pc = (q % kPieces) * 4;
+                    if (pc < cnt)
                         cp_async16_sa(smem_u32(zr + (size_t)st * tstride + c * kTailPitch + pc), tsrc + (size_t)c * nnb + i0 + pc);
                 }
-                if (lane < cnt) cp_async4_sa(smem_u32(zr + (size_t)st * tstride + ntc * kTailPitch + lane), p.w + a + i0 + lane);
+                for (int q = lane; q < cnt; q += 32)
+                    cp_async4_sa(smem_u32(zr + (size_t)st * tstride + ntc * kTailPitch + q), p.w + a + i0 + q);
                 cp_async_arrive(full + st);
             }
         }
@@ -693,42 +699,48 @@ __global__ void __launch_bounds__(kChainThreads, kLight ? 16 : 1) k_hub_chain(Sw
             }
         }
     } else {
-        // ---- sequential regime: a = fma(w_i, z_i, a) over all neighbours (same register double buffer) ----
+        // ---- sequential regime: a = fma(w_i, z_i, a) over all neighbours ----
+        // One mbarrier round trip per stage; inside a stage, pieces of 32 neighbours go through a register double
+        // buffer (the shared-memory loads of piece s + 1 are issued before the 32 dependent fmas of piece s).
         const int cl = min(lane, ntc - 1);
-        float4 zv[kTailGroup / 4], zn[kTailGroup / 4], wv[kTailGroup / 4], wn[kTailGroup / 4];
-        auto fetch = [&](int g, float4 (&dz)[kTailGroup / 4], float4 (&dw)[kTailGroup / 4]) {
-            const bool live = g < ngroups;
-            const int st = g % tstages;
-            if (live) mbar_wait(full + st, (unsigned)(g / tstages) & 1u);
-            const float4* zs = reinterpret_cast<const float4*>(zr + (size_t)st * tstride + cl * kTailPitch);
-            const float4* ws = reinterpret_cast<const float4*>(zr + (size_t)st * tstride + ntc * kTailPitch);
+        constexpr int kPiece = 32;
+        float4 zv[kPiece / 4], zn[kPiece / 4], wv[kPiece / 4], wn[kPiece / 4];
+        auto load_piece = [&](const float* zs, const float* ws, int s0, float4 (&dz)[kPiece / 4], float4 (&dw)[kPiece / 4]) {
 #pragma unroll
-            for (int j = 0; j < kTailGroup / 4; ++j) { dz[j] = zs[j]; dw[j] = ws[j]; }
-            __syncwarp();
-            if (live && lane == 0) mbar_arrive(empty + st);
+            for (int j = 0; j < kPiece / 4; ++j) {
+                dz[j] = *reinterpret_cast<const float4*>(zs + s0 + 4 * j);     // past the stage's end: stale, unused
+                dw[j] = *reinterpret_cast<const float4*>(ws + s0 + 4 * j);
+            }
         };
-        auto chain = [&](int g, const float4 (&dz)[kTailGroup / 4], const float4 (&dw)[kTailGroup / 4]) {
-            const int cnt = min(kTailGroup, nnb - g * kTailGroup);   // multiple of 8
+        auto chain_piece = [&](int cnt, const float4 (&dz)[kPiece / 4], const float4 (&dw)[kPiece / 4]) {   // cnt: multiple of 8
 #pragma unroll
-            for (int j = 0; j < kTailGroup / 4; ++j)
-                if (cnt == kTailGroup || 4 * j < cnt) {
+            for (int j = 0; j < kPiece / 4; ++j)
+                if (cnt >= kPiece || 4 * j < cnt) {
                     acc = ffma(dw[j].x, dz[j].x, acc);
                     acc = ffma(dw[j].y, dz[j].y, acc);
                     acc = ffma(dw[j].z, dz[j].z, acc);
                     acc = ffma(dw[j].w, dz[j].w, acc);
                 }
         };
-        if (kLight) {
-            for (int g = 0; g < ngroups; ++g) { fetch(g, zv, wv); chain(g, zv, wv); }
-        } else {
-            fetch(0, zv, wv);
-            for (int g = 0; g < ngroups; g += 2) {
-                fetch(g + 1, zn, wn);
-                chain(g, zv, wv);
-                if (g + 1 >= ngroups) break;
-                fetch(g + 2, zv, wv);
-                chain(g + 1, zn, wn);
+        for (int g = 0; g < ngroups; ++g) {
+            const int st = g % tstages;
+            mbar_wait(full + st, (unsigned)(g / tstages) & 1u);
+            const float* zs = zr + (size_t)st * tstride + cl * kTailPitch;
+            const float* ws = zr + (size_t)st * tstride + ntc * kTailPitch;
+            const int cnt = min(kTailGroup, nnb - g * kTailGroup);           // multiple of 8
+            load_piece(zs, ws, 0, zv, wv);
+#pragma unroll 1
+            for (int s0 = 0; s0 < cnt; s0 += 2 * kPiece) {
+                if (kTailGroup > kPiece) load_piece(zs, ws, min(s0 + kPiece, kTailGroup - kPiece), zn, wn);
+                chain_piece(cnt - s0, zv, wv);
+                if (kTailGroup > kPiece) {
+                    if (s0 + kPiece >= cnt) break;
+                    load_piece(zs, ws, min(s0 + 2 * kPiece, kTailGroup - kPiece), zv, wv);
+                    chain_piece(cnt - s0 - kPiece, zn, wn);
+                }
             }
+            __syncwarp();                    // every lane has read the stage
+            if (lane == 0) mbar_arrive(empty + st);
         }
     }
 #pragma unroll

@@ -117,9 +117,16 @@ class ShardedSweeper:
         self.rowptr = torch.from_numpy(graph._rowptr).to(dev)
         self.col = torch.from_numpy(graph._col if e else np.zeros(1, np.int32)).to(dev)
         self.erow = torch.zeros(max(e, 1), dtype=torch.int32, device=dev)
+        # X: only this rank's rows travel host -> device (a sweep reads x_v of its own rows only); the initial Z = X of
+        # the other ranks' rows arrives over NVLink (one all-gather of the slices) instead of 8 x the PCIe upload
         self.X = torch.zeros([npad, ld], dtype=torch.float32, device=dev)
-        self.X[:n, :d] = graph.X.to(dev)
+        if self.hi > self.lo:
+            self.X[self.lo:self.hi, :d] = graph.X[self.lo:self.hi].to(dev, non_blocking=True)
+        if self.world > 1:
+            lo_pad = self.rank * self.per
+            gather_rows(self.X[lo_pad:lo_pad + self.per].clone(), self.X)
         self.plan = _lib.Plan(n, e, d, graph._rowptr, self.lo, self.hi, 0)
+        self.chunks = []          # exchange "ce": (plan, row_lo, row_hi) per chunk of this rank's rows
         self.exchange = self._alloc_z(npad, ld, exchange)
         self.cur = 0
         self.w = torch.zeros(max(e, 1), dtype=torch.float32, device=dev)
@@ -156,7 +163,7 @@ class ShardedSweeper:
         available, plain device memory + NCCL all-gather otherwise."""
         L = _lib.lib()
         self.symm = None
-        if exchange in ("auto", "p2p", "multicast") and self.world > 1:
+        if exchange in ("auto", "p2p", "multicast", "ce") and self.world > 1:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 bufs = [symm_mem.empty((npad, ld), dtype=torch.float32, device=self.dev) for _ in range(2)]
@@ -166,9 +173,16 @@ class ShardedSweeper:
                     b.copy_(self.X)
                 torch.cuda.synchronize()
                 dist.barrier()
+                self.Z, self.symm = bufs, hdls
+                if exchange == "ce" or (exchange == "auto" and self.world > 2):
+                    # Copy-engine exchange: the rank's rows are swept in a few chunks; each finished chunk goes to every
+                    # peer's Znext with one peer-to-peer cudaMemcpyAsync per peer on copy streams -- NVLink at line rate,
+                    # no SM involved -- while the next chunk is being swept.  (From 4 ranks on, per-lane peer stores from
+                    # inside the sweep kernel cannot keep up: 7 x 122 MB per sweep at products shape on 8 GPUs.)
+                    self._setup_copy_engine_exchange(npad, ld)
+                    return "ce"
                 _lib.check(L.clane_plan_set_peers(self.plan.handle, self.world, self.rank, ptrs[0], ptrs[1]),
                            "clane_plan_set_peers")
-                self.Z, self.symm = bufs, hdls
                 mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in hdls]
                 # opt-in: measured at products shape on 4 GPUs, one multimem.st per row piece (1.82 ms row kernel) is
                 # slower than three unicast stores (1.60 ms) -- every rank ingests the same bytes either way
@@ -177,11 +191,53 @@ class ShardedSweeper:
                     return "multicast"
                 return "p2p"
             except Exception as exc:       # no VMM / fabric handles on this box: fall back to NCCL
-                if exchange == "p2p":
+                if exchange in ("p2p", "ce"):
                     raise
                 self.symm_error = repr(exc)
+                self.chunks = []
         self.Z = [self.X.clone(), self.X.clone()]
         return "nccl" if self.world > 1 else "none"
+
+    def _setup_copy_engine_exchange(self, npad: int, ld: int, n_chunks: int = 0) -> None:
+        n_chunks = n_chunks or int(os.environ.get("CLANE_CE_CHUNKS", "4"))
+        rows = self.hi - self.lo
+        step = max(ROW_ALIGN, -(-rows // n_chunks) // ROW_ALIGN * ROW_ALIGN)
+        if step * n_chunks < rows:
+            step += ROW_ALIGN
+        lo = self.lo
+        while lo < self.hi:
+            hi = min(lo + step, self.hi)
+            self.chunks.append((_lib.Plan(self.n, self.e, self.d, self.g._rowptr, lo, hi, 0), lo, hi))
+            lo = hi
+        # views of every peer's two Z buffers (peer-mapped symmetric memory) and a few copy streams
+        self.peer_Z = [[h.get_buffer(r, (npad, ld), torch.float32) for r in range(self.world)] for h in self.symm]
+        self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(min(self.world - 1, 4))]
+
+    def _sweep_chunks(self, zc: torch.Tensor, zn: torch.Tensor, which: int) -> int:
+        """The rank's rows chunk by chunk; chunk k travels to the peers while chunk k + 1 is swept."""
+        L = _lib.lib()
+        cur = torch.cuda.current_stream()
+        s = cur.cuda_stream
+        launches = 0
+        for plan, lo, hi in self.chunks:
+            _lib.check(L.clane_sweep(plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
+                                     self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
+                       "clane_sweep")
+            launches += plan.launches_per_sweep - 2
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            j = 0
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                cs = self.copy_streams[j % len(self.copy_streams)]
+                j += 1
+                cs.wait_event(ev)
+                with torch.cuda.stream(cs):
+                    self.peer_Z[which][r][lo:hi].copy_(zn[lo:hi], non_blocking=True)
+        for cs in self.copy_streams:     # the sweep is over when its rows have been handed to every peer's copy engine queue
+            cur.wait_stream(cs)
+        return launches
 
     def build_p(self) -> None:
         """Graph.build_P for this rank's rows: dots of the own edges, the two global norms reduced by level-1 node
@@ -224,18 +280,21 @@ class ShardedSweeper:
                 marks.append((name, ev))
 
         mark("start")
-        _lib.check(L.clane_sweep(self.plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
-                                 self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
-                   "clane_sweep")
+        if self.chunks:
+            launches = self._sweep_chunks(zc, zn, self.cur ^ 1)
+        else:
+            _lib.check(L.clane_sweep(self.plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
+                                     self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
+                       "clane_sweep")
+            launches = self.plan.launches_per_sweep - 2  # a rank's plan is never fused: no fix-up kernel; L1 counted below
         mark("sweep")
-        launches = self.plan.launches_per_sweep - 2      # a rank's plan is never fused: no fix-up kernel; L1 counted below
         if self.exchange == "nccl":
             lo = self.rank * self.per
             gather_rows(zn[lo:lo + self.per], zn)
             mark("all_gather")
         vals = self.p1[(self.n1 + 2) * 32:]
         if with_l1:
-            if self.exchange in ("p2p", "multicast") and not self.aligned:
+            if self.exchange in ("p2p", "multicast", "ce") and not self.aligned:
                 dist.all_reduce(self.sync_token)       # every rank's rows have landed before the full-array pass
             self.p1.zero_()
             _lib.check(L.clane_l1_partial(self.plan.handle, zn.data_ptr(), zc.data_ptr(), self.nlo, self.nhi,
@@ -251,7 +310,7 @@ class ShardedSweeper:
                                                 self.amount.data_ptr(), 0, 0, 0, s), "clane_l1_finish_values")
             mark("finish")
             launches += 3
-        elif self.exchange in ("p2p", "multicast"):
+        elif self.exchange in ("p2p", "multicast", "ce"):
             dist.all_reduce(self.sync_token)           # order the ranks between sweeps
         self.cur ^= 1
         if marks is not None:
@@ -307,3 +366,7 @@ class ShardedSweeper:
 
     def Z_host(self) -> torch.Tensor:
         return self.Z[self.cur][:self.n, :self.d].cpu()
+
+    def Z_host_slice(self) -> torch.Tensor:
+        """This rank's rows of the current embeddings on the host (the ranks' slices together are Z)."""
+        return self.Z[self.cur][self.lo:self.hi, :self.d].cpu()
