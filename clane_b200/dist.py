@@ -174,11 +174,12 @@ class ShardedSweeper:
                 torch.cuda.synchronize()
                 dist.barrier()
                 self.Z, self.symm = bufs, hdls
-                if exchange == "ce" or (exchange == "auto" and self.world > 2):
-                    # Copy-engine exchange: the rank's rows are swept in a few chunks; each finished chunk goes to every
-                    # peer's Znext with one peer-to-peer cudaMemcpyAsync per peer on copy streams -- NVLink at line rate,
-                    # no SM involved -- while the next chunk is being swept.  (From 4 ranks on, per-lane peer stores from
-                    # inside the sweep kernel cannot keep up: 7 x 122 MB per sweep at products shape on 8 GPUs.)
+                if exchange == "ce":
+                    # Copy-engine exchange (opt-in): the rank's rows are swept in a few chunks; each finished chunk goes
+                    # to every peer's Znext with one peer-to-peer cudaMemcpyAsync per peer on copy streams while the next
+                    # chunk is swept.  Measured at products shape: SLOWER than the stores from inside the sweep kernel --
+                    # 3.21 vs 2.90 ms per sweep on 2 GPUs, 2.84 vs 1.85 ms on 8 (28 copies of 30 MB per sweep reach
+                    # ~390 GB/s per rank; the in-kernel stores ~500 GB/s) -- so "auto" keeps the fused exchange.
                     self._setup_copy_engine_exchange(npad, ld)
                     return "ce"
                 _lib.check(L.clane_plan_set_peers(self.plan.handle, self.world, self.rank, ptrs[0], ptrs[1]),
