@@ -242,12 +242,14 @@ class Embedder(object):
 
 
 class IterativeEmbedder(Embedder):
-    """Placeholder for the reference's IterativeEmbedder (embedder.py:158-289), which cannot be
-    constructed upstream (its __init__ omits the required ``device``).
-    Out of scope for the hot path; the name exists so ``from clane.embedder import
-    IterativeEmbedder`` (reference __main__.py:12) keeps importing."""
+    """Named placeholder for the reference's IterativeEmbedder (embedder.py:158-289) -- a spec decision, see DESIGN.md
+    section 7.  Upstream the class cannot be constructed (its __init__ omits the required ``device``: TypeError;
+    the reference's own asymmetric CLI test errors), reads an undefined ``self.tolerence`` and calls an undefined
+    ``self.update_embeddings``: there is no behaviour a parity test could pin, so any working version would be a
+    new algorithm.  The name exists so that ``from clane.embedder import IterativeEmbedder`` (reference
+    __main__.py:12) keeps importing and the trainable-plugin branch of the CLI fails loudly."""
 
     def __init__(self, *args, **kwargs):
         raise NotImplementedError(
-            "IterativeEmbedder is dead code in the reference (TypeError at construction) and is "
-            "outside the B200 hot path; use Embedder with a non-trainable similarity.")
+            "IterativeEmbedder is dead code in the reference (TypeError at construction, undefined attributes past it) "
+            "and is deliberately not implemented (DESIGN.md section 7); use Embedder with a non-trainable similarity.")

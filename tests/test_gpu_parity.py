@@ -442,6 +442,88 @@ def test_adjacent_hub_rows_across_build_p_calls(monkeypatch):
     assert np.array_equal(g.Z.numpy(), Zo)
 
 
+def test_sweeps_batches_equal_single_sweeps():
+    """clane_sweeps (three rotating buffers, L1 tail of a sweep beside the next sweep's rows, at most one speculative sweep
+    after the stop) against one clane_sweep call per sweep: same amounts, same count, same Z -- for a run that stops in
+    the middle of a batch, for a bounded run, and through the conditional-WHILE launch."""
+    L = _lib.lib()
+    rng = np.random.default_rng(31)
+    for n, d, tol in [(4000, 128, 2), (3000, 100, 1), (900, 500, 2)]:
+        src, dst = synth.make_edges(n, n * 5, "powerlaw", rng)
+        src = np.concatenate([src, np.full(400, 11)])           # one hub row
+        dst = np.concatenate([dst, rng.permutation(n)[:400]])
+        X = rng.standard_normal((n, d), dtype=np.float32)
+        rowptr, col = O.csr_from_edges(src, dst, n)
+        Zo, amounts, _ = O.propagate(X, X, rowptr, col, 0.76, tol)
+        for mode in ("while", "batches", "bounded"):
+            g = Graph.from_arrays(n, src, dst, X)
+            S = g._device_state()
+            g._build_P_device(similarity.CosineSimilarity())
+            sh = S.stream.cuda_stream
+            S.stream.wait_stream(torch.cuda.current_stream())
+            cap = 5 if mode == "bounded" else 0
+            _lib.check(L.clane_patience_reset(S.state.data_ptr(), tol, cap, sh))
+            args = (S.plan.handle, S.X.data_ptr(), S.Zptrs, 1, S.rowptr.data_ptr(), S.col.data_ptr(), S.w.data_ptr(),
+                    ctypes.c_float(float(np.float32(0.76))))
+            S.Z[1].copy_(S.Z[0])
+            if mode == "while":
+                rc = L.clane_sweeps(*args, 0, 1, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, sh)
+                assert rc in (0, _lib.CLANE_EUNSUPPORTED)
+                if rc != 0:
+                    continue
+            else:
+                for _ in range(-(-(len(amounts) + 2) // 7)):    # batches of 7: the rotation does not close, stops mid-batch
+                    start = (1 + 7 * _) % 3
+                    a2 = args[:3] + (start,) + args[4:]
+                    _lib.check(L.clane_sweeps(*a2, 7, 0, S.state.data_ptr(), S.log.data_ptr(), S.log_cap, sh))
+            S.stream.synchronize()
+            st = _lib.Patience.from_buffer_copy(S.state.cpu().numpy().tobytes())
+            want = 5 if mode == "bounded" else len(amounts)
+            assert st.stop == 1 and st.sweeps == want, (mode, st.sweeps, want)
+            assert np.array_equal(S.log[:want].cpu().numpy(), amounts[:want])
+            if mode != "bounded":
+                assert np.array_equal(S.Z[(1 + want) % 3][:n, :d].cpu().numpy(), Zo)
+
+
+def test_norms_reduced_by_node_range_equal_whole():
+    """clane_norms_partial over disjoint node ranges + a sum of the slots + clane_norms_finish == the norms of
+    clane_scores_cosine (the multi-GPU build_P), and the plan's softmax == the row-range softmax."""
+    L = _lib.lib()
+    rng = np.random.default_rng(41)
+    for n, d in [(5000, 128), (3000, 100), (200, 1433), (50, 3)]:
+        src, dst = synth.make_edges(n, n * (6 if n >= 1000 else 2), "powerlaw" if n >= 1000 else "uniform", rng)
+        X = rng.standard_normal((n, d), dtype=np.float32)
+        g = Graph.from_arrays(n, src, dst, X)
+        S = g._device_state()
+        s = _lib.stream_handle()
+        z = S.Z[0].data_ptr()
+        dots = torch.zeros(S.e, device="cuda")
+        norms = torch.zeros(2, device="cuda")
+        _lib.check(L.clane_scores_cosine(S.plan.handle, z, S.erow.data_ptr(), S.col.data_ptr(), 0, S.e, dots.data_ptr(),
+                                         norms.data_ptr(), s))
+        nodes = ctypes.c_int64()
+        _lib.check(L.clane_cascade_shape(S.e * d, ctypes.byref(nodes), None))
+        k = nodes.value
+        parts = []
+        for lo, hi in [(0, k // 3), (k // 3, k // 3), (k // 3, k)]:
+            p1 = torch.zeros((k + 2) * 64, device="cuda")
+            _lib.check(L.clane_norms_partial(S.plan.handle, z, S.erow.data_ptr(), S.col.data_ptr(), lo, hi, p1.data_ptr(), s))
+            parts.append(p1)
+        total = torch.stack(parts).sum(0)
+        norms2 = torch.zeros(2, device="cuda")
+        _lib.check(L.clane_norms_finish(S.plan.handle, z, S.erow.data_ptr(), S.col.data_ptr(), total.data_ptr(),
+                                        norms2.data_ptr(), s))
+        assert np.array_equal(norms2.cpu().numpy(), norms.cpu().numpy())
+        rowptr, col = O.csr_from_edges(src, dst, n)
+        od, s1, s2 = O.scores_raw(X, rowptr, col)
+        assert np.array_equal(dots.cpu().numpy(), od) and norms.cpu().numpy().tolist() == [s1, s2]
+        w1, w2 = torch.zeros_like(dots), torch.zeros_like(dots)
+        _lib.check(L.clane_plan_softmax(S.plan.handle, dots.data_ptr(), norms.data_ptr(), S.rowptr.data_ptr(), w1.data_ptr(), s))
+        _lib.check(L.clane_row_softmax(dots.data_ptr(), norms.data_ptr(), 0, n, S.rowptr.data_ptr(), w2.data_ptr(), s))
+        assert np.array_equal(w1.cpu().numpy(), w2.cpu().numpy())
+        assert np.array_equal(w1.cpu().numpy(), O.build_p(X, rowptr, col))
+
+
 def test_peer_stores_and_value_finish_single_gpu():
     """The fused exchange on one GPU: a plan over half of the rows, with a second local buffer registered as the
     'peer' -- after the sweep the peer holds exactly the swept rows (ordinary, paired, hub), nothing else; and the
