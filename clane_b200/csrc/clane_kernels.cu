@@ -52,8 +52,8 @@ template <bool kFma> __host__ __device__ constexpr size_t dot_smem() { return (s
 
 template <bool kFma>
 __global__ void __launch_bounds__(32 * dot_warps<kFma>())
-k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ erow, const int32_t* __restrict__ col,
-       int64_t e_lo, int64_t e_hi, float* __restrict__ dots) {
+k_dots(const float* __restrict__ Za, const float* __restrict__ Zb, int ld, int d, const int32_t* __restrict__ erow,
+       const int32_t* __restrict__ col, int64_t e_lo, int64_t e_hi, float* __restrict__ dots) {   // <Za[erow[e]], Zb[col[e]]>
     extern __shared__ __align__(16) float dot_tile[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* ta = dot_tile + (size_t)warp * 32 * kDotPitch * (kFma ? 2 : 1);
@@ -68,7 +68,8 @@ k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ e
         for (int c0 = 0; c0 < d; c0 += kDotCols) {
             const int c = c0 + 4 * lane;
             const bool in = c < ld;                      // rows are padded to a multiple of 4 floats: whole float4s are readable
-            const float4* zc = reinterpret_cast<const float4*>(Z) + (in ? c >> 2 : 0);
+            const float4* zc = reinterpret_cast<const float4*>(Za) + (in ? c >> 2 : 0);
+            const float4* zd = reinterpret_cast<const float4*>(Zb) + (in ? c >> 2 : 0);
             // ---- phase A: 8 edges per round, 16 independent 128-bit loads in flight ----
             // (consecutive edges mostly share their source row -- CSR order: its piece is loaded once per run)
             int prev = -1;
@@ -80,7 +81,7 @@ k_dots(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ e
                 for (int u = 0; u < 8; ++u) {
                     oa[u] = __shfl_sync(kFull, ra, (i + u) & 31);
                     const int ob = __shfl_sync(kFull, rb, (i + u) & 31);
-                    y[u] = __ldg(zc + ob);
+                    y[u] = __ldg(zd + ob);
                     if (oa[u] != (u == 0 ? prev : oa[u - 1])) x[u] = __ldg(zc + oa[u]);     // uniform branch
                 }
 #pragma unroll
@@ -382,10 +383,10 @@ int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ero
         const int64_t ntiles = (edge_hi - edge_lo + 31) / 32;
         if (plan->d < 400) {
             const unsigned grid = (unsigned)std::min<int64_t>((ntiles + dot_warps<false>() - 1) / dot_warps<false>(), 148 * 24);
-            k_dots<false><<<grid, 32 * dot_warps<false>(), dot_smem<false>(), st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+            k_dots<false><<<grid, 32 * dot_warps<false>(), dot_smem<false>(), st>>>(d_Z, d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
         } else {
             const unsigned grid = (unsigned)std::min<int64_t>((ntiles + dot_warps<true>() - 1) / dot_warps<true>(), 148 * 24);
-            k_dots<true><<<grid, 32 * dot_warps<true>(), dot_smem<true>(), st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
+            k_dots<true><<<grid, 32 * dot_warps<true>(), dot_smem<true>(), st>>>(d_Z, d_Z, plan->ld, plan->d, d_erow, d_col, edge_lo, edge_hi, d_dots);
         }
         CLANE_LAUNCH_CHECK();
     }
@@ -438,6 +439,26 @@ int clane_plan_softmax(clane_plan* plan, const float* d_scores, const float* d_n
         CLANE_LAUNCH_CHECK();
     }
     return CLANE_OK;
+}
+
+int clane_build_p_asym(clane_plan* plan, const float* d_Z, const float* d_W, const int32_t* d_rowptr, const int32_t* d_erow,
+                       const int32_t* d_col, float* d_w, float* d_work, int32_t* d_error, clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_Z || !d_W || !d_rowptr || !d_w || !d_work || !d_error) return CLANE_EINVAL;
+    if (plan->e > 0 && (!d_erow || !d_col)) return CLANE_EINVAL;
+    float* psrc = d_work;
+    float* pdst = d_work + (size_t)plan->n * plan->ld;
+    // every node projected once on the tensor cores: [P_src | P_dst] = Z [W_src ; W_dst]^T
+    int rc = clane_asym_project(d_Z, plan->n, plan->d, plan->ld, d_W, psrc, pdst, d_error, s);
+    if (rc != CLANE_OK) return rc;
+    const int64_t e_lo = plan->edge_lo, e_hi = plan->edge_hi;
+    if (e_hi > e_lo) {
+        const int64_t ntiles = (e_hi - e_lo + 31) / 32;
+        const unsigned grid = (unsigned)std::min<int64_t>((ntiles + dot_warps<false>() - 1) / dot_warps<false>(), 148 * 24);
+        k_dots<false><<<grid, 32 * dot_warps<false>(), dot_smem<false>(), (cudaStream_t)s>>>(psrc, pdst, plan->ld, plan->d, d_erow, d_col,
+                                                                                      e_lo, e_hi, d_w);
+        CLANE_LAUNCH_CHECK();
+    }
+    return clane_plan_softmax(plan, d_w, nullptr, d_rowptr, d_w, s);     // graph.py:122-123: no norm divisor for this plugin
 }
 
 int clane_cosine_finalize(const float* d_dots, const float* d_norms2, int64_t e, float* d_out, clane_stream_t s) {

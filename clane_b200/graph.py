@@ -307,6 +307,17 @@ class Graph(Dataset):
             _lib.check(L.clane_build_p_cosine(S.plan.handle, Zc.data_ptr(), S.rowptr.data_ptr(), S.erow.data_ptr(),
                                               S.col.data_ptr(), S.w.data_ptr(), S.norms2.data_ptr(), stream),
                        "clane_build_p_cosine")
+        elif getattr(similarity, "_clane_kernel", None) == "asym" and L.clane_asym_supported(S.d) and S.e > 0:
+            # trainable bilinear scorer: every node projected once on the tensor cores, then per-edge dots + row softmax
+            if getattr(S, "asym_work", None) is None:
+                S.asym_work = torch.empty(2 * S.n * S.ld, dtype=torch.float32, device=S.device)
+                S.asym_error = torch.zeros(1, dtype=torch.int32, device=S.device)
+            W = similarity.stacked_weights(S.device)
+            _lib.check(L.clane_build_p_asym(S.plan.handle, Zc.data_ptr(), W.data_ptr(), S.rowptr.data_ptr(), S.erow.data_ptr(),
+                                            S.col.data_ptr(), S.w.data_ptr(), S.asym_work.data_ptr(), S.asym_error.data_ptr(),
+                                            stream), "clane_build_p_asym")
+            if int(S.asym_error.item()):          # synchronises: W must outlive the launch anyway
+                raise _lib.ClaneError("clane_build_p_asym: the projection kernel timed out waiting for its TMA copies")
         else:
             # user plugin: honour its scores, still on the device; the softmax stays fused
             Zv = Zc[:S.n, :S.d]

@@ -82,16 +82,29 @@ class CosineSimilarity(Similarity):
 
 
 class AsymmertricSimilarity(nn.Module, Similarity):
-    """Trainable bilinear score (similarity.py:40-57).  Only reachable through the reference's
-    IterativeEmbedder, which is broken upstream: kept as a plain torch module
-    so the registry stays complete; it runs on whatever device its inputs are on."""
+    """Trainable bilinear score ``<Phi_src z_src, Phi_dst z_dst>`` (similarity.py:40-57; the spelling is API).
+
+    ``Phi_src`` / ``Phi_dst`` are bias-free ``nn.Linear(n_dim, n_dim)`` layers with Xavier-normal weights, as upstream
+    (checkpoints and optimisers address them by these names).  A direct call scores pairs with torch on whatever device
+    the inputs live on.  ``Graph.build_P`` does not gather ``[E, d]`` rows for it: it hands the two weight matrices to
+    ``clane_build_p_asym``, which projects every NODE once on the tensor cores (tcgen05 tf32 GEMM, TMA-staged), takes the
+    per-edge dots of the projected rows and applies the row softmax -- for ``n_dim`` in {32, 64, 96, 128}; other widths go
+    through the generic plugin path.  The tensor-core inputs are TF32: scores agree with the fp32 module to ~1e-3 relative
+    (stated in tests/test_gpu_parity.py::test_asymmetric_scorer_fused_build_p)."""
+
+    _clane_kernel = "asym"
 
     def __init__(self, n_dim: int, **kwargs) -> None:
-        super(AsymmertricSimilarity, self).__init__()
-        self.Phi_src = nn.Linear(n_dim, n_dim, bias=False)
-        self.Phi_dst = nn.Linear(n_dim, n_dim, bias=False)
-        nn.init.xavier_normal_(self.Phi_src.weight)
-        nn.init.xavier_normal_(self.Phi_dst.weight)
+        super().__init__()
+        for name in ("Phi_src", "Phi_dst"):
+            layer = nn.Linear(n_dim, n_dim, bias=False)
+            nn.init.xavier_normal_(layer.weight)
+            setattr(self, name, layer)
+
+    def stacked_weights(self, device) -> torch.Tensor:
+        """``[W_src ; W_dst]`` as one contiguous fp32 ``[2 n_dim, n_dim]`` matrix on ``device`` (the B operand of the GEMM)."""
+        return torch.cat([self.Phi_src.weight, self.Phi_dst.weight]).detach().to(device=device, dtype=torch.float32).contiguous()
 
     def forward(self, z_src: torch.Tensor, z_dst: torch.Tensor) -> torch.Tensor:
-        return self.Phi_src(z_src).unsqueeze(-2).matmul(self.Phi_dst(z_dst).unsqueeze(-1)).squeeze()
+        projected_src, projected_dst = self.Phi_src(z_src), self.Phi_dst(z_dst)
+        return (projected_src.unsqueeze(-2) @ projected_dst.unsqueeze(-1)).squeeze()

@@ -181,6 +181,19 @@ int clane_row_softmax(const float* d_scores, const float* d_norms2, int32_t row_
 int clane_plan_softmax(clane_plan* plan, const float* d_scores, const float* d_norms2, const int32_t* d_rowptr, float* d_w,
                        clane_stream_t s);
 
+/* AsymmertricSimilarity (/root/reference/clane/similarity.py:40-57): score(v -> u) = <Phi_src z_v, Phi_dst z_u>.
+ * clane_asym_project: every node projected once, [P_src | P_dst] = Z [n, d] x [W_src ; W_dst]^T, d_W = the two nn.Linear
+ * weights stacked ([2d, d] row-major, contiguous), on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM,
+ * TMA-staged operands); d in {32, 64, 96, 128} (clane_asym_supported), CLANE_EUNSUPPORTED otherwise -- the caller then
+ * runs the plugin itself.  d_Psrc / d_Pdst: [n, ld]; *d_error is set to 1 if the kernel gave up waiting for its copies.
+ * clane_build_p_asym: Graph.build_P with that scorer for the plan's rows -- projection, per-edge dots of the projected
+ * rows, row softmax (no norm divisor); d_work: 2 * n * ld floats. */
+int clane_asym_supported(int32_t d);
+int clane_asym_project(const float* d_Z, int32_t n, int32_t d, int32_t ld, const float* d_W, float* d_Psrc, float* d_Pdst,
+                       int32_t* d_error, clane_stream_t s);
+int clane_build_p_asym(clane_plan* plan, const float* d_Z, const float* d_W, const int32_t* d_rowptr, const int32_t* d_erow,
+                       const int32_t* d_col, float* d_w, float* d_work, int32_t* d_error, clane_stream_t s);
+
 /* The final division of CosineSimilarity.__call__ (similarity.py:37) for standalone plugin
  * calls: d_out[i] = d_dots[i] / fl(fl(sqrt(norms2[0])) * fl(sqrt(norms2[1]))).  May alias. */
 int clane_cosine_finalize(const float* d_dots, const float* d_norms2, int64_t e, float* d_out, clane_stream_t s);

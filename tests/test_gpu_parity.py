@@ -524,6 +524,48 @@ def test_norms_reduced_by_node_range_equal_whole():
         assert np.array_equal(w1.cpu().numpy(), O.build_p(X, rowptr, col))
 
 
+@pytest.mark.parametrize("n,d", [(1000, 128), (300, 64), (4097, 32), (777, 96)])
+def test_asymmetric_scorer_fused_build_p(n, d):
+    """AsymmertricSimilarity through Graph.build_P: the tcgen05 projection + per-edge dots + row softmax against the
+    fp32 torch module on gathered rows (what the reference's build_P would do with this plugin, graph.py:120-123).
+    Tolerance: the tensor cores read TF32 inputs (10-bit mantissa) and accumulate in fp32 -- projected values within
+    2e-3 of the row scale, scores within 1e-2 * |z|^2-scale, weights of P within 2e-3 absolute."""
+    L = _lib.lib()
+    torch.manual_seed(d)
+    rng = np.random.default_rng(n + d)
+    src, dst = synth.make_edges(n, n * 5, "powerlaw", rng)
+    X = (rng.standard_normal((n, d)) * 0.5).astype(np.float32)
+    g = Graph.from_arrays(n, src, dst, X)
+    sim = similarity.AsymmertricSimilarity(n_dim=d)
+    assert sim.is_trainable() and hasattr(sim, "parameters")
+    # the projection alone, against fp32 matmul
+    S = g._device_state()
+    W = sim.stacked_weights(S.device)
+    work = torch.zeros(2 * n * S.ld, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.clane_asym_project(S.Z[0].data_ptr(), n, d, S.ld, W.data_ptr(), work.data_ptr(), work[n * S.ld:].data_ptr(),
+                                    err.data_ptr(), _lib.stream_handle()))
+    assert int(err.item()) == 0
+    P = work.view(2, n, S.ld)[:, :, :d].cpu().numpy()
+    Xt = torch.from_numpy(X)
+    want_src = (Xt @ sim.Phi_src.weight.detach().T).numpy()
+    want_dst = (Xt @ sim.Phi_dst.weight.detach().T).numpy()
+    scale = np.abs(want_src).max()
+    assert np.abs(P[0] - want_src).max() <= 2e-3 * scale and np.abs(P[1] - want_dst).max() <= 2e-3 * scale
+    # the whole build_P
+    Pm = g.build_P(sim)
+    rows, cols = g._coo_indices()
+    with torch.no_grad():
+        scores = sim(Xt[rows], Xt[cols]).numpy().astype(np.float32)
+    want = O.softmax_rows(scores, g._rowptr.astype(np.int64))
+    got = Pm.values().numpy()
+    assert np.abs(got - want).max() <= 2e-3
+    rs = Pm.to_dense().sum(1)
+    assert abs(rs.max().item() - 1) < 1e-3
+    # other widths fall back to the generic plugin path (scores by the module itself, softmax in CUDA)
+    assert L.clane_asym_supported(100) == 0 and L.clane_asym_supported(128) == 1
+
+
 def test_peer_stores_and_value_finish_single_gpu():
     """The fused exchange on one GPU: a plan over half of the rows, with a second local buffer registered as the
     'peer' -- after the sweep the peer holds exactly the swept rows (ordinary, paired, hub), nothing else; and the
