@@ -379,6 +379,22 @@ int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ero
     if (!plan || !d_Z || !d_erow || !d_col || !d_dots) return CLANE_EINVAL;
     if (edge_lo < 0 || edge_hi > plan->e || edge_lo > edge_hi) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
+    // the dots and the norm cascade are independent and both latency-bound at partial occupancy: with a schedule plan (it
+    // owns side streams) the dots run on a side stream beside the cascade on the caller's
+    cudaStream_t caller = st;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool beside = d_norms2 != nullptr && plan->side != nullptr && edge_hi > edge_lo;
+    if (beside) {
+        while (plan->evs.size() < 2) {
+            cudaEvent_t ev = nullptr;
+            CLANE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            plan->evs.push_back(ev);
+        }
+        ev_fork = plan->evs[0]; ev_join = plan->evs[1];
+        CLANE_CUDA(cudaEventRecord(ev_fork, caller));
+        CLANE_CUDA(cudaStreamWaitEvent(plan->side, ev_fork, 0));
+        st = plan->side;
+    }
     if (edge_hi > edge_lo) {
         const int64_t ntiles = (edge_hi - edge_lo + 31) / 32;
         if (plan->d < 400) {
@@ -391,8 +407,11 @@ int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ero
         CLANE_LAUNCH_CHECK();
     }
     if (!d_norms2) return CLANE_OK;       // dots only: a rank of a row-partitioned run reduces the norms by node range
+    if (beside) CLANE_CUDA(cudaEventRecord(ev_join, plan->side));
     ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld, plan->e};
-    return cascade_launch(el, plan->e * (int64_t)plan->d, plan->d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, st);
+    int rc = cascade_launch(el, plan->e * (int64_t)plan->d, plan->d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, caller);
+    if (beside) CLANE_CUDA(cudaStreamWaitEvent(caller, ev_join, 0));
+    return rc;
 }
 
 int clane_norms_partial(clane_plan* plan, const float* d_Z, const int32_t* d_erow, const int32_t* d_col, int64_t node_lo,
@@ -430,14 +449,27 @@ int clane_plan_softmax(clane_plan* plan, const float* d_scores, const float* d_n
     if (!plan || !plan->has_schedule || !d_scores || !d_rowptr || !d_w) return CLANE_EINVAL;
     const int32_t rows = plan->row_hi - plan->row_lo;
     if (rows <= 0) return CLANE_OK;
-    k_row_softmax_short<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)s>>>(d_scores, d_norms2, plan->row_lo, plan->row_hi,
-                                                                                   d_rowptr, d_w);
-    CLANE_LAUNCH_CHECK();
-    if (plan->n_long_rows > 0) {
-        k_row_softmax_long<<<(unsigned)plan->n_long_rows, kSoftmaxLongThreads, 0, (cudaStream_t)s>>>(d_scores, d_norms2, plan->d_long_rows,
-                                                                                                 plan->row_lo, d_rowptr, d_w);
-        CLANE_LAUNCH_CHECK();
+    // the two kernels own disjoint rows: the long rows go beside the short ones on the plan's side stream
+    cudaStream_t st = (cudaStream_t)s;
+    const bool beside = plan->n_long_rows > 0 && plan->side != nullptr;
+    if (beside) {
+        while (plan->evs.size() < 2) {
+            cudaEvent_t ev = nullptr;
+            CLANE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            plan->evs.push_back(ev);
+        }
+        CLANE_CUDA(cudaEventRecord(plan->evs[0], st));
+        CLANE_CUDA(cudaStreamWaitEvent(plan->side, plan->evs[0], 0));
     }
+    if (plan->n_long_rows > 0) {
+        k_row_softmax_long<<<(unsigned)plan->n_long_rows, kSoftmaxLongThreads, 0, beside ? plan->side : st>>>(
+            d_scores, d_norms2, plan->d_long_rows, plan->row_lo, d_rowptr, d_w);
+        CLANE_LAUNCH_CHECK();
+        if (beside) CLANE_CUDA(cudaEventRecord(plan->evs[1], plan->side));
+    }
+    k_row_softmax_short<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(d_scores, d_norms2, plan->row_lo, plan->row_hi, d_rowptr, d_w);
+    CLANE_LAUNCH_CHECK();
+    if (beside) CLANE_CUDA(cudaStreamWaitEvent(st, plan->evs[1], 0));
     return CLANE_OK;
 }
 
