@@ -302,14 +302,22 @@ namespace {
 
 // kernel launch with an explicit priority: the attribute stays on the kernel node when the launch is captured into a
 // graph (a captured node does not reliably inherit the priority of the stream it was captured from)
+// measurement aid (CLANE_L2_WINDOW): an L2 access-policy window the next launch carries
+thread_local const cudaAccessPolicyWindow* tl_window = nullptr;
 template <class... KArgs, class... Args>
 cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributePriority;
     attr[0].val.priority = prio;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (tl_window != nullptr) {
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow = *tl_window;
+        cfg.numAttrs = 2;
+        tl_window = nullptr;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -607,6 +615,7 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
         p.st = a.state;
         p.n_remote = 0;
         p.mc = nullptr;
+        p.bulk = 0;
         p.trace = nullptr;
         unsigned long long* tr = (plan->d_trace != nullptr && t < kTraceSweeps) ? plan->d_trace + (size_t)t * kTraceSlots * 2 : nullptr;
         for (int q = 0; q < 2 && plan->n_peers > 1 && !no_peer_stores; ++q)
@@ -615,6 +624,9 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
                 for (int r = 0; r < plan->n_peers; ++r)
                     if (r != plan->self_rank) p.peer[p.n_remote++] = plan->peers[q][r];
             }
+        // whole rows per warp and unicast peers: the spans' rows leave as bulk stores (sweep.cuh, flush_rows)
+        static const char* bulk_env = getenv("CLANE_PEER_BULK");         // 0: lane stores (measurement aid)
+        if (p.n_remote > 0 && plan->nslab == 1 && plan->G <= kStageRows && !(bulk_env && atoi(bulk_env) == 0)) p.bulk = 1;
         // what the previous sweeps must have finished before this one may start
         cudaEvent_t prev_tail = nullptr;       // the tail whose inputs this sweep overwrites / whose flag it reads
         if (nz >= 3) { if (t >= 2) prev_tail = eL[t - 2]; }
@@ -627,8 +639,9 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             if (prev_tail) CLANE_CUDA(cudaStreamWaitEvent(plan->side, prev_tail, 0));
             SweepParams ps = p;
             ps.n_tasks = plan->n_seg_tasks;
+            ps.bulk = 0;
             ps.trace = tr;
-            CLANE_CUDA(launch_prio(k_sweep_rows, dim3((unsigned)seg_ctas), dim3(kRowThreads), 0, plan->side, plan->prio_hi, ps));
+            CLANE_CUDA(launch_prio(k_sweep_rows<false>, dim3((unsigned)seg_ctas), dim3(kRowThreads), 0, plan->side, plan->prio_hi, ps));
             cudaEvent_t eS = nullptr;
             CLANE_CUDA(mark(&eS, plan->side));
             eS_cur = eS;
@@ -667,7 +680,31 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             SweepParams pr = p;
             pr.task_lo = plan->n_seg_tasks;
             pr.trace = tr ? tr + 6 : nullptr;
-            CLANE_CUDA(launch_prio(k_sweep_rows, dim3((unsigned)span_ctas), dim3(kRowThreads), 0, st, plan->prio_lo, pr));
+            static const char* win_env = getenv("CLANE_L2_WINDOW");     // hit ratio of a persisting window over Zcur
+            cudaAccessPolicyWindow win = {};
+            if (win_env && atof(win_env) > 0.0) {
+                static bool limit_set = false;
+                int dev = 0, max_persist = 0, max_win = 0;
+                CLANE_CUDA(cudaGetDevice(&dev));
+                CLANE_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+                CLANE_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+                if (!limit_set) {
+                    CLANE_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+                    fprintf(stderr, "clane: L2 window: max persisting %d MB, max window %d MB\n", max_persist >> 20, max_win >> 20);
+                    limit_set = true;
+                }
+                win.base_ptr = const_cast<float*>(Zc);
+                win.num_bytes = std::min<size_t>((size_t)plan->n * plan->ld * 4, (size_t)max_win);
+                win.hitRatio = (float)atof(win_env);
+                win.hitProp = cudaAccessPropertyPersisting;
+                win.missProp = cudaAccessPropertyNormal;
+                tl_window = &win;
+            }
+            if (pr.bulk)
+                CLANE_CUDA(launch_prio(k_sweep_rows<true>, dim3((unsigned)span_ctas), dim3(kRowThreads), kRowWarps * kRowStageBytes, st,
+                                       plan->prio_lo, pr));
+            else
+                CLANE_CUDA(launch_prio(k_sweep_rows<false>, dim3((unsigned)span_ctas), dim3(kRowThreads), 0, st, plan->prio_lo, pr));
         }
         if (prof) CLANE_CUDA(prof_mark(plan, 2, st));
         CLANE_CUDA(mark(&eR[t], st));
@@ -979,7 +1016,7 @@ int clane_internal_prepare_kernels(void) {
     CLANE_CUDA(cudaFuncSetAttribute(k_dots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<false>()));
     CLANE_CUDA(cudaFuncSetAttribute(k_dots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<true>()));
     if (const char* v = getenv("CLANE_ROW_CARVEOUT"))    // timing experiments: shared-memory carveout (percent) of the row kernel
-        CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
+        CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)
     done = true;
     return CLANE_OK;

@@ -72,6 +72,8 @@ struct SweepParams {
     float* peer[kMaxPeers];
     int n_remote;
     float* mc;                  // multicast (NVLS) address of Znext: one store reaches every rank; replaces peer[]
+    int bulk;                   // 1 (k_sweep_rows<true>): a span's finished rows are staged in shared memory and leave as one
+                                //    bulk store per destination (own Znext + every peer) instead of a store per lane, row and peer
     unsigned long long* trace;  // measurement aid (clane_plan_trace): {first CTA start, last CTA end} in ns, or null
 };
 
@@ -286,6 +288,33 @@ __device__ __forceinline__ void block_batch(const int2* __restrict__ mp, const f
 // ------------------------------------------------------------------------------------------
 // row kernel: one warp per (task, 128-column slab)
 // ------------------------------------------------------------------------------------------
+// Row-partitioned runs with whole rows per warp (ld <= 128): the rows of a span are contiguous in every Znext copy, so the
+// warp parks them in shared memory and one lane per destination hands [first row, last row] to the bulk-copy engine.
+// The stores leave the SM as full 128-byte lines (a 400-byte row of the products shape starts on a 16-byte boundary:
+// stored lane by lane, every row ends in partial sectors on NVLink) and cost one instruction per destination and span
+// instead of one per destination and row.
+constexpr int kStageRows = 8;                                   // rows of a span in a partitioned run (G = 8)
+constexpr size_t kRowStageBytes = (size_t)kStageRows * 128 * sizeof(float);   // per warp, dynamic shared memory
+__device__ __forceinline__ void bulk_store(float* dst, const float* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// rows [ra, rb) of the span starting at row r0 are parked at stage + r * ld: lane 0 stores them to Znext, lane j to peer j - 1
+__device__ __forceinline__ void flush_rows(const SweepParams& p, const float* stage, int r0, int ra, int rb, int lane) {
+    fence_async_smem();                        // the lanes' generic-proxy writes, before the async proxy reads them
+    __syncwarp();
+    float* dst = p.Zn;
+#pragma unroll
+    for (int j = 0; j < kMaxPeers; ++j)
+        if (lane == j + 1) dst = p.peer[j];
+    if (lane <= p.n_remote) {
+        bulk_store(dst + (size_t)(r0 + ra) * p.ld, stage + ra * p.ld, (unsigned)((rb - ra) * p.ld) * 4u);
+        bulk_commit();
+    }
+}
 #ifndef CLANE_PF_AHEAD
 #define CLANE_PF_AHEAD 0       // window positions the L2 prefetch of neighbour rows runs ahead of the gathers (0: off)
 #endif
@@ -344,8 +373,9 @@ __device__ __noinline__ void restage_meta(const SweepParams& p, int lane, int2* 
 // would occupy while the gathers are in flight are free: the kernel fits 64 registers = 32 resident warps per SM,
 // each with one batch of loads in flight (tools/l1pf_probe.cu: resident warps beat deeper per-warp pipelines on
 // this access pattern).
+template <bool kBulk>
 __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, int slab, int lane, int2* meta, float* scratch,
-                                         float4* rowbuf, int* state) {
+                                         float4* rowbuf, int* state, float* stage) {
     const int r0 = t0.z, nrows = t0.w & 0xff;
     const bool direct = (t0.w & kTaskDirect) != 0 && p.fuse != 0;
     const int c0 = slab * 128 + lane * 4;
@@ -380,9 +410,13 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, in
     }
     if (CLANE_PF_AHEAD > 0)
         for (; pf < CLANE_PF_AHEAD && pf < wcnt; pf += 8) prefetch_batch(zslab, slab_bytes, meta, pf, wcnt, lane);
+    int run0 = -1;                             // bulk mode: first row of the run of finished rows parked in `stage`
     for (int r = 0; r < nrows; ++r) {
         int k = __shfl_sync(kFull, deg, r);
-        if (k == 0) continue;                  // a sink inside the span: never updated (embedder.py:88-89), |delta| = +0
+        if (k == 0) {                          // a sink inside the span: never updated (embedder.py:88-89), |delta| = +0
+            if (kBulk && run0 >= 0) { flush_rows(p, stage, r0, run0, r, lane); run0 = -1; }
+            continue;
+        }
         {
 #ifdef CLANE_DEBUG_ROW0          // timing experiments only: every row's X / own / Znext piece is row 0's (wrong results)
             const int row_off = cc;
@@ -428,7 +462,10 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, in
 #else
         const int row_off = (r0 + r) * p.ld + cc;
 #endif
-        if (active) {
+        if (kBulk) {
+            if (active) *reinterpret_cast<float4*>(stage + r * p.ld + cc) = out;
+            if (run0 < 0) run0 = r;
+        } else if (active) {
             st_stream4(p.Zn + row_off, out);
             if (p.mc != nullptr) multimem_st4(p.mc + row_off, out);
             for (int j = 0; j < p.n_remote; ++j) *reinterpret_cast<float4*>(p.peer[j] + row_off) = out;
@@ -448,6 +485,10 @@ __device__ __forceinline__ void run_span(const SweepParams& p, const int4 t0, in
     }
     // the span is one whole level-0 chunk: its rows were added in order, skipped rows count +0
     if (direct) p.P0[(size_t)((r0 - p.row_lo) / p.G) * 32 + lane] = chunk_acc;
+    if (kBulk) {
+        if (run0 >= 0) flush_rows(p, stage, r0, run0, nrows, lane);
+        bulk_wait_read();                      // the copy engine has read the parked rows: the CTA may give up its shared memory
+    }
 }
 
 // hub segment task: up to 16 full 8-blocks of one hub row; park {z6, z4, X, Y} per (block, column), or the
@@ -514,8 +555,10 @@ __device__ __forceinline__ void run_segment(const SweepParams& p, const int4 t0,
     }
 }
 
+template <bool kBulk>
 __global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_sweep_rows(SweepParams p) {
     __shared__ __align__(16) unsigned char smem[kRowSmemBytes];
+    extern __shared__ __align__(128) unsigned char stage_smem[];     // kRowWarps * kRowStageBytes when p.bulk, else none
     if (p.st != nullptr && p.st->stop) return;
     trace_begin(p.trace);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -531,7 +574,8 @@ __global__ void __launch_bounds__(kRowThreads, kRowWarpsPerSM / kRowWarps) k_swe
     if (ti < p.n_tasks) {
         const int4 t0 = __ldg(reinterpret_cast<const int4*>(p.tasks + ti));
         if (t0.w & kTaskSegment) run_segment(p, t0, __ldg(reinterpret_cast<const int4*>(p.tasks + ti) + 1), slab, lane, meta);
-        else run_span(p, t0, slab, lane, meta, scratch, rowbuf, state);
+        else run_span<kBulk>(p, t0, slab, lane, meta, scratch, rowbuf, state,
+                      reinterpret_cast<float*>(stage_smem + (size_t)warp * kRowStageBytes));
     }
     if (p.trace != nullptr) { __syncthreads(); trace_end(p.trace); }
 }
