@@ -304,6 +304,19 @@ namespace {
 // graph (a captured node does not reliably inherit the priority of the stream it was captured from)
 // measurement aid (CLANE_L2_WINDOW): an L2 access-policy window the next launch carries
 thread_local const cudaAccessPolicyWindow* tl_window = nullptr;
+// sets the persisting share of the L2 aside once (not allowed while a stream captures: called before); the largest window
+int l2_window_max() {
+    static int max_win = -1;
+    if (max_win < 0) {
+        int dev = 0, max_persist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        fprintf(stderr, "clane: L2 window: max persisting %d MB, max window %d MB\n", max_persist >> 20, max_win >> 20);
+    }
+    return max_win;
+}
 template <class... KArgs, class... Args>
 cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -683,16 +696,7 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
             static const char* win_env = getenv("CLANE_L2_WINDOW");     // hit ratio of a persisting window over Zcur
             cudaAccessPolicyWindow win = {};
             if (win_env && atof(win_env) > 0.0) {
-                static bool limit_set = false;
-                int dev = 0, max_persist = 0, max_win = 0;
-                CLANE_CUDA(cudaGetDevice(&dev));
-                CLANE_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-                CLANE_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-                if (!limit_set) {
-                    CLANE_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
-                    fprintf(stderr, "clane: L2 window: max persisting %d MB, max window %d MB\n", max_persist >> 20, max_win >> 20);
-                    limit_set = true;
-                }
+                int max_win = l2_window_max();
                 win.base_ptr = const_cast<float*>(Zc);
                 win.num_bytes = std::min<size_t>((size_t)plan->n * plan->ld * 4, (size_t)max_win);
                 win.hitRatio = (float)atof(win_env);
@@ -770,6 +774,7 @@ static int launch_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z, 
         return enqueue_sweeps(plan, a, Z, nz, c0, n_sweeps, st);
     }
     const void* key[12] = {a.X, Z[0], Z[1], nz > 2 ? Z[2] : nullptr, a.rowptr, a.col, a.w, a.amount, a.state, a.log, st, nullptr};
+    if (getenv("CLANE_L2_WINDOW")) l2_window_max();
     clane_plan::SweepGraph* slot = nullptr;
     for (auto& g : plan->graphs)
         if (g.exec && g.gamma == a.gamma && g.log_cap == a.log_cap && g.n_sweeps == n_sweeps && g.nz == nz && g.c0 == c0 &&
