@@ -324,8 +324,9 @@ def run_gpu(args):
         L1 + patience tail of every sweep beside the rows of the next one); the patience counter is set so that it
         never stops inside the timed region."""
         if runner is not None:
-            for i in range(k):
-                one_step(i, True)
+            # the sharded counterpart: ShardedSweeper.sweeps (exact L1 of sweep t beside sweep t + 1, three rotating buffers)
+            runner.sweeps(k)
+            launches_per_step[0] = runner.launches_last_sweep or launches_per_step[0]
             return
         _lib.check(L.clane_patience_reset(S.state.data_ptr(), 1 << 30, 0, sh))
         _lib.check(L.clane_sweeps(S.plan.handle, S.X.data_ptr(), S.Zptrs, S.cur, S.rowptr.data_ptr(), S.col.data_ptr(),
@@ -429,9 +430,15 @@ def run_gpu(args):
                      else "rows swept in chunks, every finished chunk copied to all ranks' Z by the copy engines (peer-to-peer "
                           "cudaMemcpyAsync over NVLink) while the next chunk is swept; one all-reduce of the L1 slots per sweep"
                      if exch == "ce" else "NCCL all-gather of Z per sweep"),
-                     "step": "span tasks with the hub segments + chains beside them, exact L1 change (fused partials / cascade) "
-                            "and device patience of every sweep beside the next sweep's rows (three rotating Z buffers, "
-                            "replayed graphs of 6 sweeps); P frozen",
+                     "step": ("span tasks with the hub segments + chains beside them, exact L1 change (fused partials / cascade) "
+                             "and device patience of every sweep beside the next sweep's rows (three rotating Z buffers, "
+                             "replayed graphs of 6 sweeps); P frozen") if world == 1 else
+                            ("span tasks (a span's rows leave as bulk stores to every rank) with the hub segments + chains beside "
+                             "them; " + ("exact L1 of sweep t (own level-1 nodes, all-reduce of the slots on a second process "
+                                         "group, finish) on a tail stream beside sweep t + 1, three rotating symmetric buffers, "
+                                         "one token all-reduce per sweep orders the ranks" if getattr(runner, "pipelined", False)
+                                         else "exact L1 (own level-1 nodes, all-reduce of the slots, finish) after every sweep")
+                             + "; P frozen"),
                     "plan": {"group_rows": PLAN.group_rows, "spans": PLAN.n_spans, "hub_rows": PLAN.n_hub_rows,
                              "fused_l1": PLAN.fused_l1}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -477,8 +484,7 @@ def run_gpu(args):
         dist.barrier()
         t0 = time.perf_counter()
         r2 = cdist.ShardedSweeper(g, sim, GAMMA, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
-        for i in range(args.steps):
-            r2.sweep(True)
+        r2.sweeps(args.steps)
         Zh = r2.Z_host_slice()           # every rank downloads its own rows: together they are Z
         amount2 = r2.last_amount()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda")
@@ -489,7 +495,7 @@ def run_gpu(args):
         line["e2e"] = {"value": e * args.steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                        "d2h_bytes_per_step": d2h / args.steps, "seconds": secs, "steps": args.steps,
                        "last_amount": amount2,
-                       "note": "ShardedSweeper(graph from host arrays) + steps x sweep(exact L1) + Z_host_slice() on every rank, "
+                       "note": "ShardedSweeper(graph from host arrays) + sweeps(steps) (exact L1 of every sweep) + Z_host_slice() on every rank, "
                                "wall clock, max over ranks; every rank uploads the CSR and its own rows of X (the other rows "
                                "arrive over NVLink) and downloads its own rows of Z; upload, plan build, build_P and the "
                                "download are inside the timed region and amortised over the steps of the call"}
@@ -508,10 +514,7 @@ def run_gpu(args):
         # ---- parity of the sharded path against the single-GPU path, outside every timed region ----
         K = 3
         rc_ = cdist.ShardedSweeper(g, sim, GAMMA, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
-        am = []
-        for i in range(K):
-            rc_.sweep(True)
-            am.append(rc_.last_amount())
+        am = [float(a) for a in rc_.sweeps(K)]
         Zs = rc_.Z[rc_.cur][:n]
         Zb = torch.empty_like(Zs)
         amb = torch.zeros(K, dtype=torch.float64, device="cuda")

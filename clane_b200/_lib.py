@@ -72,6 +72,7 @@ SIGNATURES = {
     "clane_l1_tail_values": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clane_l1_finish_values": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
     "clane_plan_set_peers": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_vp]),
+    "clane_plan_set_peers_third": (C.c_int, [c_vp, c_vp]),
     "clane_plan_set_multicast": (C.c_int, [c_vp, C.c_uint64, C.c_uint64]),
     "clane_plan_trace": (C.c_int, [c_vp, C.c_int, c_vp]),
     "clane_plan_profile": (C.c_int, [c_vp, C.c_int]),

@@ -631,7 +631,7 @@ static int enqueue_sweeps(clane_plan* plan, const SweepArgs& a, float* const* Z,
         p.bulk = 0;
         p.trace = nullptr;
         unsigned long long* tr = (plan->d_trace != nullptr && t < kTraceSweeps) ? plan->d_trace + (size_t)t * kTraceSlots * 2 : nullptr;
-        for (int q = 0; q < 2 && plan->n_peers > 1 && !no_peer_stores; ++q)
+        for (int q = 0; q < 3 && plan->n_peers > 1 && !no_peer_stores; ++q)
             if (plan->peers[q][plan->self_rank] == Zn) {
                 if (plan->mc[q] != nullptr) { p.mc = plan->mc[q]; continue; }   // one multicast store instead of n - 1 unicast ones
                 for (int r = 0; r < plan->n_peers; ++r)
@@ -925,11 +925,20 @@ int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, c
     if (n_peers > 0 && (!h_ptrs_a || !h_ptrs_b)) return CLANE_EINVAL;
     plan->n_peers = n_peers;
     plan->self_rank = self_rank;
+    for (int r = 0; r < 16; ++r) plan->peers[2][r] = nullptr;
     for (int r = 0; r < n_peers; ++r) {
         plan->peers[0][r] = reinterpret_cast<float*>(h_ptrs_a[r]);
         plan->peers[1][r] = reinterpret_cast<float*>(h_ptrs_b[r]);
     }
     for (auto& g : plan->graphs)   // cached sweeps were captured with the old peer set
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    return CLANE_OK;
+}
+
+int clane_plan_set_peers_third(clane_plan* plan, const uint64_t* h_ptrs_c) {
+    if (!plan || !h_ptrs_c || plan->n_peers < 1) return CLANE_EINVAL;
+    for (int r = 0; r < plan->n_peers; ++r) plan->peers[2][r] = reinterpret_cast<float*>(h_ptrs_c[r]);
+    for (auto& g : plan->graphs)
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     return CLANE_OK;
 }

@@ -38,8 +38,8 @@ struct clane_plan {
     std::vector<cudaEvent_t> evs;
     // row-partitioned run: peer Znext buffers for the two Z ping-pong buffers (entry self = own buffer)
     int32_t n_peers = 0, self_rank = 0;
-    float* peers[2][16] = {};
-    float* mc[2] = {nullptr, nullptr};   // multicast (NVLS) addresses of the two buffers, or null
+    float* peers[3][16] = {};            // per Z buffer (two, or three when the caller rotates three): every rank's address
+    float* mc[3] = {nullptr, nullptr, nullptr};   // multicast (NVLS) addresses of the two buffers, or null
     int32_t* d_coloff = nullptr;       // col[e] * ld, rebuilt when the caller's column array changes
     const int32_t* coloff_src = nullptr;
     // CUDA-graph cache of enqueued sweep batches (all streams, all kernels): a propagate() call cycles through a few

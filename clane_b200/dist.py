@@ -92,6 +92,19 @@ def node_range(n_nodes: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_TAIL_GROUP = None
+
+
+def tail_group():
+    """A second process group (its own communicator and stream) for the all-reduce of the L1 slots, so that it can
+    run beside the ordering all-reduce of the next sweep.  Created once per process, by every rank, at the first
+    ShardedSweeper."""
+    global _TAIL_GROUP
+    if _TAIL_GROUP is None:
+        _TAIL_GROUP = dist.new_group()
+    return _TAIL_GROUP
+
+
 def gather_rows(local: torch.Tensor, full: torch.Tensor, group=None) -> None:
     """all-gather equal-length row slices into `full` ([world * per, ld], contiguous)."""
     dist.all_gather_into_tensor(full, local.contiguous(), group=group)
@@ -154,6 +167,15 @@ class ShardedSweeper:
         s = _lib.stream_handle()
         _lib.check(L.clane_edge_rows(self.rowptr.data_ptr(), n, e, self.erow.data_ptr(), s))
         self.tol, self.max_sweeps = tol, max_sweeps
+        # pipelined sweeps (three buffers): the exact-L1 pass of sweep t on its own stream / process group, beside sweep t + 1
+        self.pipelined = len(self.Z) == 3 and self.aligned and self.exchange == "p2p" and self.world > 1
+        if self.pipelined:
+            self.tail_stream = torch.cuda.Stream(device=dev)
+            self.tail_pg = tail_group()
+            self.ring = 16
+            self.amounts_dev = torch.zeros(self.ring, dtype=torch.float32, device=dev)
+            self.amounts_host = torch.zeros(self.ring, dtype=torch.float32).pin_memory()
+        self.launches_last_sweep = 0
         self.timing, self.phase_ms = False, {}     # measurement aid: CUDA-event brackets around the phases of a sweep
         self.build_p()
         _lib.check(L.clane_patience_reset(self.state.data_ptr(), tol, max_sweeps, s))
@@ -166,14 +188,19 @@ class ShardedSweeper:
         if exchange in ("auto", "p2p", "multicast", "ce") and self.world > 1:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                bufs = [symm_mem.empty((npad, ld), dtype=torch.float32, device=self.dev) for _ in range(2)]
-                hdls = [symm_mem.rendezvous(b, dist.group.WORLD) for b in bufs]
-                ptrs = [(ctypes.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in hdls]
+                # "auto" / "p2p": three rotating buffers, so that the L1 reduction of a sweep can run beside the next sweep
+                nbuf = 3 if exchange in ("auto", "p2p") and os.environ.get("CLANE_DIST_PIPELINE", "1") != "0" else 2
+                # one allocation, one rendezvous (the expensive part of the setup): the buffers are slices of it
+                whole = symm_mem.empty((nbuf * npad, ld), dtype=torch.float32, device=self.dev)
+                hdl = symm_mem.rendezvous(whole, dist.group.WORLD)
+                bufs = [whole[i * npad:(i + 1) * npad] for i in range(nbuf)]
+                step = npad * ld * 4
+                ptrs = [(ctypes.c_uint64 * self.world)(*[int(p) + i * step for p in hdl.buffer_ptrs]) for i in range(nbuf)]
                 for b in bufs:
                     b.copy_(self.X)
                 torch.cuda.synchronize()
                 dist.barrier()
-                self.Z, self.symm = bufs, hdls
+                self.Z, self.symm, self._symm_whole = bufs, hdl, whole
                 if exchange == "ce":
                     # Copy-engine exchange (opt-in): the rank's rows are swept in a few chunks; each finished chunk goes
                     # to every peer's Znext with one peer-to-peer cudaMemcpyAsync per peer on copy streams while the next
@@ -184,7 +211,10 @@ class ShardedSweeper:
                     return "ce"
                 _lib.check(L.clane_plan_set_peers(self.plan.handle, self.world, self.rank, ptrs[0], ptrs[1]),
                            "clane_plan_set_peers")
-                mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in hdls]
+                if nbuf == 3:
+                    _lib.check(L.clane_plan_set_peers_third(self.plan.handle, ptrs[2]), "clane_plan_set_peers_third")
+                mc0 = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                mc = [mc0 + i * step if mc0 else 0 for i in range(2)]
                 # opt-in: measured at products shape on 4 GPUs, one multimem.st per row piece (1.82 ms row kernel) is
                 # slower than three unicast stores (1.60 ms) -- every rank ingests the same bytes either way
                 if exchange == "multicast" and all(mc):
@@ -211,7 +241,9 @@ class ShardedSweeper:
             self.chunks.append((_lib.Plan(self.n, self.e, self.d, self.g._rowptr, lo, hi, 0), lo, hi))
             lo = hi
         # views of every peer's two Z buffers (peer-mapped symmetric memory) and a few copy streams
-        self.peer_Z = [[h.get_buffer(r, (npad, ld), torch.float32) for r in range(self.world)] for h in self.symm]
+        nbuf = len(self.Z)
+        whole = [self.symm.get_buffer(r, (nbuf * npad, ld), torch.float32) for r in range(self.world)]
+        self.peer_Z = [[w[i * npad:(i + 1) * npad] for w in whole] for i in range(nbuf)]
         self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(min(self.world - 1, 4))]
 
     def _sweep_chunks(self, zc: torch.Tensor, zn: torch.Tensor, which: int) -> int:
@@ -271,7 +303,8 @@ class ShardedSweeper:
         patience.  Returns the number of kernels this rank launched."""
         L = _lib.lib()
         s = _lib.stream_handle()
-        zc, zn = self.Z[self.cur], self.Z[self.cur ^ 1]
+        nxt = (self.cur + 1) % len(self.Z)
+        zc, zn = self.Z[self.cur], self.Z[nxt]
         marks = [] if self.timing else None
 
         def mark(name):
@@ -282,7 +315,7 @@ class ShardedSweeper:
 
         mark("start")
         if self.chunks:
-            launches = self._sweep_chunks(zc, zn, self.cur ^ 1)
+            launches = self._sweep_chunks(zc, zn, nxt)
         else:
             _lib.check(L.clane_sweep(self.plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
                                      self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s),
@@ -313,7 +346,7 @@ class ShardedSweeper:
             launches += 3
         elif self.exchange in ("p2p", "multicast", "ce"):
             dist.all_reduce(self.sync_token)           # order the ranks between sweeps
-        self.cur ^= 1
+        self.cur = nxt
         if marks is not None:
             marks[-1][1].synchronize()
             for (_, a), (name, b) in zip(marks, marks[1:]):
@@ -324,6 +357,100 @@ class ShardedSweeper:
     def last_amount(self) -> float:
         return float(self.amount.cpu()[0])
 
+    def sweeps(self, max_sweeps: int = 0, until_stop: bool = False) -> list:
+        """Up to `max_sweeps` sweeps (0: unbounded, with `until_stop`), optionally ended by the strict-minimum patience
+        counter of embedder.py:94-108.  Returns the per-sweep L1 amounts (fp32).
+
+        Pipelined over three rotating buffers when the exchange is fused and the slices are node-aligned: sweep t + 1
+        (main stream) needs only the rows of sweep t on every rank -- one all-reduce of a token orders the ranks -- so
+        the exact L1 of sweep t (own level-1 nodes, all-reduce of the slots on a second process group, finish, amount
+        into a pinned ring) runs beside it on the tail stream, and the host reads amount t while sweep t + 1 runs.
+        A sweep overwrites the buffer the L1 pass of two sweeps earlier read: the ordering all-reduce before it is
+        issued only after that pass.  At most ONE speculative sweep runs after the stop, into a buffer that is not the
+        result (the same contract as clane_sweeps on one GPU).  Otherwise: a loop over sweep()."""
+        if not (max_sweeps or until_stop):
+            raise ValueError("sweeps(): give max_sweeps or until_stop")
+        minimum, patience, amounts = np.float32(np.inf), self.tol, []
+        if not self.pipelined or self.timing:
+            while True:
+                self.sweep(True)
+                amount = np.float32(self.amount.cpu().numpy()[0])
+                amounts.append(amount)
+                if until_stop:
+                    if minimum > amount:
+                        patience, minimum = self.tol, amount
+                    else:
+                        patience -= 1
+                    if patience == 0:
+                        return amounts
+                if max_sweeps and len(amounts) >= max_sweeps:
+                    return amounts
+        L = _lib.lib()
+        main, tail = torch.cuda.current_stream(), self.tail_stream
+        s_main, s_tail = main.cuda_stream, tail.cuda_stream
+        start, ring = self.cur, self.ring
+        l1_read, done = {}, {}
+        with_tail_values = (self.hi == self.n and self.lo < self.hi) or (self.n == 0 and self.rank == 0)
+        vals = self.p1[(self.n1 + 2) * 32:]
+
+        def issue(t: int) -> None:
+            c = (start + t) % 3
+            zc, zn = self.Z[c], self.Z[(c + 1) % 3]
+            if t >= 2:
+                main.wait_event(l1_read.pop(t - 2))    # this rank's L1 pass has read the buffer sweep t overwrites everywhere
+            dist.all_reduce(self.sync_token)           # every rank's previous sweep has landed
+            _lib.check(L.clane_sweep(self.plan.handle, self.X.data_ptr(), zc.data_ptr(), zn.data_ptr(), self.rowptr.data_ptr(),
+                                     self.col.data_ptr(), self.w.data_ptr(), ctypes.c_float(self.gamma), 0, 0, 0, 0, s_main),
+                       "clane_sweep")
+            swept = torch.cuda.Event()
+            swept.record(main)
+            with torch.cuda.stream(tail):
+                tail.wait_event(swept)
+                self.p1.zero_()
+                _lib.check(L.clane_l1_partial(self.plan.handle, zn.data_ptr(), zc.data_ptr(), self.nlo, self.nhi,
+                                              self.p1.data_ptr(), s_tail), "clane_l1_partial")
+                if with_tail_values:
+                    _lib.check(L.clane_l1_tail_values(self.plan.handle, zn.data_ptr(), zc.data_ptr(), vals.data_ptr(), s_tail),
+                               "clane_l1_tail_values")
+                ev = torch.cuda.Event()
+                ev.record(tail)
+                l1_read[t] = ev
+                dist.all_reduce(self.p1, op=dist.ReduceOp.SUM, group=self.tail_pg)
+                slot = self.amounts_dev[t % ring:t % ring + 1]
+                _lib.check(L.clane_l1_finish_values(self.plan.handle, self.p1.data_ptr(), vals.data_ptr(), slot.data_ptr(),
+                                                    0, 0, 0, s_tail), "clane_l1_finish_values")
+                self.amounts_host[t % ring:t % ring + 1].copy_(slot, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(tail)
+                done[t] = ev
+
+        limit = max_sweeps if max_sweeps else 1 << 62
+        issue(0)
+        issued = 1
+        while True:
+            if issued < limit:
+                issue(issued)                          # one sweep ahead of the amount the host looks at
+                issued += 1
+            t = len(amounts)
+            done.pop(t).synchronize()
+            amount = np.float32(self.amounts_host[t % ring].item())
+            amounts.append(amount)
+            if until_stop:
+                if minimum > amount:
+                    patience, minimum = self.tol, amount
+                else:
+                    patience -= 1
+                if patience == 0:
+                    break
+            if len(amounts) >= limit:
+                break
+        main.wait_stream(tail)                         # whatever follows on the main stream sees the tails finished
+        k = len(amounts)
+        self.cur = (start + k) % 3
+        self.amount.copy_(self.amounts_dev[(k - 1) % ring:(k - 1) % ring + 1])
+        self.launches_last_sweep = self.plan.launches_per_sweep - 2 + 3 + (1 if with_tail_values else 0)
+        return amounts
+
     # -- the reference's loops, replicated on every rank (never broadcast: the amounts are bit-identical) ----
     def propagate(self, max_sweeps: int = 0) -> list:
         """One Embedder.propagate() call (/root/reference/clane/embedder.py:71-108): build_P once, then sweeps
@@ -331,17 +458,7 @@ class ShardedSweeper:
         runs on the host here (one scalar read per sweep: microseconds against a multi-millisecond sharded
         sweep), on fp32 values, exactly as the reference compares them."""
         self.build_p()
-        minimum, patience, amounts = np.float32(np.inf), self.tol, []
-        while True:
-            self.sweep(True)
-            amount = np.float32(self.amount.cpu().numpy()[0])
-            amounts.append(amount)
-            if minimum > amount:
-                patience, minimum = self.tol, amount
-            else:
-                patience -= 1
-            if patience == 0 or (max_sweeps and len(amounts) >= max_sweeps):
-                return amounts
+        return self.sweeps(max_sweeps, until_stop=True)
 
     def iterate(self, max_outer: int = 0):
         """Embedder.iterate() (embedder.py:56-69).  Returns (sweeps per propagate() call, outer amounts)."""

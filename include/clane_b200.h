@@ -271,6 +271,10 @@ int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, f
  * sweeps (the all-reduce of the L1 slots does).  n_peers = 0 turns it off. */
 int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
                          const uint64_t* h_ptrs_b);
+/* Optional, after clane_plan_set_peers: every rank's address of a THIRD Z buffer.  With three rotating buffers the
+ * caller can run the exact-L1 reduction of sweep t (own rows, all-reduce of the slots, finish) beside sweep t + 1:
+ * the sweep that overwrites a buffer is two sweeps behind the one whose L1 pass reads it (clane_b200/dist.py). */
+int clane_plan_set_peers_third(clane_plan* plan, const uint64_t* h_ptrs_c);
 
 /* Optional, after clane_plan_set_peers: the multicast (NVLS) addresses of the two Z buffers (e.g.
  * torch symmetric memory's multicast_ptr; 0 = none).  The sweep then reaches all ranks with one

@@ -31,6 +31,13 @@ for shape, scale in (("arxiv", 0.3), ("products", 0.01), ("pubmed", 1.0), ("cora
     e.verbose = False
     e.propagate(max_sweeps=4)
     same = np.array_equal(Zs, g1.Z.numpy()) and np.array_equal(np.float32(amounts), e.amounts_per_call[0])
+    # the pipelined call (L1 of sweep t beside sweep t + 1), twice in a row from the same sweeper
+    sw2 = cdist.ShardedSweeper(g, sim, 0.76, exchange=os.environ.get("CLANE_EXCHANGE", "auto"))
+    am2 = sw2.sweeps(3) + sw2.sweeps(1)
+    same = same and np.array_equal(sw2.Z_host().numpy(), Zs) and np.array_equal(np.float32(am2), np.float32(amounts))
+    if rank == 0:
+        print(f"  pipelined={sw2.pipelined}", flush=True)
+    del sw2
     t = torch.tensor([int(same)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
