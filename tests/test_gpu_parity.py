@@ -604,6 +604,16 @@ def test_peer_stores_and_value_finish_single_gpu():
                                  S.col.data_ptr(), S.w.data_ptr(), ctypes.c_float(0.76), 0, 0, 0, 0, s))
         torch.cuda.synchronize()
         assert np.array_equal(full.cpu().numpy()[swept], zn_h[swept])
+        # a third rotating buffer (clane_plan_set_peers_third): a sweep into it reaches its own peer copy, not the others'
+        z3, peer3 = S.Z[1].clone(), torch.full_like(zn, -9.0)
+        third = (ctypes.c_uint64 * 2)(z3.data_ptr(), peer3.data_ptr())
+        _lib.check(L.clane_plan_set_peers_third(plan.handle, third))
+        peer.fill_(-7.0)
+        _lib.check(L.clane_sweep(plan.handle, S.X.data_ptr(), S.Z[0].data_ptr(), z3.data_ptr(), S.rowptr.data_ptr(),
+                                 S.col.data_ptr(), S.w.data_ptr(), ctypes.c_float(0.76), 0, 0, 0, 0, s))
+        torch.cuda.synchronize()
+        assert np.array_equal(peer3.cpu().numpy()[swept], zn_h[swept]) and np.all(peer3.cpu().numpy()[~swept] == -9.0)
+        assert np.all(peer.cpu().numpy() == -7.0)
         # value-based finish == clane_l1_diff
         nodes = ctypes.c_int64()
         _lib.check(L.clane_cascade_shape(n * d, ctypes.byref(nodes), None))
