@@ -247,7 +247,7 @@ int clane_plan_destroy(clane_plan* plan) {
     cudaFree(plan->d_P0); cudaFree(plan->d_coloff); cudaFree(plan->d_trace);
     for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int i = 0; i < 8; ++i) if (plan->ev_prof[i]) cudaEventDestroy(plan->ev_prof[i]);
-    cudaFree(plan->d_p1); cudaFree(plan->d_p2);
+    cudaFree(plan->d_p1); cudaFree(plan->d_p2); cudaFree(plan->d_p0n);
     delete plan;
     return CLANE_OK;
 }

@@ -123,6 +123,152 @@ k_dots(const float* __restrict__ Za, const float* __restrict__ Zb, int ld, int d
 }
 
 // ------------------------------------------------------------------------------------------
+// Dots AND the level-0 partials of the two global norms from ONE set of gathers (d in {32, 64, 128}: a row is whole cascade rows,
+// and a level-0 chunk of the cascade over [E*d] is `chunk_edges` = step * 32 / d whole edges, a power of two <= 32).
+// The norm cascade's lane m adds Z[row][32 s + m]^2 over the chunk's edges in order, s = 0..d/32-1 inside an edge: the two
+// rows of a round of 8 edges are parked once more in a small staging tile (lane = float4 of columns when written, lane =
+// cascade lane when read: conflict-free both ways), and every lane accumulates its cascade lane.  One 32-lane partial
+// per (chunk, norm) goes to P0n[chunk][2][32]; the last, incomplete chunk's partial is the cascade's "leftover rows".
+// Without this the norm cascade gathers the same 2 * E rows a second time (k_cascade_l01<ElemGatherSq2>: the two
+// kernels are L2-bandwidth-bound on 1.2 GB each at arxiv shape).
+// ------------------------------------------------------------------------------------------
+constexpr int kDotNormWarps = 4;
+constexpr size_t kDotNormWarpFloats = (size_t)32 * kDotPitch + 2 * 8 * kDotPitch;
+constexpr size_t kDotNormSmem = kDotNormWarps * kDotNormWarpFloats * sizeof(float);
+
+// the two rows of the 8 edges of round `i` of a tile: independent 128-bit loads (a source row equal to the previous edge's
+// is not loaded again: CSR order -- resolve_round copies it once the loads have landed)
+__device__ __forceinline__ void load_round(const float4* __restrict__ zc, int ra, int rb, int i, int prev_o, float4 (&x)[8],
+                                           float4 (&y)[8], int (&oa)[8]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        oa[u] = __shfl_sync(kFull, ra, (i + u) & 31);
+        const int ob = __shfl_sync(kFull, rb, (i + u) & 31);
+        y[u] = __ldg(zc + ob);
+        if (oa[u] != (u == 0 ? prev_o : oa[u - 1])) x[u] = __ldg(zc + oa[u]);     // uniform branch
+    }
+}
+__device__ __forceinline__ void resolve_round(int prev_o, const float4& xprev, float4 (&x)[8], const int (&oa)[8]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (oa[u] == (u == 0 ? prev_o : oa[u - 1])) x[u] = u == 0 ? xprev : x[u - 1];
+}
+
+__global__ void __launch_bounds__(32 * kDotNormWarps)
+k_dots_norms(const float* __restrict__ Z, int ld, int d, const int32_t* __restrict__ erow, const int32_t* __restrict__ col,
+             int64_t E, int chunk_shift, float* __restrict__ dots, float* __restrict__ P0n) {
+    extern __shared__ __align__(16) float dot_tile[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ta = dot_tile + (size_t)warp * kDotNormWarpFloats;     // products of 32 edges
+    float* sa = ta + 32 * kDotPitch;                              // source rows of a round of 8 edges
+    float* sb = sa + 8 * kDotPitch;                               // destination rows
+    const int64_t ntiles = (E + 31) / 32;
+    const int nseg = d >> 5;
+    const int64_t cmask = ((int64_t)1 << chunk_shift) - 1;
+    const int c = 4 * lane;
+    const bool in = c < ld;
+    const float4* zc = reinterpret_cast<const float4*>(Z) + (in ? c >> 2 : 0);
+    for (int64_t tile = (int64_t)blockIdx.x * kDotNormWarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * kDotNormWarps) {
+        const int64_t e0 = tile * 32;
+        const int cnt = (int)min((int64_t)32, E - e0);
+        int ra = 0, rb = 0;
+        if (lane < cnt) { ra = __ldg(erow + e0 + lane) * (ld >> 2); rb = __ldg(col + e0 + lane) * (ld >> 2); }
+        int prev = -1;
+        float4 xprev = make_float4(0.f, 0.f, 0.f, 0.f);
+        float na = 0.0f, nb = 0.0f;                               // this lane's cascade lane of the open chunk
+        // two register buffers: the loads of round r + 1 are in flight while round r is parked and accumulated
+        float4 x[2][8], y[2][8];
+        int oa[2][8];
+        load_round(zc, ra, rb, 0, -1, x[0], y[0], oa[0]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = r * 8, b = r & 1;
+            if (i < cnt) {                                        // uniform
+                if (r < 3 && i + 8 < cnt) load_round(zc, ra, rb, i + 8, oa[b][7], x[b ^ 1], y[b ^ 1], oa[b ^ 1]);
+                resolve_round(prev, xprev, x[b], oa[b]);
+                prev = oa[b][7];
+                xprev = x[b][7];
+                __syncwarp();                                     // the previous round's staging has been read
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    *reinterpret_cast<float4*>(ta + (i + u) * kDotPitch + c) =
+                        make_float4(fmul(x[b][u].x, y[b][u].x), fmul(x[b][u].y, y[b][u].y), fmul(x[b][u].z, y[b][u].z),
+                                    fmul(x[b][u].w, y[b][u].w));
+                    *reinterpret_cast<float4*>(sa + u * kDotPitch + c) = x[b][u];
+                    *reinterpret_cast<float4*>(sb + u * kDotPitch + c) = y[b][u];
+                }
+                __syncwarp();
+                // all of the round's squares first (independent shared-memory reads), then the two in-order chains
+                float qa[8][4], qb[8][4];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int sg = 0; sg < 4; ++sg) {
+                        const float xa = sg < nseg ? sa[u * kDotPitch + 32 * sg + lane] : 0.0f;
+                        const float xb = sg < nseg ? sb[u * kDotPitch + 32 * sg + lane] : 0.0f;
+                        qa[u][sg] = fmul(xa, xa);
+                        qb[u][sg] = fmul(xb, xb);
+                    }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (i + u < cnt) {                            // uniform
+                        const int64_t e = e0 + i + u;
+                        if ((e & cmask) == 0) { na = 0.0f; nb = 0.0f; }   // a chunk opens
+#pragma unroll
+                        for (int sg = 0; sg < 4; ++sg)
+                            if (sg < nseg) {
+                                na = fadd(na, qa[u][sg]);
+                                nb = fadd(nb, qb[u][sg]);
+                            }
+                        if (((e + 1) & cmask) == 0 || e + 1 == E) {   // the chunk closes (or the array ends inside it)
+                            float* o = P0n + (size_t)(e >> chunk_shift) * 64 + lane;
+                            o[0] = na;
+                            o[32] = nb;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // lane i sums edge i in feature order
+        const float* pp = ta + lane * kDotPitch;
+        float acc = 0.0f;
+        for (int j = 0; j < d; j += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(pp + j);
+            acc = fadd(acc, q.x); acc = fadd(acc, q.y); acc = fadd(acc, q.z); acc = fadd(acc, q.w);
+        }
+        if (lane < cnt) dots[e0 + lane] = acc;
+        __syncwarp();
+    }
+}
+
+// level 1 of the two norms from the chunk partials of k_dots_norms: `step` consecutive chunks per node, in order
+__global__ void __launch_bounds__(256)
+k_level1_from_p0n(CascadeShape sh, const float* __restrict__ P0n, float* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // (node, norm)
+    const int64_t node = w >> 1;
+    const int q = (int)(w & 1);
+    if (node >= sh.n1_nodes) return;
+    const int step = (int)sh.step;
+    const int cnt = node < sh.n1_full ? step : (int)sh.c_rem;
+    const float* src = P0n + ((size_t)node * step * 2 + q) * 32 + lane;
+    float acc = 0.0f;
+    int i = 0;
+    for (; i + 8 <= cnt; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(i + u) * 64);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fadd(acc, v[u]);
+    }
+    for (; i < cnt; ++i) acc = fadd(acc, __ldg(src + (size_t)i * 64));
+    ws[((size_t)node * 2 + q) * 32 + lane] = acc;
+    if (node == sh.n1_nodes - 1 && sh.rem_rows > 0 && sh.r_rem > 0)               // leftover rows = the last, partial chunk
+        ws[(size_t)(sh.n1_nodes + 1) * 64 + q * 32 + lane] = __ldg(P0n + ((size_t)(sh.n1_full * step + sh.c_rem) * 2 + q) * 32 + lane);
+}
+
+// ------------------------------------------------------------------------------------------
 // Sleef_expf_u10 (what ATen's vectorised softmax calls)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pow2if(int q) { return __int_as_float((q + 127) << 23); }
@@ -400,6 +546,37 @@ int clane_scores_cosine(clane_plan* plan, const float* d_Z, const int32_t* d_ero
     if (!plan || !d_Z || !d_erow || !d_col || !d_dots) return CLANE_EINVAL;
     if (edge_lo < 0 || edge_hi > plan->e || edge_lo > edge_hi) return CLANE_EINVAL;
     cudaStream_t st = (cudaStream_t)s;
+    // One pass for the dots and the norms' level-0 partials when a chunk of the cascade is a few whole edges: OPT-IN
+    // (CLANE_FUSED_NORMS=1).  Measured at arxiv shape: build_P 0.336 ms against 0.304 ms for the two kernels side by side --
+    // the tile + staging leave 8 warps per SM, and the in-order chains of phases B and C then stall the issue slots
+    // (profiles/r02_notes.md).  Bit-exact either way (tests/test_gpu_parity.py::test_dots_and_norms_from_one_pass).
+    const char* fuse_env = getenv("CLANE_FUSED_NORMS");
+    if (d_norms2 != nullptr && edge_lo == 0 && edge_hi == plan->e && plan->e > 0 && fuse_env && atoi(fuse_env) != 0 &&
+        (plan->d == 32 || plan->d == 64 || plan->d == 128)) {
+        const CascadeShape sh = cascade_shape(plan->e * (int64_t)plan->d);
+        const int64_t chunk_edges = sh.step * 32 / plan->d;
+        if (chunk_edges >= 1 && chunk_edges <= 32) {
+            int shift = 0;
+            while (((int64_t)1 << shift) < chunk_edges) ++shift;
+            const size_t need = (size_t)((plan->e >> shift) + 1) * 64;
+            if (plan->p0n_floats < need) {
+                if (plan->d_p0n) CLANE_CUDA(cudaFree(plan->d_p0n));
+                plan->d_p0n = nullptr; plan->p0n_floats = 0;
+                CLANE_CUDA(cudaMalloc(&plan->d_p0n, need * sizeof(float)));
+                plan->p0n_floats = need;
+            }
+            const int64_t ntiles = (plan->e + 31) / 32;
+            const unsigned grid = (unsigned)std::min<int64_t>((ntiles + kDotNormWarps - 1) / kDotNormWarps, 148 * 16);
+            k_dots_norms<<<grid, 32 * kDotNormWarps, kDotNormSmem, st>>>(d_Z, plan->ld, plan->d, d_erow, d_col, plan->e, shift, d_dots,
+                                                                    plan->d_p0n);
+            CLANE_LAUNCH_CHECK();
+            const int64_t warps = sh.n1_nodes * 2;
+            k_level1_from_p0n<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(sh, plan->d_p0n, plan->d_p1);
+            CLANE_LAUNCH_CHECK();
+            ElemGatherSq2 el{d_Z, d_erow, d_col, plan->d, plan->ld, plan->e};
+            return cascade_launch_finish(el, plan->e * (int64_t)plan->d, plan->d_p1, plan->d_p2, d_norms2, nullptr, nullptr, 0, nullptr, st);
+        }
+    }
     // the dots and the norm cascade are independent and both latency-bound at partial occupancy: with a schedule plan (it
     // owns side streams) the dots run on a side stream beside the cascade on the caller's
     cudaStream_t caller = st;
@@ -1029,6 +1206,7 @@ int clane_internal_prepare_kernels(void) {
     CLANE_CUDA(cudaFuncSetAttribute(k_hub_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeavySmemBytes));
     CLANE_CUDA(cudaFuncSetAttribute(k_dots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<false>()));
     CLANE_CUDA(cudaFuncSetAttribute(k_dots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dot_smem<true>()));
+    CLANE_CUDA(cudaFuncSetAttribute(k_dots_norms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDotNormSmem));
     if (const char* v = getenv("CLANE_ROW_CARVEOUT"))    // timing experiments: shared-memory carveout (percent) of the row kernel
         CLANE_CUDA(cudaFuncSetAttribute(k_sweep_rows<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)));
     // the cascade level-0/1 kernel needs step*NQ*128 bytes (<= 32 KB for step = 128, NQ = 2)

@@ -64,6 +64,8 @@ struct clane_plan {
     // cascade scratch: level-1 slots and level-2 slots, sized for max(n*d x1, e*d x2)
     float* d_p1 = nullptr;
     float* d_p2 = nullptr;
+    float* d_p0n = nullptr;     // build_P: level-0 partials of the two norms from k_dots_norms, [chunk][2][32] (allocated on first use)
+    size_t p0n_floats = 0;
     size_t p1_floats = 0, p2_floats = 0;
 };
 

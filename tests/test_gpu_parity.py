@@ -524,6 +524,37 @@ def test_norms_reduced_by_node_range_equal_whole():
         assert np.array_equal(w1.cpu().numpy(), O.build_p(X, rowptr, col))
 
 
+@pytest.mark.parametrize("n,e,d", [(50, 3, 128), (50, 33, 128), (900, 4001, 128), (40000, 270003, 128), (700, 3001, 64),
+                                   (30000, 530001, 64), (900, 5003, 32), (60000, 1050007, 32)])
+def test_dots_and_norms_from_one_pass(n, e, d, monkeypatch):
+    """k_dots_norms (opt-in, CLANE_FUSED_NORMS=1; d = 32 / 64 / 128: the norms' level-0 partials come from the gathers
+    of the dots) against the oracle and against the default two-kernel form, at every chunk size (4 / 8 / 16 / 32 edges
+    per level-0 chunk), with partial last chunks and partial tiles."""
+    monkeypatch.setenv("CLANE_FUSED_NORMS", "1")
+    L = _lib.lib()
+    rng = np.random.default_rng(n + e + d)
+    src, dst = synth.make_edges(n, e, "powerlaw" if n >= 900 else "uniform", rng)
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    g = Graph.from_arrays(n, src, dst, X)
+    S = g._device_state()
+    assert S.e == e
+    s = _lib.stream_handle()
+    dots = torch.zeros(S.e, device="cuda")
+    norms = torch.zeros(2, device="cuda")
+    _lib.check(L.clane_scores_cosine(S.plan.handle, S.Z[0].data_ptr(), S.erow.data_ptr(), S.col.data_ptr(), 0, S.e,
+                                     dots.data_ptr(), norms.data_ptr(), s))
+    O.set_threads(O.max_threads())
+    rowptr, col = O.csr_from_edges(src, dst, n)
+    od, s1, s2 = O.scores_raw(X, rowptr, col)
+    assert np.array_equal(dots.cpu().numpy(), od)
+    assert norms.cpu().numpy().tolist() == [s1, s2]
+    monkeypatch.setenv("CLANE_FUSED_NORMS", "0")
+    dots2, norms2 = torch.zeros_like(dots), torch.zeros_like(norms)
+    _lib.check(L.clane_scores_cosine(S.plan.handle, S.Z[0].data_ptr(), S.erow.data_ptr(), S.col.data_ptr(), 0, S.e,
+                                     dots2.data_ptr(), norms2.data_ptr(), s))
+    assert torch.equal(dots, dots2) and torch.equal(norms, norms2)
+
+
 @pytest.mark.parametrize("n,d", [(1000, 128), (300, 64), (4097, 32), (777, 96)])
 def test_asymmetric_scorer_fused_build_p(n, d):
     """AsymmertricSimilarity through Graph.build_P: the tcgen05 projection + per-edge dots + row softmax against the
