@@ -485,6 +485,8 @@ cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
 using namespace clane;
 
 constexpr int kSweepBatch = 6;     // sweeps per replayed graph of clane_sweeps (a multiple of the three Z buffers)
+constexpr int kWhileBatch = 6;     // sweeps per iteration of the conditional-WHILE body (until_stop); CLANE_WHILE_BATCH = 12 / 24
+                                   // measured no better (arxiv shape, time to converge 0.105 / 0.107 / 0.115 s)
 // The L1 tail of sweep t runs while the span tasks of sweep t + 1 fill every SM (12 CTAs x 64 threads x 80 registers leave
 // 4096 registers per SM): 64-thread CTAs of <= 64 registers are what still fits beside them.
 constexpr int kTailThreads = 64;
@@ -1058,7 +1060,13 @@ int clane_sweeps(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t
     if (until_stop) {
         static const bool env_force = getenv("CLANE_FORCE_GRAPHS") != nullptr;
         if (!plan->while_ok || (plan->prefer_direct && !env_force)) return CLANE_EUNSUPPORTED;
-        rc = launch_sweeps(plan, a, d_Z3, 3, cur, kSweepBatch, 1, st);
+        // sweeps per iteration of the WHILE body (a multiple of 3: the body always starts at buffer `cur`)
+        static const int body = [] {
+            const char* v = getenv("CLANE_WHILE_BATCH");
+            const int b = v ? atoi(v) : kWhileBatch;
+            return std::max(3, b - b % 3);
+        }();
+        rc = launch_sweeps(plan, a, d_Z3, 3, cur, body, 1, st);
         return rc == CLANE_EINVAL ? CLANE_EUNSUPPORTED : rc;
     }
     // whole batches replay one cached graph per starting buffer (kSweepBatch is a multiple of 3: the rotation closes)
