@@ -188,6 +188,7 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
     struct Span { int32_t row, nrows, direct; int64_t work; };
     std::vector<Span> spans;
     std::vector<int32_t> fix, hub_rows;
+    spans.reserve((size_t)n_groups + 16);
     for (int32_t g = 0; g < n_groups; ++g) {
         const int32_t r0 = row_lo + g * G, r1 = std::min(r0 + G, row_hi);
         bool has_hub = false;
@@ -216,7 +217,20 @@ int clane_group_schedule(const int32_t* h_rowptr, int32_t n, int32_t d, int32_t 
         else if (fuse && (made > 0 || has_hub)) fix.push_back(g);
         // groups of sinks only are never updated (embedder.py:88-89): no span, partial stays +0
     }
-    std::stable_sort(spans.begin(), spans.end(), [](const Span& x, const Span& y) { return x.work > y.work; });
+    {   // spans by edge count, descending, ties in row order: a stable counting sort (the keys are <= a hub row's length)
+        int64_t maxw = 0;
+        for (const Span& sp : spans) maxw = std::max(maxw, sp.work);
+        if (maxw <= (int64_t)1 << 22) {
+            std::vector<uint32_t> first((size_t)maxw + 2, 0);
+            for (const Span& sp : spans) first[(size_t)(maxw - sp.work) + 1]++;
+            for (size_t i = 1; i < first.size(); ++i) first[i] += first[i - 1];
+            std::vector<Span> sorted(spans.size());
+            for (const Span& sp : spans) sorted[first[(size_t)(maxw - sp.work)]++] = sp;
+            spans.swap(sorted);
+        } else {
+            std::stable_sort(spans.begin(), spans.end(), [](const Span& x, const Span& y) { return x.work > y.work; });
+        }
+    }
     auto by_degree_desc = [&](int32_t x, int32_t y) {
         const int32_t kx = h_rowptr[x + 1] - h_rowptr[x], ky = h_rowptr[y + 1] - h_rowptr[y];
         return kx != ky ? kx > ky : x < y;
@@ -487,6 +501,10 @@ static int copy_rows_h2d(clane_session* s, float* d_dst, const float* h_src) {
 }
 
 static int copy_rows_d2h(clane_session* s, float* h_dst, const float* d_src) {
+    if (s->ld == s->d) {
+        CLANE_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)s->n * s->d * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        return CLANE_OK;
+    }
     CLANE_CUDA(cudaMemcpy2DAsync(h_dst, (size_t)s->d * sizeof(float), d_src, (size_t)s->ld * sizeof(float),
                                  (size_t)s->d * sizeof(float), (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
     return CLANE_OK;
@@ -608,7 +626,14 @@ int clane_session_propagate(clane_session* s, float gamma, int32_t tol, int32_t 
     const int start = s->cur;
     // one graph launch for the whole call (conditional WHILE over batches of sweeps); without conditional nodes:
     // batches of 12 sweeps (whole buffer rotations), one host synchronisation per batch
-    rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 0, 1, s->state, s->log, s->log_cap, s->stream);
+    // ... except for a short bounded call (max_sweeps <= 24): its sweeps are enqueued directly, once -- no graph to build,
+    // the device-side counter turns whatever follows the stop into no-ops
+    static const bool no_direct = getenv("CLANE_NO_DIRECT") != nullptr;     // measurement aid
+    if (max_sweeps > 0 && max_sweeps <= 24 && !no_direct)
+        rc = clane_internal_sweeps_direct(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, max_sweeps, s->state, s->log,
+                                          s->log_cap, s->stream);
+    else
+        rc = clane_sweeps(s->plan, s->X, s->Z, start, s->rowptr, s->col, s->w, gamma, 0, 1, s->state, s->log, s->log_cap, s->stream);
     if (rc != CLANE_OK && rc != CLANE_EUNSUPPORTED) return rc;
     const bool looped = rc == CLANE_OK;
     for (;;) {

@@ -1081,6 +1081,22 @@ int clane_sweeps(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t
     return rc;
 }
 
+// A bounded, short run of sweeps enqueued directly (no graph): what a propagate() of a few sweeps wants -- building and
+// instantiating a graph costs ~1.2 ms at arxiv shape, the direct launches of 20 sweeps stay ahead of the device.  Same
+// pipeline and the same device-side patience as clane_sweeps (sweeps after the stop are no-ops).  Library-internal
+// (the session API); not part of include/clane_b200.h.
+int clane_internal_sweeps_direct(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t cur, const int32_t* d_rowptr,
+                                 const int32_t* d_col, const float* d_w, float gamma, int32_t n_sweeps, clane_patience* d_state,
+                                 float* d_amounts_log, int32_t log_cap, clane_stream_t s) {
+    if (!plan || !plan->has_schedule || !d_X || !d_Z3 || !d_rowptr || !d_state || cur < 0 || cur > 2 || n_sweeps < 0)
+        return CLANE_EINVAL;
+    cudaStream_t st = (cudaStream_t)s;
+    int rc = ensure_coloff(plan, d_col, st);
+    if (rc != CLANE_OK) return rc;
+    SweepArgs a{d_X, d_rowptr, d_col, d_w, gamma, nullptr, d_state, d_amounts_log, log_cap};
+    return enqueue_sweeps(plan, a, d_Z3, 3, cur, n_sweeps, st);
+}
+
 int clane_l1_diff(clane_plan* plan, const float* d_Za, const float* d_Zb, float* d_out, clane_stream_t s) {
     if (!plan || !d_Za || !d_Zb || !d_out) return CLANE_EINVAL;
     ElemAbsDiff el{d_Za, d_Zb, plan->d, plan->ld};

@@ -72,3 +72,7 @@ struct clane_plan {
 constexpr int kTraceSweeps = 64, kTraceSlots = 6;   // slots: segments, long chains, short chains, spans, L1 tail, -
 
 extern "C" int clane_internal_prepare_kernels(void);
+extern "C" int clane_internal_sweeps_direct(clane_plan* plan, const float* d_X, float* const* d_Z3, int32_t cur,
+                                            const int32_t* d_rowptr, const int32_t* d_col, const float* d_w, float gamma,
+                                            int32_t n_sweeps, clane_patience* d_state, float* d_amounts_log, int32_t log_cap,
+                                            clane_stream_t s);
