@@ -180,6 +180,7 @@ def test_group_schedule_degree_sorted_row_blocks():
         kk = np.where(k > hub, 0, k)                  # hub rows are not part of a span's work
         work = np.array([kk[r:r + m].sum() for r, m in zip(sr, nrows)])
         assert np.all(work > 0) and np.all(np.diff(work) <= 0)                        # longest first, no empty span
+        assert np.all(np.diff(sr)[np.diff(work) == 0] > 0)                            # equal spans stay in row order (stable)
         covered = np.zeros(n, bool)
         for r, m, w_, dr in zip(sr, nrows, work, direct):
             assert (r - lo) // G == (r + m - 1 - lo) // G                              # a span stays inside one group
