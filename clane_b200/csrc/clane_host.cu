@@ -286,6 +286,10 @@ int build_program(const int32_t* h_rowptr, int fuse, const int32_t* srow, const 
     using namespace clane;
     try {
         blk0.assign((size_t)std::max(n_hrows, 1), 0);
+        size_t n_seg = 0;
+        for (int32_t h = 0; h < n_hrows; ++h)
+            n_seg += (size_t)((h_rowptr[hrows[h] + 1] - h_rowptr[hrows[h]]) / 8 + kSegEdges / 8 - 1) / (kSegEdges / 8);
+        tasks.reserve(tasks.size() + n_seg + (size_t)n_spans);
         int64_t blocks = 0;
         for (int32_t h = 0; h < n_hrows; ++h) {
             const int32_t v = hrows[h], a = h_rowptr[v], nblk = (h_rowptr[v + 1] - a) / 8;
