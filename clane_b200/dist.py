@@ -2,11 +2,14 @@
 
 Nodes are partitioned by contiguous id range; every rank keeps the full CSR and a full replica
 of Z (out-neighbours span all ranks) and sweeps its own rows.  The exchange is fused into the
-sweep: the two Z ping-pong buffers live in peer-mapped symmetric memory, and the sweep kernel
-stores every finished row of Znext to ALL ranks' buffers (clane_plan_set_peers) -- NVLink writes
-issued row by row from inside the kernel, overlapping the gathers, no collective on the data
-path.  Where symmetric memory is unavailable the slices are exchanged with one NCCL all-gather
-per sweep instead.  The three global scalars stay bit-identical on every rank:
+sweep: the Z buffers (three, rotating; slices of one peer-mapped symmetric allocation) are known
+to the sweep kernel on every rank (clane_plan_set_peers / _third), which stores a span's finished
+rows of Znext to ALL ranks' buffers -- one bulk store per destination, issued from inside the
+kernel, overlapping the gathers, no collective on the data path.  ShardedSweeper.sweeps() pipelines
+the rest: a token all-reduce orders the ranks between sweeps on the main stream, the exact L1 of
+sweep t runs on a tail stream and a second process group beside sweep t + 1.  Where symmetric
+memory is unavailable the slices are exchanged with one NCCL all-gather per sweep instead.  The
+three global scalars stay bit-identical on every rank:
 
   * L1 change per sweep (embedder.py:94): the ATen cascade's level-1 nodes are independent, so
     each rank reduces the nodes of its OWN rows right after its sweep, from local data only (the
@@ -14,9 +17,9 @@ per sweep instead.  The three global scalars stay bit-identical on every rank:
     ranks); the ranks all-reduce(SUM) the node slots -- every slot is written by exactly one rank
     and is +0 elsewhere, so the sum is exact -- together with the <= 31 trailing element values,
     and each rank finishes levels 2-3 and the patience state machine itself
-    (clane_l1_finish_values).  That all-reduce is also the only inter-rank ordering a sweep
-    needs: once it completes on a rank, every rank has finished reading Zcur and its peer
-    stores of Znext have landed.  Patience is replicated, never broadcast.  When the shape
+    (clane_l1_finish_values).  In the synchronous form (sweep()) that all-reduce is also the only
+    inter-rank ordering a sweep needs: once it completes on a rank, every rank has finished
+    reading Zcur and its peer stores of Znext have landed.  Patience is replicated, never broadcast.  When the shape
     cannot be cut that way (d odd, tiny n) the ranks first synchronise, then reduce balanced
     node ranges of the full array.
   * the two Frobenius norms of build_P (similarity.py:37) are cascade sums over the flattened [E*d] gathered
@@ -181,7 +184,7 @@ class ShardedSweeper:
         _lib.check(L.clane_patience_reset(self.state.data_ptr(), tol, max_sweeps, s))
 
     def _alloc_z(self, npad: int, ld: int, exchange: str) -> str:
-        """The two Z buffers: peer-mapped symmetric memory (exchange fused into the sweep kernel) when
+        """The Z buffers (three for the pipelined fused exchange, else two): peer-mapped symmetric memory (exchange fused into the sweep kernel) when
         available, plain device memory + NCCL all-gather otherwise."""
         L = _lib.lib()
         self.symm = None
@@ -240,7 +243,7 @@ class ShardedSweeper:
             hi = min(lo + step, self.hi)
             self.chunks.append((_lib.Plan(self.n, self.e, self.d, self.g._rowptr, lo, hi, 0), lo, hi))
             lo = hi
-        # views of every peer's two Z buffers (peer-mapped symmetric memory) and a few copy streams
+        # views of every peer's Z buffers (peer-mapped symmetric memory) and a few copy streams
         nbuf = len(self.Z)
         whole = [self.symm.get_buffer(r, (nbuf * npad, ld), torch.float32) for r in range(self.world)]
         self.peer_Z = [[w[i * npad:(i + 1) * npad] for w in whole] for i in range(nbuf)]

@@ -264,10 +264,10 @@ int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, f
                            clane_patience* d_state, float* d_amounts_log, int32_t log_cap, clane_stream_t s);
 
 /* Row-partitioned run on n_peers GPUs of one NVLink domain: the device addresses
- * of every rank's two Z ping-pong buffers (peer-mapped, e.g. CUDA VMM / torch symmetric memory;
+ * of every rank's two Z buffers (peer-mapped, e.g. CUDA VMM / torch symmetric memory;
  * entry self_rank = this rank's own buffers).  From then on clane_sweep stores every finished
- * row of Znext to all ranks' buffers from inside the sweep kernel -- the exchange overlaps the
- * sweep row by row and needs no collective; the caller only has to order the ranks between
+ * row of Znext to all ranks' buffers from inside the sweep kernel (rows of one span as one bulk store per
+ * rank when a row fits one warp pass) -- the exchange overlaps the sweep and needs no collective; the caller only has to order the ranks between
  * sweeps (the all-reduce of the L1 slots does).  n_peers = 0 turns it off. */
 int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
                          const uint64_t* h_ptrs_b);
