@@ -266,9 +266,10 @@ int clane_l1_finish_values(clane_plan* plan, float* d_p1, const float* d_vals, f
 /* Row-partitioned run on n_peers GPUs of one NVLink domain: the device addresses
  * of every rank's two Z buffers (peer-mapped, e.g. CUDA VMM / torch symmetric memory;
  * entry self_rank = this rank's own buffers).  From then on clane_sweep stores every finished
- * row of Znext to all ranks' buffers from inside the sweep kernel (rows of one span as one bulk store per
- * rank when a row fits one warp pass) -- the exchange overlaps the sweep and needs no collective; the caller only has to order the ranks between
- * sweeps (the all-reduce of the L1 slots does).  n_peers = 0 turns it off. */
+ * row of Znext to all ranks' buffers from inside the sweep kernel (rows of one span as one bulk
+ * store per rank when a row fits one warp pass) -- the exchange overlaps the sweep and needs no
+ * collective; the caller only has to order the ranks between sweeps (an all-reduce of the L1
+ * slots, or of a token, does).  n_peers = 0 turns it off. */
 int clane_plan_set_peers(clane_plan* plan, int32_t n_peers, int32_t self_rank, const uint64_t* h_ptrs_a,
                          const uint64_t* h_ptrs_b);
 /* Optional, after clane_plan_set_peers: every rank's address of a THIRD Z buffer.  With three rotating buffers the
