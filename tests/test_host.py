@@ -534,3 +534,27 @@ def test_csr_build_is_thread_count_independent():
     finally:
         if have:
             os.sched_setaffinity(0, have)
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys, same metric / unit / config object as the GPU arm; ranks other than 0 print nothing and exit 0."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--workload", "cora", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().split("\n") if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "edges_per_sec_per_sweep" and j["unit"] == "edges/s"
+    assert j["higher_is_better"] is True and j["steps"] == 2 and j["warmup"] == 1 and j["value"] > 0
+    assert j["config"]["workload"].startswith("cora") and j["config"]["nodes"] == 2708
+    assert j["cpu_baseline"]["kind"] in ("port", "reference") and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import os
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
